@@ -1,0 +1,104 @@
+"""ctypes binding of the C-ABI in include/disco_b200.h.  No CPU fallback: a missing library is an error."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdisco_b200.so")
+
+PREC_FP16 = 0
+PREC_BF16X3 = 1
+OUT_ACT = 0
+OUT_F32 = 1
+
+
+class DiscoError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    """struct disco_conv_desc (include/disco_b200.h)."""
+    _fields_ = [
+        ("src", C.c_void_p * 2),
+        ("src_lo_off", C.c_longlong * 2),
+        ("src_c", C.c_int * 2),
+        ("src_up", C.c_int * 2),
+        ("n", C.c_int), ("h_in", C.c_int), ("w_in", C.c_int),
+        ("h_out", C.c_int), ("w_out", C.c_int),
+        ("stride", C.c_int), ("taps", C.c_int), ("c_blk", C.c_int),
+        ("c_out", C.c_int), ("block_n", C.c_int),
+        ("wpack", C.c_void_p), ("wref", C.c_void_p), ("bias", C.c_void_p),
+        ("relu", C.c_int), ("precision", C.c_int),
+        ("out_mode", C.c_int),
+        ("out", C.c_void_p * 2),
+        ("out_lo_off", C.c_longlong),
+        ("out_split", C.c_int),
+    ]
+
+
+class FusionDesc(C.Structure):
+    """struct disco_fusion_desc (include/disco_b200.h)."""
+    _fields_ = [
+        ("feat_hi", C.c_void_p), ("feat_lo_off", C.c_longlong), ("precision", C.c_int),
+        ("en", C.c_void_p), ("hid", C.c_int),
+        ("w2", C.c_void_p), ("b2", C.c_void_p),
+        ("w3", C.c_void_p), ("b3", C.c_void_p),
+        ("w4", C.c_void_p), ("b4", C.c_void_p),
+        ("trans", C.c_void_p), ("num_agent", C.c_void_p),
+        ("B", C.c_int), ("A", C.c_int), ("h", C.c_int), ("w", C.c_int), ("C", C.c_int),
+        ("only_v2i", C.c_int), ("trans_scale", C.c_float),
+        ("out_hi", C.c_void_p), ("out_lo_off", C.c_longlong),
+        ("weights", C.c_void_p),
+    ]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "disco_version": (C.c_int, []),
+    "disco_last_error": (C.c_int, [C.c_char_p, C.c_size_t]),
+    "disco_device_check": (C.c_int, []),
+    "disco_conv_forward": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    "disco_conv_reference": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    "disco_conv_smem_bytes": (C.c_int, [C.POINTER(ConvDesc)]),
+    "disco_bev_pack": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
+    "disco_act_unpack_nchw": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p]),
+    "disco_voxelize_occupy": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                        C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]),
+    "disco_bev_scatter": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_int,
+                                    C.c_int, C.c_void_p]),
+    "disco_fusion_forward": (C.c_int, [C.POINTER(FusionDesc), C.c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libdisco_b200.so (built by `python -m disconet_b200.build`).  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DiscoError(
+            f"{LIB_PATH} is missing: build it with `python -m disconet_b200.build` "
+            "(or __graft_entry__.build()).  disconet_b200 has no CPU / PyTorch fallback path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)  # AttributeError if an exported symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    buf = C.create_string_buffer(512)
+    load().disco_last_error(buf, 512)
+    return buf.value.decode(errors="replace")
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc < 0:
+        raise DiscoError(f"{what or 'libdisco_b200'} failed (code {rc}): {last_error()}")

@@ -1,0 +1,83 @@
+// C-ABI of libdisco_b200.so (declared in include/disco_b200.h).  Plain pointers and sizes only; every
+// entry point returns 0 or a negative DISCO_E* code and never throws / aborts; text via
+// disco_last_error().  All launches go to the caller's stream, no internal synchronisation.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+#include "conv.h"
+#include "ops.h"
+
+static thread_local char g_err[512] = "";
+
+void disco_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" {
+
+int disco_version(void) { return 100; }
+
+int disco_last_error(char* buf, size_t len) {
+    if (!buf || len == 0) return DISCO_EINVAL;
+    strncpy(buf, g_err, len - 1);
+    buf[len - 1] = 0;
+    return DISCO_OK;
+}
+
+// Fails unless the current device is compute capability 10.x (the only target this library is built for).
+int disco_device_check(void) {
+    int dev = 0;
+    DISCO_CHECK_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    DISCO_CHECK_CUDA(cudaGetDeviceProperties(&p, dev));
+    if (p.major != 10) {
+        disco_set_error("device %d is sm_%d%d; libdisco_b200 contains sm_100a code only", dev, p.major, p.minor);
+        return DISCO_EARCH;
+    }
+    return DISCO_OK;
+}
+
+int disco_conv_forward(const disco_conv_desc* d, void* stream) {
+    if (!d) { disco_set_error("null descriptor"); return DISCO_EINVAL; }
+    return disco_conv_tc_launch(d, stream);
+}
+int disco_conv_reference(const disco_conv_desc* d, void* stream) {
+    if (!d) { disco_set_error("null descriptor"); return DISCO_EINVAL; }
+    return disco_conv_ref_launch(d, stream);
+}
+int disco_conv_smem_bytes(const disco_conv_desc* d) {
+    if (!d) { disco_set_error("null descriptor"); return DISCO_EINVAL; }
+    return disco_conv_tc_smem_bytes(d);
+}
+
+int disco_bev_pack(const float* bev, long long n_pix, int z, void* out_hi, long long out_lo_off, int precision,
+                   void* stream) {
+    return disco_bev_pack_launch(bev, n_pix, z, out_hi, out_lo_off, precision, stream);
+}
+
+int disco_act_unpack_nchw(const void* act_hi, long long lo_off, int precision, int n, int h, int w, int c,
+                          float* out_nchw, void* stream) {
+    return disco_act_unpack_nchw_launch(act_hi, lo_off, precision, n, h, w, c, out_nchw, stream);
+}
+
+int disco_voxelize_occupy(const float* points, int n_points, int point_stride, const double* extents,
+                          const double* voxel_size, const int* dims, unsigned int* bitmap, int* voxel_indices,
+                          int* n_voxels, float* dense, void* stream) {
+    return disco_voxelize_launch(points, n_points, point_stride, extents, voxel_size, dims, bitmap, voxel_indices,
+                                 n_voxels, dense, stream);
+}
+
+int disco_bev_scatter(const int* voxel_indices, int n_voxels, const int* dims, float* bev_f32, void* act_hi,
+                      int act_c, int precision, void* stream) {
+    return disco_bev_scatter_launch(voxel_indices, n_voxels, dims, bev_f32, act_hi, act_c, precision, stream);
+}
+
+int disco_fusion_forward(const disco_fusion_desc* d, void* stream) {
+    if (!d) { disco_set_error("null descriptor"); return DISCO_EINVAL; }
+    return disco_fusion_launch(d, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,44 @@
+// Convolution descriptor shared by the tcgen05 kernel (conv_tc.cu), the CUDA-core validator
+// (conv_ref.cu) and the C-ABI (capi.cu).  Mirrors `disco_conv_desc` in include/disco_b200.h.
+#pragma once
+#include <stdint.h>
+
+// Activations are NHWC 16-bit tensors.  precision:
+//   DISCO_PREC_FP16   : one fp16 tensor, one tensor-core pass
+//   DISCO_PREC_BF16X3 : value = hi + lo (two bf16 tensors, `lo` at element offset lo_off from `hi`),
+//                       three tensor-core passes (hi*Whi + lo*Whi + hi*Wlo), fp32 accumulate
+#define DISCO_PREC_FP16 0
+#define DISCO_PREC_BF16X3 1
+
+#define DISCO_OUT_ACT 0   // 16-bit activation tensor (hi [+ lo]) NHWC, channel stride out_cstride[0]
+#define DISCO_OUT_F32 1   // fp32 NHWC; optionally split in two tensors at channel `out_split`
+
+struct disco_conv_desc {
+    // ---- input: channel-concatenation of up to two NHWC sources --------------------------------
+    const void* src[2];      // hi tensors (16-bit elements)
+    long long src_lo_off[2]; // elements from hi to lo tensor (BF16X3 only)
+    int src_c[2];            // channels per source (multiple of 16; second may be 0)
+    int src_up[2];           // 1: source is (H_in/2 x W_in/2), nearest-upsampled x2 on the fly
+    int n, h_in, w_in;       // logical (post-upsample) conv input size
+    int h_out, w_out;
+    int stride;              // 1 | 2
+    int taps;                // 9 (3x3, pad 1) | 1 (1x1, pad 0, stride 1)
+    int c_blk;               // channels per K stage: 16 | 32 | 64; divides src_c[0] and src_c[1]
+    // ---- weights ---------------------------------------------------------------------------------
+    int c_out;               // real output channels
+    int block_n;             // N tile (multiple of 16, <= 256); weights are padded to n_tiles*block_n rows
+    const void* wpack;       // [n_tile][c_block][tap][part][c_blk/8][block_n][8] 16-bit (part: hi, lo)
+    const float* wref;       // validator only: [c_out][tap][c_in] fp32 (BN already folded)
+    const float* bias;       // [n_tiles*block_n] fp32 (BN folded; zero padded)
+    int relu;
+    int precision;           // DISCO_PREC_*
+    // ---- output ----------------------------------------------------------------------------------
+    int out_mode;            // DISCO_OUT_*
+    void* out[2];            // OUT_ACT: out[0] = hi; OUT_F32: out[0] (channels < out_split), out[1] (rest)
+    long long out_lo_off;    // OUT_ACT + BF16X3: elements from hi to lo
+    int out_split;           // OUT_F32: first channel of out[1]; == c_out when out[1] unused
+};
+
+int disco_conv_tc_launch(const disco_conv_desc* d, void* stream);
+int disco_conv_ref_launch(const disco_conv_desc* d, void* stream);
+int disco_conv_tc_smem_bytes(const disco_conv_desc* d);

@@ -1,0 +1,223 @@
+// DiscoGraph fusion block as ONE kernel (reference: ~560 launches of a Python triple loop per scene).
+//
+// For every scene b, ego agent i and BEV cell (y,x) of the collaboration layer:
+//   * neighbour j's feature map is warped into the ego frame (affine_grid + bilinear grid_sample with
+//     zeros padding, align_corners=False -- DetModelBase.py:139-169).  The reference flips H before and
+//     after the warp (DetModelBase.py:67,91); here the flip is folded into the row index.
+//   * PixelWeightedFusionSoftmax (DiscoNet.py:132-155) scores cat[ego, neighbour]: the 2C->128 1x1 conv
+//     is linear and bias-free on the neighbour half, so it commutes with the bilinear warp; it is
+//     applied once per agent on the tensor cores (conv_tc, `en` input) and only the 128->32->8->1 tail
+//     runs here, one warp per cell with warp shuffles for the narrow layers.
+//   * agent-axis softmax exp(w_k)/sum_k exp(w_k) over k = {ego, neighbours...} and the weighted feature
+//     sum (DiscoNet.py:94-108) are accumulated on the fly; agents >= num_agent[b] keep their features
+//     (local_com_mat_update is initialised as a copy, DiscoNet.py:52-57).
+#include "common.cuh"
+#include "conv.h"
+#include "ops.h"
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kCellsPerWarp = 4;
+constexpr int kHid = 128, kH2 = 32, kH3 = 8;
+
+template <int VEC>  // VEC uint4 (8 channels each) per lane: C = 256*VEC
+__device__ __forceinline__ void load_feat(const uint16_t* p, long long lo_off, int precision, float wgt,
+                                          float (&acc)[8 * VEC]) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        const uint4 hi = __ldg(reinterpret_cast<const uint4*>(p) + v);
+        const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w};
+        if (precision == DISCO_PREC_BF16X3) {
+            const uint4 lo = __ldg(reinterpret_cast<const uint4*>(p + lo_off) + v);
+            const uint32_t lw[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float a = __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16);
+                const float b = __uint_as_float(hw[q] & 0xffff0000u) + __uint_as_float(lw[q] & 0xffff0000u);
+                acc[8 * v + 2 * q] = fmaf(wgt, a, acc[8 * v + 2 * q]);
+                acc[8 * v + 2 * q + 1] = fmaf(wgt, b, acc[8 * v + 2 * q + 1]);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[q]));
+                acc[8 * v + 2 * q] = fmaf(wgt, f.x, acc[8 * v + 2 * q]);
+                acc[8 * v + 2 * q + 1] = fmaf(wgt, f.y, acc[8 * v + 2 * q + 1]);
+            }
+        }
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kWarps * 32) fusion_kernel(const disco_fusion_desc d) {
+    __shared__ float s_w2[kH2][kHid + 1];
+    __shared__ float s_b2[kH2];
+    __shared__ float s_w3[kH3][kH2];
+    __shared__ float s_b3[kH3];
+    __shared__ float s_w4[kH3];
+    __shared__ float s_b4;
+    __shared__ __align__(16) float s_h1[kWarps][kHid];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int e = tid; e < kH2 * kHid; e += blockDim.x) s_w2[e / kHid][e % kHid] = d.w2[e];
+    for (int e = tid; e < kH3 * kH2; e += blockDim.x) s_w3[e / kH2][e % kH2] = d.w3[e];
+    if (tid < kH2) s_b2[tid] = d.b2[tid];
+    if (tid < kH3) { s_b3[tid] = d.b3[tid]; s_w4[tid] = d.w4[tid]; }
+    if (tid == 0) s_b4 = d.b4[0];
+    __syncthreads();
+
+    const int C = d.C, h = d.h, w = d.w, A = d.A, B = d.B;
+    const uint16_t* feat = reinterpret_cast<const uint16_t*>(d.feat_hi);
+    uint16_t* out = reinterpret_cast<uint16_t*>(d.out_hi);
+    const long long cells = (long long)B * A * h * w;
+    const int cpl = 8 * VEC;  // channels per lane
+
+    for (int t = 0; t < kCellsPerWarp; ++t) {
+        const long long cell = ((long long)blockIdx.x * kWarps + warp) * kCellsPerWarp + t;
+        if (cell >= cells) break;  // warp-uniform
+        const int x = (int)(cell % w);
+        const int y = (int)((cell / w) % h);
+        const int i = (int)((cell / ((long long)w * h)) % A);
+        const int b = (int)(cell / ((long long)w * h * A));
+        const int n_ag = d.num_agent[b];
+        const long long row_i = (((long long)(i * B + b) * h + y) * w + x);
+
+        float acc[8 * VEC];
+#pragma unroll
+        for (int c = 0; c < 8 * VEC; ++c) acc[c] = 0.f;
+        float esum = 0.f;
+
+        if (i >= n_ag) {  // absent agent: features pass through unchanged
+            load_feat<VEC>(feat + row_i * C + lane * cpl, d.feat_lo_off, d.precision, 1.f, acc);
+            esum = 1.f;
+        } else {
+            const float4 e4 = __ldg(reinterpret_cast<const float4*>(d.en + row_i * (2 * kHid)) + lane);
+            const int yf = h - 1 - y;  // row in the H-flipped frame the reference warps in
+            const float xb = (2.f * x + 1.f) / w - 1.f;
+            const float yb = (2.f * yf + 1.f) / h - 1.f;
+            for (int k = 0; k < n_ag; ++k) {
+                // reference order: ego first, then neighbours j = 0..n-1 skipping i
+                const int j = (k == 0) ? i : ((k - 1 < i) ? k - 1 : k);
+                if (j != i && d.only_v2i && i != 0 && j != 0) continue;
+                float nb[8 * VEC];
+#pragma unroll
+                for (int c = 0; c < 8 * VEC; ++c) nb[c] = 0.f;
+                float nn[4] = {0.f, 0.f, 0.f, 0.f};
+                if (j == i) {
+                    load_feat<VEC>(feat + row_i * C + lane * cpl, d.feat_lo_off, d.precision, 1.f, nb);
+                    const float4 n4 = __ldg(reinterpret_cast<const float4*>(d.en + row_i * (2 * kHid) + kHid) + lane);
+                    nn[0] = n4.x; nn[1] = n4.y; nn[2] = n4.z; nn[3] = n4.w;
+                } else {
+                    const double* T = d.trans + (((long long)b * A + j) * A + i) * 16;
+                    const float m00 = (float)T[0], m01 = (float)T[1], m02 = (-(float)T[3]) * d.trans_scale;
+                    const float m10 = (float)T[4], m11 = (float)T[5], m12 = (-(float)T[7]) * d.trans_scale;
+                    const float gx = m00 * xb + m01 * yb + m02;
+                    const float gy = m10 * xb + m11 * yb + m12;
+                    const float ix = ((gx + 1.f) * w - 1.f) * 0.5f;
+                    const float iy = ((gy + 1.f) * h - 1.f) * 0.5f;
+                    const float fx = floorf(ix), fy = floorf(iy);
+                    const float ax = ix - fx, ay = iy - fy;
+                    // guard against inf/nan/huge coordinates before the int conversion
+                    const bool finite = (fabsf(ix) < 1e6f) && (fabsf(iy) < 1e6f);
+                    const int x0 = finite ? (int)fx : -10, y0 = finite ? (int)fy : -10;
+                    const float tw[4] = {(1.f - ax) * (1.f - ay), ax * (1.f - ay), (1.f - ax) * ay, ax * ay};
+#pragma unroll
+                    for (int tp = 0; tp < 4; ++tp) {
+                        const int xs = x0 + (tp & 1), ysf = y0 + (tp >> 1);
+                        if (xs < 0 || xs >= w || ysf < 0 || ysf >= h) continue;  // zeros padding
+                        const long long row_j = (((long long)(j * B + b) * h + (h - 1 - ysf)) * w + xs);
+                        load_feat<VEC>(feat + row_j * C + lane * cpl, d.feat_lo_off, d.precision, tw[tp], nb);
+                        const float4 n4 =
+                            __ldg(reinterpret_cast<const float4*>(d.en + row_j * (2 * kHid) + kHid) + lane);
+                        nn[0] = fmaf(tw[tp], n4.x, nn[0]); nn[1] = fmaf(tw[tp], n4.y, nn[1]);
+                        nn[2] = fmaf(tw[tp], n4.z, nn[2]); nn[3] = fmaf(tw[tp], n4.w, nn[3]);
+                    }
+                }
+                // ---- PWF tail: 128 -> 32 -> 8 -> 1 ------------------------------------------------
+                float4 h1;
+                h1.x = fmaxf(e4.x + nn[0], 0.f); h1.y = fmaxf(e4.y + nn[1], 0.f);
+                h1.z = fmaxf(e4.z + nn[2], 0.f); h1.w = fmaxf(e4.w + nn[3], 0.f);
+                __syncwarp();
+                reinterpret_cast<float4*>(s_h1[warp])[lane] = h1;
+                __syncwarp();
+                float h2 = s_b2[lane];
+#pragma unroll 8
+                for (int c = 0; c < kHid; c += 4) {
+                    const float4 hv = *reinterpret_cast<const float4*>(&s_h1[warp][c]);
+                    h2 = fmaf(s_w2[lane][c], hv.x, h2);
+                    h2 = fmaf(s_w2[lane][c + 1], hv.y, h2);
+                    h2 = fmaf(s_w2[lane][c + 2], hv.z, h2);
+                    h2 = fmaf(s_w2[lane][c + 3], hv.w, h2);
+                }
+                h2 = fmaxf(h2, 0.f);
+                float wk = s_b4;
+#pragma unroll
+                for (int q = 0; q < kH3; ++q) {
+                    float part = s_w3[q][lane] * h2;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                    wk = fmaf(s_w4[q], fmaxf(part + s_b3[q], 0.f), wk);
+                }
+                wk = fmaxf(wk, 0.f);
+                const float ek = expf(wk);
+                esum += ek;
+#pragma unroll
+                for (int c = 0; c < 8 * VEC; ++c) acc[c] = fmaf(ek, nb[c], acc[c]);
+                if (d.weights && lane == 0)
+                    d.weights[((((long long)b * A + i) * A + j) * h + y) * w + x] = ek;
+            }
+            if (d.weights) {
+                __syncwarp();
+                if (lane < A) {
+                    const long long wi = ((((long long)b * A + i) * A + lane) * h + y) * w + x;
+                    const bool used = (lane < n_ag) && (lane == i || !(d.only_v2i && i != 0 && lane != 0));
+                    d.weights[wi] = used ? d.weights[wi] / esum : 0.f;
+                }
+            }
+        }
+        // ---- normalise and store -------------------------------------------------------------------
+        const float inv = 1.f / esum;
+        uint16_t* o = out + row_i * C + lane * cpl;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float a = (i >= n_ag) ? acc[8 * v + 2 * q] : acc[8 * v + 2 * q] * inv;
+                const float c2 = (i >= n_ag) ? acc[8 * v + 2 * q + 1] : acc[8 * v + 2 * q + 1] * inv;
+                if (d.precision == DISCO_PREC_BF16X3) {
+                    uint16_t h0, l0, h1_, l1;
+                    split_bf16(a, h0, l0);
+                    split_bf16(c2, h1_, l1);
+                    hi[q] = (uint32_t)h0 | ((uint32_t)h1_ << 16);
+                    lo[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                } else {
+                    hi[q] = (uint32_t)f32_to_f16_bits(a) | ((uint32_t)f32_to_f16_bits(c2) << 16);
+                    lo[q] = 0;
+                }
+            }
+            reinterpret_cast<uint4*>(o)[v] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (d.precision == DISCO_PREC_BF16X3)
+                reinterpret_cast<uint4*>(o + d.out_lo_off)[v] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+    }
+}
+
+}  // namespace
+
+int disco_fusion_launch(const disco_fusion_desc* d, void* stream) {
+    DISCO_REQUIRE(d->feat_hi && d->en && d->out_hi && d->trans && d->num_agent, "fusion: null tensor");
+    DISCO_REQUIRE(d->w2 && d->b2 && d->w3 && d->b3 && d->w4 && d->b4, "fusion: null PWF weights");
+    DISCO_REQUIRE(d->hid == kHid, "fusion: PWF hidden width must be %d (got %d)", kHid, d->hid);
+    DISCO_REQUIRE(d->C == 256 || d->C == 512, "fusion: C must be 256 or 512 (got %d)", d->C);
+    DISCO_REQUIRE(d->A >= 1 && d->A <= 32 && d->B >= 1 && d->h > 0 && d->w > 0, "fusion: bad scene shape");
+    const long long cells = (long long)d->B * d->A * d->h * d->w;
+    const long long per_block = kWarps * kCellsPerWarp;
+    const long long blocks = (cells + per_block - 1) / per_block;
+    DISCO_REQUIRE(blocks < (1ll << 31), "fusion: too many cells");
+    if (d->C == 256) fusion_kernel<1><<<(unsigned)blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(*d);
+    else fusion_kernel<2><<<(unsigned)blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(*d);
+    DISCO_CHECK_CUDA(cudaGetLastError());
+    return DISCO_OK;
+}

@@ -1,0 +1,41 @@
+// Non-GEMM kernels of the hot path: BEV pack / voxelize / scatter / DiscoGraph fusion.
+#pragma once
+#include <stdint.h>
+
+// DiscoGraph fusion block descriptor (mirrors include/disco_b200.h).
+struct disco_fusion_desc {
+    // collaboration-layer features, agent-major rows n = a*B + b, NHWC
+    const void* feat_hi;       // 16-bit [A*B, h, w, C]
+    long long feat_lo_off;     // BF16X3: elements from hi to lo
+    int precision;             // DISCO_PREC_*
+    // PWF first layer applied per agent by the conv kernel (fp32 [A*B, h, w, 2*hid]):
+    //   channels [0,hid)     = s*(W_ego  x) + s*(b - mean) + beta      (BN folded)
+    //   channels [hid,2hid)  = s*(W_nb   x)
+    const float* en;
+    int hid;                   // 128
+    // PWF tail (BN folded), fp32 row-major
+    const float* w2; const float* b2;   // [h2, hid], [h2]     (h2 = 32)
+    const float* w3; const float* b3;   // [h3, h2],  [h3]     (h3 = 8)
+    const float* w4; const float* b4;   // [1, h3],   [1]
+    // scene description
+    const double* trans;       // [B, A, A, 4, 4] float64 (trans_matrices)
+    const int* num_agent;      // [B]
+    int B, A, h, w, C;
+    int only_v2i;
+    float trans_scale;         // 4/128 (DetModelBase.py:163)
+    // outputs
+    void* out_hi;              // fused features, same layout as feat
+    long long out_lo_off;
+    float* weights;            // optional [B, A(ego), A(neighbour id), h, w] softmax weights, unflipped frame
+};
+
+int disco_fusion_launch(const disco_fusion_desc* d, void* stream);
+int disco_bev_pack_launch(const float* bev, long long n_pix, int z, void* out_hi, long long out_lo_off, int precision,
+                          void* stream);
+int disco_act_unpack_nchw_launch(const void* act_hi, long long lo_off, int precision, int n, int h, int w, int c,
+                                 float* out_nchw, void* stream);
+int disco_voxelize_launch(const float* points, int n_points, int point_stride, const double* extents,
+                          const double* voxel_size, const int* dims, unsigned int* bitmap, int* voxel_indices,
+                          int* n_voxels, float* dense, void* stream);
+int disco_bev_scatter_launch(const int* voxel_indices, int n_voxels, const int* dims, float* bev_f32, void* act_hi,
+                             int act_c, int precision, void* stream);

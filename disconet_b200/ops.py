@@ -1,0 +1,110 @@
+"""Thin launch wrappers: torch tensors (device memory + stream plumbing) -> C-ABI descriptors."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import OUT_ACT, OUT_F32, PREC_BF16X3, PREC_FP16, ConvDesc, FusionDesc, check, load
+from .plan import ConvPlan
+
+
+def act_dtype(precision: int):
+    return torch.bfloat16 if precision == PREC_BF16X3 else torch.float16
+
+
+def act_parts(precision: int) -> int:
+    return 2 if precision == PREC_BF16X3 else 1
+
+
+def alloc_act(n, h, w, c, precision, device) -> torch.Tensor:
+    """Activation buffer [parts, n, h, w, c]: part 0 = hi (or the single fp16 tensor), part 1 = lo."""
+    return torch.empty((act_parts(precision), n, h, w, c), dtype=act_dtype(precision), device=device)
+
+
+def _lo_off(t: torch.Tensor) -> int:
+    return t.stride(0) if t.shape[0] == 2 else 0
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise ValueError("disconet_b200 kernels take CUDA tensors only (no CPU fallback path)")
+
+
+def conv_forward(plan: ConvPlan, srcs: Sequence[torch.Tensor], ups: Sequence[int], out, *, n, h_in, w_in,
+                 out_split: Optional[int] = None, reference: bool = False):
+    """Run one conv layer.  srcs: activation buffers [parts,n,hs,ws,c]; out: activation buffer (OUT_ACT)
+    or a tuple of fp32 NHWC tensors (OUT_F32)."""
+    lib = load()
+    d = ConvDesc()
+    _require_cuda(*srcs)
+    for i in range(2):
+        if i < len(srcs):
+            s = srcs[i]
+            d.src[i] = s.data_ptr()
+            d.src_lo_off[i] = _lo_off(s)
+            d.src_c[i] = s.shape[-1]
+            d.src_up[i] = int(ups[i])
+        else:
+            d.src[i] = None
+            d.src_lo_off[i] = 0
+            d.src_c[i] = 0
+            d.src_up[i] = 0
+    assert sum(s.shape[-1] for s in srcs) == plan.c_in, (plan.name, [s.shape for s in srcs], plan.c_in)
+    d.n, d.h_in, d.w_in = n, h_in, w_in
+    d.stride, d.taps, d.c_blk = plan.stride, plan.taps, plan.c_blk
+    d.h_out = (h_in - 1) // plan.stride + 1
+    d.w_out = (w_in - 1) // plan.stride + 1
+    d.c_out, d.block_n = plan.c_out, plan.block_n
+    d.wpack = plan.wpack.data_ptr()
+    d.wref = plan.wref.data_ptr() if plan.wref is not None else None
+    d.bias = plan.bias.data_ptr()
+    d.relu = int(plan.relu)
+    d.precision = plan.precision
+    if isinstance(out, torch.Tensor) and out.dtype in (torch.bfloat16, torch.float16):
+        _require_cuda(out)
+        assert out.shape[-1] == plan.c_out
+        d.out_mode = OUT_ACT
+        d.out[0] = out.data_ptr()
+        d.out[1] = None
+        d.out_lo_off = _lo_off(out)
+        d.out_split = plan.c_out
+    else:
+        outs = out if isinstance(out, (tuple, list)) else (out,)
+        _require_cuda(*outs)
+        d.out_mode = OUT_F32
+        d.out[0] = outs[0].data_ptr()
+        d.out[1] = outs[1].data_ptr() if len(outs) > 1 else None
+        d.out_lo_off = 0
+        d.out_split = plan.c_out if out_split is None else out_split
+    stream = _stream_ptr(srcs[0].device)
+    fn = lib.disco_conv_reference if reference else lib.disco_conv_forward
+    check(fn(C.byref(d), stream), f"conv[{plan.name}]")
+
+
+def bev_pack(bev: torch.Tensor, out: torch.Tensor, precision: int):
+    """bev fp32 [..., Z] contiguous -> out activation buffer [parts, n, h, w, 16]."""
+    _require_cuda(bev, out)
+    assert bev.dtype == torch.float32 and bev.is_contiguous()
+    z = bev.shape[-1]
+    n_pix = bev.numel() // z
+    assert out.shape[-1] == 16 and out[0].numel() == n_pix * 16
+    check(load().disco_bev_pack(bev.data_ptr(), n_pix, z, out.data_ptr(), _lo_off(out), precision,
+                                _stream_ptr(bev.device)), "bev_pack")
+
+
+def act_to_nchw_f32(act: torch.Tensor, precision: int) -> torch.Tensor:
+    """activation buffer [parts,n,h,w,c] -> fp32 [n,c,h,w] (contiguous)."""
+    _require_cuda(act)
+    _, n, h, w, c = act.shape
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=act.device)
+    check(load().disco_act_unpack_nchw(act.data_ptr(), _lo_off(act), precision, n, h, w, c, out.data_ptr(),
+                                       _stream_ptr(act.device)), "act_unpack")
+    return out

@@ -1,0 +1,104 @@
+"""Host-side weight preparation for the tcgen05 conv kernel: BN folding and UMMA operand packing.
+
+Pure tensor bookkeeping (runs on whatever device the parameters live on); no compute of the hot path
+happens here.  Layout contract with csrc/conv_tc.cu:
+
+    wpack[n_tile][c_block][tap][part][c_blk/8][block_n][8]   16-bit, part = (hi, lo) for bf16x3
+
+i.e. for every (channel block, filter tap) one contiguous shared-memory image of the B operand in the
+UMMA no-swizzle K-major core-matrix layout, streamed by a single bulk copy.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+
+from ._lib import PREC_BF16X3, PREC_FP16
+
+BN_EPS = 1e-5
+
+
+def fold_bn(weight, bias, bn_w, bn_b, bn_mean, bn_var, eps: float = BN_EPS):
+    """conv -> BatchNorm(eval) == conv with w*s, (b-mean)*s+beta,  s = gamma/sqrt(var+eps)."""
+    w = weight.detach().float()
+    s = bn_w.detach().float() / torch.sqrt(bn_var.detach().float() + eps)
+    wf = w * s.view(-1, *([1] * (w.dim() - 1)))
+    b0 = bias.detach().float() if bias is not None else torch.zeros_like(s)
+    bf = (b0 - bn_mean.detach().float()) * s + bn_b.detach().float()
+    return wf, bf
+
+
+def split_bf16(t: torch.Tensor):
+    """fp32 -> (hi, lo) bf16 with hi = bf16(t), lo = bf16(t - hi)."""
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def choose_c_blk(src_channels, precision: int, stride: int) -> int:
+    cap = 64
+    if precision == PREC_BF16X3 or stride == 2:
+        cap = 32
+    for cb in (64, 32, 16):
+        if cb <= cap and all(c % cb == 0 for c in src_channels if c):
+            return cb
+    raise ValueError(f"source channels {src_channels} must be multiples of 16")
+
+
+@dataclass
+class ConvPlan:
+    """Packed weights + static geometry of one conv layer."""
+    taps: int
+    stride: int
+    c_in: int                 # padded input channels (sum of sources)
+    c_out: int
+    c_blk: int
+    block_n: int
+    relu: bool
+    precision: int
+    wpack: torch.Tensor       # int16 storage
+    bias: torch.Tensor        # fp32 [n_tiles*block_n]
+    wref: Optional[torch.Tensor] = None   # fp32 [c_out, taps, c_in] (validator only)
+    name: str = ""
+    flops_per_pixel: int = field(default=0)
+
+
+def pack_conv(wf: torch.Tensor, bf: torch.Tensor, *, src_channels, stride: int = 1, relu: bool = True,
+              precision: int = PREC_BF16X3, block_n: Optional[int] = None, keep_ref: bool = False,
+              name: str = "") -> ConvPlan:
+    """wf [c_out, c_in_real, k, k] fp32 (BN folded), bf [c_out] -> ConvPlan.
+
+    `src_channels` are the (padded) channel counts of the concatenated NHWC sources in order; real
+    input channels are laid out at the start of each source (only the first conv pads 13 -> 16).
+    """
+    c_out, c_in_real, k, _ = wf.shape
+    taps = k * k
+    assert taps in (1, 9)
+    c_in = int(sum(src_channels))
+    assert c_in >= c_in_real
+    c_blk = choose_c_blk(src_channels, precision, stride)
+    c_out_pad16 = (c_out + 15) // 16 * 16
+    if block_n is None:
+        block_n = min(c_out_pad16, 256)
+    n_tiles = (c_out + block_n - 1) // block_n
+    n_rows = n_tiles * block_n
+    dev = wf.device
+    w = torch.zeros(n_rows, c_in, taps, dtype=torch.float32, device=dev)
+    w[:c_out, :c_in_real] = wf.reshape(c_out, c_in_real, taps)
+    bias = torch.zeros(n_rows, dtype=torch.float32, device=dev)
+    bias[:c_out] = bf
+    ncb = c_in // c_blk
+    # [n_tile, n, cb, chunk, 8, tap] -> [n_tile, cb, tap, chunk, n, 8]
+    w6 = w.view(n_tiles, block_n, ncb, c_blk // 8, 8, taps).permute(0, 2, 5, 3, 1, 4).contiguous()
+    if precision == PREC_BF16X3:
+        hi, lo = split_bf16(w6)
+        parts = torch.stack((hi, lo), dim=3)          # [n_tile, cb, tap, part, chunk, n, 8]
+        wpack = parts.contiguous().view(torch.int16)
+    else:
+        wpack = w6.to(torch.float16).contiguous().view(torch.int16)
+    wref = w[:c_out].permute(0, 2, 1).contiguous() if keep_ref else None   # [c_out, taps, c_in]
+    return ConvPlan(taps=taps, stride=stride, c_in=c_in, c_out=c_out, c_blk=c_blk, block_n=block_n, relu=relu,
+                    precision=precision, wpack=wpack.reshape(-1), bias=bias, wref=wref, name=name,
+                    flops_per_pixel=2 * taps * c_in_real * c_out)

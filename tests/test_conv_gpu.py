@@ -1,0 +1,116 @@
+"""GPU parity of the tcgen05 conv kernel (through the C-ABI) against torch fp32 conv2d and the
+CUDA-core validator, over every layer shape class of the DiscoNet path."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from disconet_b200._lib import PREC_BF16X3, PREC_FP16
+from disconet_b200.ops import alloc_act, conv_forward
+from disconet_b200.plan import pack_conv
+from helpers import act_value, rel_max, to_act
+
+pytestmark = pytest.mark.gpu
+
+# (name, n, h, w, sources [(c_real, c_pad, up)], c_out, k, stride, out)   out: 'act' | 'f32' | (split,)
+CASES = [
+    ("c32_s1", 2, 32, 32, [(32, 32, 0)], 32, 3, 1, "act"),
+    ("pre1_13to32", 2, 32, 40, [(13, 16, 0)], 32, 3, 1, "act"),
+    ("c32to64_s2", 2, 64, 64, [(32, 32, 0)], 64, 3, 2, "act"),
+    ("upcat_64up_32", 2, 32, 32, [(64, 64, 1), (32, 32, 0)], 32, 3, 1, "act"),
+    ("upcat_512up_256", 1, 32, 32, [(512, 512, 1), (256, 256, 0)], 256, 3, 1, "act"),
+    ("c256_s1_multi_stage", 3, 32, 32, [(256, 256, 0)], 256, 3, 1, "act"),
+    ("c256to512_s2_two_ntiles", 2, 32, 32, [(256, 256, 0)], 512, 3, 2, "act"),
+    ("c512_16x16", 2, 16, 16, [(512, 512, 0)], 512, 3, 1, "act"),
+    ("partial_tiles_24x20", 1, 24, 20, [(64, 64, 0)], 64, 3, 1, "act"),
+    ("tiny_8x8_s2", 1, 8, 8, [(64, 64, 0)], 128, 3, 2, "act"),
+    ("pw_64to64", 2, 32, 32, [(64, 64, 0)], 64, 1, 1, "act"),
+    ("pw_256to256_f32", 2, 32, 32, [(256, 256, 0)], 256, 1, 1, "f32"),
+    ("pw_heads_64to48_split", 1, 32, 24, [(64, 64, 0)], 48, 1, 1, (12,)),
+    ("pw_ragged_pixels", 1, 10, 13, [(32, 32, 0)], 32, 1, 1, "act"),
+]
+
+
+def _run_case(case, precision, dev, seed=0):
+    name, n, h, w, sources, c_out, k, stride, outk = case
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    xs, acts, ups = [], [], []
+    for (c_real, c_pad, up) in sources:
+        hs, ws = (h // 2, w // 2) if up else (h, w)
+        x = torch.randn(n, c_real, hs, ws, generator=g).to(dev)
+        a = to_act(x, precision, c_pad)
+        acts.append(a)
+        ups.append(up)
+        v = act_value(a)[..., :c_real].permute(0, 3, 1, 2)  # value the kernel actually sees
+        xs.append(F.interpolate(v, scale_factor=2) if up else v)
+    x_cat = torch.cat(xs, 1)
+    c_in_real = x_cat.shape[1]
+    wgt = (torch.randn(c_out, c_in_real, k, k, generator=g) / (c_in_real * k * k) ** 0.5).to(dev)
+    bias = torch.randn(c_out, generator=g).to(dev) * 0.1
+    relu = outk == "act"
+    # weights as the kernel sees them (rounded to the operand precision) so the check isolates the kernel
+    if precision == PREC_BF16X3:
+        hi = wgt.to(torch.bfloat16)
+        w_seen = hi.float() + (wgt - hi.float()).to(torch.bfloat16).float()
+    else:
+        w_seen = wgt.to(torch.float16).float()
+    # real channels sit at the start of each padded source: scatter weights accordingly
+    w_pad = torch.zeros(c_out, sum(s[1] for s in sources), k, k, device=dev)
+    o_r = o_p = 0
+    for (c_real, c_pad, up) in sources:
+        w_pad[:, o_p:o_p + c_real] = wgt[:, o_r:o_r + c_real]
+        o_r += c_real
+        o_p += c_pad
+    plan = pack_conv(w_pad, bias, src_channels=[s[1] for s in sources], stride=stride, relu=relu,
+                     precision=precision, keep_ref=True, name=name)
+    ref = F.conv2d(x_cat, w_seen, bias, stride=stride, padding=k // 2)
+    if relu:
+        ref = F.relu(ref)
+    ref = ref.permute(0, 2, 3, 1).contiguous()
+    ho, wo = ref.shape[1], ref.shape[2]
+    results = {}
+    for which in ("tc", "ref"):
+        if outk == "act":
+            out = alloc_act(n, ho, wo, c_out, precision, dev)
+            out.fill_(float("nan"))
+            conv_forward(plan, acts, ups, out, n=n, h_in=h, w_in=w, reference=(which == "ref"))
+            got = act_value(out)
+        elif outk == "f32":
+            out = torch.full((n, ho, wo, c_out), float("nan"), device=dev)
+            conv_forward(plan, acts, ups, (out,), n=n, h_in=h, w_in=w, reference=(which == "ref"))
+            got = out
+        else:
+            sp = outk[0]
+            o0 = torch.full((n, ho, wo, sp), float("nan"), device=dev)
+            o1 = torch.full((n, ho, wo, c_out - sp), float("nan"), device=dev)
+            conv_forward(plan, acts, ups, (o0, o1), n=n, h_in=h, w_in=w, out_split=sp, reference=(which == "ref"))
+            got = torch.cat((o0, o1), -1)
+        torch.cuda.synchronize()
+        results[which] = got
+    return results, ref
+
+
+@pytest.mark.parametrize("precision", [PREC_FP16, PREC_BF16X3], ids=["fp16", "bf16x3"])
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_conv_matches_torch(case, precision, cuda_dev):
+    results, ref = _run_case(case, precision, cuda_dev)
+    # output rounding: fp16 act 2^-11, bf16 hi+lo ~2^-17; fp32 accumulate-order noise ~1e-6;
+    # bf16x3 drops the lo*lo term (~2^-16 relative per product)
+    tol = {PREC_FP16: 1e-3, PREC_BF16X3: 5e-5}[precision]
+    for which, got in results.items():
+        assert torch.isfinite(got).all(), f"{which}: non-finite / unwritten outputs"
+        err = rel_max(got, ref)
+        assert err < tol, f"{case[0]} {which}: rel-max error {err:.3e} >= {tol}"
+
+
+def test_conv_rejects_bad_descriptor(cuda_dev):
+    from disconet_b200._lib import DiscoError
+    w = torch.randn(32, 24, 3, 3, device=cuda_dev)
+    with pytest.raises(ValueError):
+        pack_conv(w, torch.zeros(32, device=cuda_dev), src_channels=[24])  # not a multiple of 16
+    plan = pack_conv(torch.randn(32, 32, 3, 3, device=cuda_dev), torch.zeros(32, device=cuda_dev), src_channels=[32])
+    a = alloc_act(1, 16, 16, 32, PREC_BF16X3, cuda_dev)
+    out = alloc_act(1, 16, 16, 32, PREC_BF16X3, cuda_dev)
+    with pytest.raises(DiscoError):
+        conv_forward(plan, [a], [1], out, n=1, h_in=15, w_in=16)  # odd size with upsample flag
+    with pytest.raises(ValueError):
+        conv_forward(plan, [a.cpu()], [0], out, n=1, h_in=16, w_in=16)  # CPU tensor: no fallback
