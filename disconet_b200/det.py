@@ -1,0 +1,295 @@
+"""Host-side mirror of `coperception.models.det` for the DiscoNet hot path (drop-in boundary).
+
+Same class names, constructor arguments, `forward` signatures, return structures, attribute names and
+`state_dict` layout as the reference (DiscoNet.py:21-129, FaFNet.py:17-39, TeacherNet.py:7-13), so that
+tools/det/train_codet.py / test_codet.py construct and call them unchanged (`--com disco`).  All compute
+runs in libdisco_b200 (sm_100a CUDA) on torch's current stream; there is no CPU or torch-op fallback:
+CPU tensors or a missing library raise.
+"""
+from __future__ import annotations
+
+import collections.abc
+import os
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import engine, ops
+from ._lib import DiscoError, load
+from .modules import (BackboneParams, ClassificationHeadParams, PixelWeightedFusionParams, RegressionHeadParams)
+
+DEFAULT_PRECISION = os.environ.get("DISCO_B200_PRECISION", "bf16x3")
+
+
+class AgentWeightList(collections.abc.Sequence):
+    """`save_agent_weight_list` of the reference (DiscoNet.py:57,113): one entry per (scene, ego) holding
+    the list of [h, w] softmax weight maps in neighbour order [ego, j0, j1, ...] (H-flipped frame, as the
+    reference computes them).  Materialised lazily so that the forward itself needs no host sync."""
+
+    def __init__(self, weights: torch.Tensor, num_agent: torch.Tensor, only_v2i: bool):
+        self._w, self._na, self._v2i, self._items = weights, num_agent, only_v2i, None
+
+    def _build(self):
+        if self._items is None:
+            items = []
+            na = self._na.tolist()
+            wf = torch.flip(self._w, (3,))
+            for b, n in enumerate(na):
+                for i in range(n):
+                    js = [i] + [j for j in range(n) if j != i and not (self._v2i and i != 0 and j != 0)]
+                    items.append([wf[b, i, j] for j in js])
+            self._items = items
+        return self._items
+
+    def __len__(self):
+        return len(self._build())
+
+    def __getitem__(self, k):
+        return self._build()[k]
+
+
+class _DetBase(nn.Module):
+    """Shared plumbing: config fields, heads, plan/workspace caches (DetModelBase.py:27-51)."""
+
+    def __init__(self, config, layer=3, in_channels=13, kd_flag=True, p_com_outage=0.0, num_agent=5,
+                 only_v2i=False, precision: Optional[str] = None):
+        super().__init__()
+        self.motion_state = config.motion_state
+        self.out_seq_len = 1 if config.only_det else config.pred_len
+        self.box_code_size = config.box_code_size
+        self.category_num = config.category_num
+        self.use_map = config.use_map
+        self.anchor_num_per_loc = len(config.anchor_size)
+        if config.use_map or getattr(config, "use_vis", False) or config.motion_state:
+            raise NotImplementedError("disconet_b200 implements the default detection config "
+                                      "(use_map=False, use_vis=False, motion_state=False)")
+        if not (config.binary and config.only_det):
+            raise NotImplementedError("disconet_b200 implements the binary/only_det regression head")
+        channel = 32
+        self.classification = ClassificationHeadParams(channel, self.category_num, self.anchor_num_per_loc)
+        self.regression = RegressionHeadParams(channel, self.anchor_num_per_loc * self.box_code_size * self.out_seq_len)
+        self.agent_num = num_agent
+        self.kd_flag = kd_flag
+        self.layer = layer
+        self.p_com_outage = p_com_outage
+        self.neighbor_feat_list = []
+        self.tg_agent = None
+        self.only_v2i = only_v2i
+        self.in_channels = in_channels
+        self.precision_name = precision or DEFAULT_PRECISION
+        if self.precision_name not in engine.PRECISIONS:
+            raise ValueError(f"precision must be one of {list(engine.PRECISIONS)}")
+        self._plans = None
+        self._plans_key = None
+        self._ws: Dict[tuple, engine.Workspace] = {}
+
+    # ---- caches ---------------------------------------------------------------------------------------
+    @property
+    def precision(self) -> int:
+        return engine.PRECISIONS[self.precision_name]
+
+    def _param_key(self):
+        ts = list(self.parameters()) + list(self.buffers())
+        return (self.precision_name, ts[0].device, tuple(t._version for t in ts), tuple(t.data_ptr() for t in ts[:4]))
+
+    def _getter(self):
+        sd = dict(self.named_parameters())
+        sd.update(dict(self.named_buffers()))
+        return sd.__getitem__
+
+    def _build_plans(self, get):  # pragma: no cover - overridden
+        raise NotImplementedError
+
+    def plans(self):
+        key = self._param_key()
+        if self._plans is None or key != self._plans_key:
+            with torch.no_grad():
+                self._plans = self._build_plans(self._getter())
+            self._plans_key = key
+            self._ws.clear()
+        return self._plans
+
+    def _check_inputs(self, bevs):
+        load()  # raises if libdisco_b200.so is missing
+        if self.training:
+            raise NotImplementedError(
+                "disconet_b200 round 1 implements the eval-mode forward (BN folded); call model.eval(). "
+                "The training forward/backward kernels are the next row of DESIGN.md §scope.")
+        if not bevs.is_cuda:
+            raise ValueError("disconet_b200 runs on CUDA tensors only (no CPU fallback); got a CPU `bevs`")
+        if bevs.dim() != 5 or bevs.shape[1] != 1 or bevs.shape[4] != self.in_channels:
+            raise ValueError(f"bevs must be [N, 1, H, W, {self.in_channels}] (got {tuple(bevs.shape)})")
+        dev = next(self.parameters()).device
+        if dev != bevs.device:
+            raise ValueError(f"model parameters on {dev} but bevs on {bevs.device}")
+
+    def _pack_input(self, bevs, ws: engine.Workspace):
+        bev = bevs.detach()
+        if bev.dtype != torch.float32:
+            bev = bev.float()
+        ops.bev_pack(bev.contiguous(), ws.buf["a0"], self.precision)
+
+    def _run_heads(self, ws: engine.Workspace, stream):
+        n, h, w = ws.n, ws.h, ws.w
+        cls = torch.empty((n, h, w, ws.n_cls), dtype=torch.float32, device=ws.device)
+        loc = torch.empty((n, h, w, ws.n_reg), dtype=torch.float32, device=ws.device)
+        ws.head_calls[0].launch(stream)
+        ws.head_calls[1].set_output((cls, loc), ws.n_cls)
+        ws.head_calls[1].launch(stream)
+        # NHWC is already the reference's permute(0,2,3,1) layout (DetModelBase.py:239-252)
+        cls = cls.view(n, -1, self.category_num)
+        loc = loc.view(-1, h, w, self.anchor_num_per_loc, self.out_seq_len, self.box_code_size)
+        return {"loc": loc, "cls": cls}
+
+    def _nchw(self, ws, key):
+        return ops.act_to_nchw_f32(ws.buf[key], self.precision)
+
+
+class DiscoNet(_DetBase):
+    """DiscoNet (reference: coperception/models/det/DiscoNet.py:7-129), B200-native eval forward."""
+
+    def __init__(self, config, layer=3, in_channels=13, kd_flag=True, num_agent=5, compress_level=0,
+                 only_v2i=False, precision: Optional[str] = None):
+        super().__init__(config, layer, in_channels, kd_flag, num_agent=num_agent, only_v2i=only_v2i,
+                         precision=precision)
+        # registration order = reference (heads, u_encoder, decoder, pixel_weighted_fusion)
+        self.u_encoder = BackboneParams(in_channels, compress_level)
+        self.decoder = BackboneParams(in_channels)
+        self.compress_level = compress_level
+        if self.layer == 3:
+            self.pixel_weighted_fusion = PixelWeightedFusionParams(256)
+        elif self.layer == 2:
+            self.pixel_weighted_fusion = PixelWeightedFusionParams(128)
+
+    def _build_plans(self, get):
+        if self.layer != 3:
+            raise NotImplementedError("disconet_b200 implements collaboration at --layer 3 (the CLI default)")
+        p = self.precision
+        return {
+            "enc": engine.build_encoder_plans(get, "u_encoder.", p, compress=self.compress_level > 0),
+            "dec": engine.build_decoder_plans(get, "decoder.", p),
+            "heads": engine.build_head_plans(get, p),
+            "pwf": engine.build_pwf_plans(get, p),
+        }
+
+    def _workspace(self, n, h, w, batch_size, device) -> engine.Workspace:
+        key = (n, h, w, batch_size, str(device))
+        ws = self._ws.get(key)
+        if ws is None:
+            P = self.plans()
+            ws = engine.Workspace(n, h, w, self.precision, device, P["enc"], P["dec"], P["heads"], P["pwf"],
+                                  batch_size=batch_size, agents=self.agent_num)
+            self._ws[key] = ws
+        return ws
+
+    def outage(self) -> bool:
+        """DetModelBase.py:129-137 (consumes the numpy RNG exactly like the reference)."""
+        return bool(np.random.choice([True, False], p=[self.p_com_outage, 1 - self.p_com_outage]))
+
+    def forward(self, bevs, trans_matrices, num_agent_tensor, batch_size=1):
+        """Same contract as the reference forward (DiscoNet.py:28-129).
+
+        bevs [A*B, 1, H, W, 13] (agent-major), trans_matrices [B, A, A, 4, 4], num_agent_tensor [B, A].
+        Returns (result, x_8, x_7, x_6, x_5, feat_fuse_mat) if kd_flag == 1 else (result, weight list).
+        """
+        self._check_inputs(bevs)
+        if self.p_com_outage != 0.0:
+            raise NotImplementedError("communication outage (p_com_outage > 0) is not implemented yet")
+        dev = bevs.device
+        N, _, H, W, _ = bevs.shape
+        A, B = self.agent_num, int(batch_size)
+        if N != A * B:
+            raise ValueError(f"bevs has {N} rows but agent_num*batch_size = {A}*{B}")
+        if tuple(trans_matrices.shape) != (B, A, A, 4, 4):
+            raise ValueError(f"trans_matrices must be [{B},{A},{A},4,4] (got {tuple(trans_matrices.shape)})")
+        P = self.plans()
+        ws = self._workspace(N, H, W, B, dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        trans = trans_matrices.detach().to(device=dev, dtype=torch.float64).contiguous()
+        num_agent = num_agent_tensor.detach()[:, 0].to(device=dev, dtype=torch.int32).contiguous()
+
+        self._pack_input(bevs, ws)
+        for c in ws.enc_calls:
+            c.launch(stream)
+        ws.en_call.launch(stream)
+        f = ws.fusion
+        f.trans = trans.data_ptr()
+        f.num_agent = num_agent.data_ptr()
+        f.only_v2i = int(bool(self.only_v2i))
+        weights = None
+        if self.kd_flag != 1:
+            weights = torch.empty((B, A, A, ws.h // 8, ws.w // 8), dtype=torch.float32, device=dev)
+            f.weights = weights.data_ptr()
+        else:
+            f.weights = None
+        ops.fusion_forward(f, stream)
+        for c in ws.dec_calls:
+            c.launch(stream)
+        result = self._run_heads(ws, stream)
+        # `trans`/`num_agent` are consumed by kernels already enqueued on this stream; the caching allocator
+        # keeps stream order, so releasing them here is safe.
+        if self.kd_flag == 1:
+            return (result, self._nchw(ws, "x8"), self._nchw(ws, "x7"), self._nchw(ws, "x6"), self._nchw(ws, "x5"),
+                    self._nchw(ws, "x3f"))
+        return result, AgentWeightList(weights, num_agent, bool(self.only_v2i))
+
+
+class _StpnModel(_DetBase):
+    """NonIntermediateModelBase.py:12-24: one STPN_KD backbone named `stpn`, no fusion."""
+
+    def __init__(self, config, layer=3, in_channels=13, kd_flag=True, num_agent=5, compress_level=0,
+                 precision: Optional[str] = None):
+        super().__init__(config, layer, in_channels, kd_flag, num_agent=num_agent, precision=precision)
+        self.stpn = BackboneParams(config.map_dims[2], compress_level)
+        self.compress_level = compress_level
+
+    def _build_plans(self, get):
+        p = self.precision
+        return {"enc": engine.build_encoder_plans(get, "stpn.", p, compress=self.compress_level > 0),
+                "dec": engine.build_decoder_plans(get, "stpn.", p),
+                "heads": engine.build_head_plans(get, p)}
+
+    def _workspace(self, n, h, w, device):
+        key = (n, h, w, str(device))
+        ws = self._ws.get(key)
+        if ws is None:
+            P = self.plans()
+            ws = engine.Workspace(n, h, w, self.precision, device, P["enc"], P["dec"], P["heads"], None)
+            self._ws[key] = ws
+        return ws
+
+    def _backbone(self, bevs):
+        self._check_inputs(bevs)
+        N, _, H, W, _ = bevs.shape
+        ws = self._workspace(N, H, W, bevs.device)
+        stream = torch.cuda.current_stream(bevs.device).cuda_stream
+        self._pack_input(bevs, ws)
+        for c in ws.enc_calls + ws.dec_calls:
+            c.launch(stream)
+        return ws, stream
+
+
+class FaFNet(_StpnModel):
+    """Early-fusion / no-fusion baseline (reference FaFNet.py:4-39); BASELINE config 1."""
+
+    def forward(self, bevs, maps=None, vis=None, batch_size=None):
+        ws, stream = self._backbone(bevs)
+        result = self._run_heads(ws, stream)
+        if self.kd_flag == 1:
+            return (result, self._nchw(ws, "x8"), self._nchw(ws, "x7"), self._nchw(ws, "x6"), self._nchw(ws, "x5"),
+                    self._nchw(ws, ws.x3_key))
+        return result
+
+
+class TeacherNet(_StpnModel):
+    """KD teacher (reference TeacherNet.py:4-13): returns (x_8, x_7, x_6, x_5, x_3, x_4)."""
+
+    def __init__(self, config, precision: Optional[str] = None):
+        super().__init__(config, compress_level=0, precision=precision)
+
+    def forward(self, bevs, maps=None, vis=None):
+        ws, _ = self._backbone(bevs)
+        return (self._nchw(ws, "x8"), self._nchw(ws, "x7"), self._nchw(ws, "x6"), self._nchw(ws, "x5"),
+                self._nchw(ws, ws.x3_key), self._nchw(ws, "x4"))

@@ -108,3 +108,64 @@ def act_to_nchw_f32(act: torch.Tensor, precision: int) -> torch.Tensor:
     check(load().disco_act_unpack_nchw(act.data_ptr(), _lo_off(act), precision, n, h, w, c, out.data_ptr(),
                                        _stream_ptr(act.device)), "act_unpack")
     return out
+
+
+class ConvCall:
+    """A prebuilt conv launch (descriptor filled once; only output pointers may be re-pointed)."""
+
+    def __init__(self, plan: ConvPlan, srcs, ups, out, *, n, h_in, w_in, out_split=None):
+        self.plan = plan
+        self.keep = (plan, list(srcs), out)   # keep tensors alive as long as the descriptor exists
+        d = ConvDesc()
+        _require_cuda(*srcs)
+        for i in range(2):
+            if i < len(srcs):
+                s = srcs[i]
+                d.src[i] = s.data_ptr()
+                d.src_lo_off[i] = _lo_off(s)
+                d.src_c[i] = s.shape[-1]
+                d.src_up[i] = int(ups[i])
+        if sum(s.shape[-1] for s in srcs) != plan.c_in:
+            raise ValueError(f"conv[{plan.name}]: sources {[tuple(s.shape) for s in srcs]} != c_in {plan.c_in}")
+        d.n, d.h_in, d.w_in = n, h_in, w_in
+        d.stride, d.taps, d.c_blk = plan.stride, plan.taps, plan.c_blk
+        d.h_out = (h_in - 1) // plan.stride + 1
+        d.w_out = (w_in - 1) // plan.stride + 1
+        d.c_out, d.block_n = plan.c_out, plan.block_n
+        d.wpack = plan.wpack.data_ptr()
+        d.wref = plan.wref.data_ptr() if plan.wref is not None else None
+        d.bias = plan.bias.data_ptr()
+        d.relu = int(plan.relu)
+        d.precision = plan.precision
+        self.desc = d
+        self.flops = plan.flops_per_pixel * n * d.h_out * d.w_out
+        self.set_output(out, out_split)
+        self._fn = load().disco_conv_forward
+        self._ref = load().disco_conv_reference
+
+    def set_output(self, out, out_split=None):
+        d = self.desc
+        if isinstance(out, torch.Tensor) and out.dtype in (torch.bfloat16, torch.float16):
+            _require_cuda(out)
+            if out.shape[-1] != self.plan.c_out:
+                raise ValueError(f"conv[{self.plan.name}]: output channels {out.shape[-1]} != {self.plan.c_out}")
+            d.out_mode = OUT_ACT
+            d.out[0] = out.data_ptr()
+            d.out[1] = None
+            d.out_lo_off = _lo_off(out)
+            d.out_split = self.plan.c_out
+        else:
+            outs = out if isinstance(out, (tuple, list)) else (out,)
+            _require_cuda(*outs)
+            d.out_mode = OUT_F32
+            d.out[0] = outs[0].data_ptr()
+            d.out[1] = outs[1].data_ptr() if len(outs) > 1 else None
+            d.out_lo_off = 0
+            d.out_split = self.plan.c_out if out_split is None else out_split
+
+    def launch(self, stream_ptr: int, reference: bool = False):
+        check((self._ref if reference else self._fn)(C.byref(self.desc), stream_ptr), f"conv[{self.plan.name}]")
+
+
+def fusion_forward(desc: FusionDesc, stream_ptr: int):
+    check(load().disco_fusion_forward(C.byref(desc), stream_ptr), "fusion")

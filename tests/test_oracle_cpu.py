@@ -1,0 +1,196 @@
+"""CPU suite: the oracle restatement against the golden fixtures generated from the live reference,
+the host-side logic (BN folding, operand packing, state_dict layout) and the C-ABI surface."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import disconet_oracle as O
+from oracle import voxel_oracle as V
+from oracle.make_golden import DISCO_CASES, STRIDES, golden_case_inputs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+class _Cfg:
+    """The fields of coperception Config the model constructors read (Config.py:70-177 defaults)."""
+    motion_state = False
+    only_det = True
+    pred_len = 1
+    box_code_size = 6
+    category_num = 2
+    use_map = False
+    use_vis = False
+    binary = True
+    anchor_size = np.zeros((6, 3))
+    map_dims = [256, 256, 13]
+
+
+def _template(case_name):
+    with open(os.path.join(GOLD, "state_dict_keys.json")) as f:
+        keys = json.load(f)[case_name]
+    return {k: torch.empty(shape) for k, shape in keys}
+
+
+def _check_sub(name, t, rec, key, tol=2e-5, stride=None):
+    f = t.detach().reshape(-1).double()
+    sub = f[::(stride or STRIDES[key])].float().numpy()
+    ref = rec[key + "_sub"]
+    assert sub.shape == ref.shape, (name, key)
+    scale = rec[key + "_stats"][2]
+    assert np.abs(sub - ref).max() <= tol * scale, f"{name}.{key}: {np.abs(sub - ref).max() / scale:.2e}"
+    st = rec[key + "_stats"]
+    assert abs(f.abs().sum().item() - st[1]) <= 1e-4 * st[1]
+    assert list(t.shape) == list(rec[key + "_shape"])
+
+
+@pytest.mark.parametrize("name", list(DISCO_CASES))
+def test_oracle_matches_reference_golden(name):
+    case = DISCO_CASES[name]
+    rec = np.load(os.path.join(GOLD, name + ".npz"))
+    sd, bev, T, na = golden_case_inputs(case, _template(name))
+    out = O.disconet_forward(sd, bev, T, na, case["B"], agent_num=case["A"], only_v2i=case["only_v2i"],
+                             return_all=True)
+    _check_sub(name, out["cls"], rec, "cls")
+    _check_sub(name, out["loc"], rec, "loc")
+    if case["kd_flag"] == 1:
+        for k in ("x_8", "x_7", "x_6", "x_5", "fused"):
+            _check_sub(name, out[k], rec, k)
+    else:
+        wl = [e for per_b in out["weights"] for e in per_b]
+        assert [len(wl)] + [len(e) for e in wl] == rec["n_weight_entries"].tolist()
+        cat = torch.cat([torch.stack(e).reshape(-1) for e in wl]).numpy()[::37]
+        assert np.abs(cat - rec["weights_cat"]).max() < 1e-5
+
+
+def test_oracle_fafnet_golden():
+    rec = np.load(os.path.join(GOLD, "fafnet_a2_128.npz"))
+    sd = O.synth_state_dict(_template("fafnet_a2_128"), seed=21)
+    out = O.fafnet_forward(sd, O.synth_bev(2, H=128, W=128, seed=121))
+    for k in ("cls", "loc"):
+        _check_sub("fafnet", out[k], rec, k, stride=97)
+
+
+def test_voxel_oracle_bit_exact_vs_reference_golden():
+    rec = np.load(os.path.join(GOLD, "voxel.npz"))
+    cases = [("veh", V.synth_points(1, 40000), V.EXTENTS), ("rsu", V.synth_points(0, 30000, rsu=True), V.EXTENTS_RSU),
+             ("tiny", V.synth_points(3, 7), V.EXTENTS), ("xyz_only", V.synth_points(2, 5000)[:, :3], V.EXTENTS),
+             ("edge", rec["edge_pts"], V.EXTENTS)]
+    for tag, pts, ext in cases:
+        grid, idx = V.voxelize_occupy(pts, V.VOXEL_SIZE, ext)
+        assert np.array_equal(idx.astype(np.int32), rec[tag + "_idx"]), tag
+        if tag + "_grid_sum" in rec:
+            assert grid.sum() == rec[tag + "_grid_sum"][0] and list(grid.shape) == rec[tag + "_grid_sum"][1:].tolist()
+            bev = V.bev_scatter(idx, grid.shape)
+            assert np.array_equal(np.argwhere(bev > 0).astype(np.int16), rec[tag + "_bev_nz"]), tag
+    # empty cloud and all-out-of-range cloud
+    g, i = V.voxelize_occupy(np.zeros((0, 4), np.float32), V.VOXEL_SIZE, V.EXTENTS)
+    assert g.sum() == 0 and i.shape == (0, 3)
+    g, i = V.voxelize_occupy(np.full((5, 4), 100.0, np.float32), V.VOXEL_SIZE, V.EXTENTS)
+    assert g.sum() == 0 and i.shape == (0, 3)
+
+
+# ------------------------------------------------------------------------------------------------------
+# host logic of the product package (no GPU needed)
+# ------------------------------------------------------------------------------------------------------
+def test_state_dict_layout_matches_reference():
+    from disconet_b200 import DiscoNet, FaFNet, TeacherNet
+    with open(os.path.join(GOLD, "state_dict_keys.json")) as f:
+        keys = json.load(f)
+    cfg = _Cfg()
+    for name, case in DISCO_CASES.items():
+        m = DiscoNet(cfg, layer=3, kd_flag=case["kd_flag"], num_agent=case["A"], compress_level=case["compress_level"],
+                     only_v2i=case["only_v2i"])
+        got = [[k, list(v.shape)] for k, v in m.state_dict().items()]
+        assert got == keys[name], name
+    assert [[k, list(v.shape)] for k, v in FaFNet(cfg, kd_flag=0, num_agent=2).state_dict().items()] == keys["fafnet_a2_128"]
+    assert [[k, list(v.shape)] for k, v in TeacherNet(cfg).state_dict().items()] == keys["teacher"]
+    # DataParallel-style "module." prefixed checkpoints load through nn.DataParallel (test_codet.py:164,194)
+    m = DiscoNet(cfg, kd_flag=0, num_agent=2)
+    sd = {"module." + k: v for k, v in m.state_dict().items()}
+    torch.nn.DataParallel(m).load_state_dict(sd)
+
+
+def test_fold_bn_and_pack_roundtrip():
+    from disconet_b200._lib import PREC_BF16X3, PREC_FP16
+    from disconet_b200.plan import fold_bn, pack_conv
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(48, 40, 3, 3, generator=g)
+    b = torch.randn(48, generator=g)
+    bn = [torch.rand(48, generator=g) + 0.5, torch.randn(48, generator=g), torch.randn(48, generator=g),
+          torch.rand(48, generator=g) + 0.5]
+    wf, bf = fold_bn(w, b, *bn)
+    x = torch.randn(2, 40, 9, 9, generator=g)
+    ref = torch.nn.functional.batch_norm(torch.nn.functional.conv2d(x, w, b, padding=1), bn[2], bn[3], bn[0], bn[1],
+                                         False, 0.0, 1e-5)
+    got = torch.nn.functional.conv2d(x, wf, bf, padding=1)
+    assert (got - ref).abs().max() < 1e-4
+    wpad = torch.zeros(48, 48, 3, 3)
+    wpad[:, :40] = wf
+    for prec in (PREC_FP16, PREC_BF16X3):
+        plan = pack_conv(wpad, bf, src_channels=[32, 16], precision=prec, block_n=32, keep_ref=True)
+        assert plan.c_blk == 16 and plan.block_n == 32 and plan.bias.numel() == 64
+        parts = 2 if prec == PREC_BF16X3 else 1
+        dt = torch.bfloat16 if prec == PREC_BF16X3 else torch.float16
+        wp = plan.wpack.view(dt).view(2, 3, 9, parts, 2, 32, 8).float().sum(3)   # [nt, cb, tap, chunk, n, 8]
+        dec = wp.permute(0, 4, 1, 3, 5, 2).reshape(64, 48, 9)                      # [n, c_in, tap]
+        tol = (2.0 ** -16 if prec == PREC_BF16X3 else 2.0 ** -10) * wpad.abs().max().item()
+        assert (dec[:48] - wpad.reshape(48, 48, 9)).abs().max() < tol
+        assert dec[48:].abs().max() == 0
+        assert torch.equal(plan.wref, wpad.reshape(48, 48, 9).permute(0, 2, 1))
+
+
+def test_agent_weight_list_order():
+    from disconet_b200.det import AgentWeightList
+    B, A, h, w = 2, 3, 4, 4
+    wt = torch.arange(B * A * A, dtype=torch.float32).view(B, A, A, 1, 1).expand(B, A, A, h, w).contiguous()
+    wl = AgentWeightList(wt, torch.tensor([3, 2], dtype=torch.int32), only_v2i=False)
+    assert len(wl) == 5
+    # scene 0, ego 1 -> neighbours [1, 0, 2]
+    assert [int(t[0, 0]) for t in wl[1]] == [0 * 9 + 1 * 3 + 1, 0 * 9 + 1 * 3 + 0, 0 * 9 + 1 * 3 + 2]
+    # scene 1 has 2 agents: ego 0 -> [0, 1]
+    assert [int(t[0, 0]) for t in wl[3]] == [9 + 0, 9 + 1]
+    wl = AgentWeightList(wt, torch.tensor([3, 3], dtype=torch.int32), only_v2i=True)
+    assert [int(t[0, 0]) for t in wl[1]] == [4, 3]      # ego 1 only hears the RSU (agent 0)
+    assert [int(t[0, 0]) for t in wl[0]] == [0, 1, 2]   # the RSU hears everyone
+
+
+def test_no_cpu_fallback_and_train_mode_raises():
+    from disconet_b200 import DiscoNet
+    m = DiscoNet(_Cfg(), kd_flag=0, num_agent=2)
+    bev = torch.zeros(2, 1, 32, 32, 13)
+    with pytest.raises(NotImplementedError):
+        m.train()(bev, torch.zeros(1, 2, 2, 4, 4), torch.ones(1, 2, dtype=torch.int64), batch_size=1)
+    with pytest.raises(ValueError, match="CUDA"):
+        m.eval()(bev, torch.zeros(1, 2, 2, 4, 4), torch.ones(1, 2, dtype=torch.int64), batch_size=1)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from disconet_b200 import _lib
+    with open(os.path.join(ROOT, "include", "disco_b200.h")) as f:
+        declared = set(re.findall(r"^int\s+(disco_\w+)\s*\(", f.read(), flags=re.M))
+    assert declared and declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.disco_version() >= 100
+    # struct layouts agree with the header (field order + count)
+    with open(os.path.join(ROOT, "include", "disco_b200.h")) as f:
+        hdr = f.read()
+    for struct, cls in (("disco_conv_desc", _lib.ConvDesc), ("disco_fusion_desc", _lib.FusionDesc)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), hdr, flags=re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            first, *rest = decl.split(",")
+            names.append(re.findall(r"(\w+)(?:\[\d+\])?$", first.strip())[0])
+            names += [re.findall(r"(\w+)", r)[0] for r in rest]
+        assert names == [f[0] for f in cls._fields_], (struct, names)
