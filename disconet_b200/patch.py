@@ -1,0 +1,33 @@
+"""Swap the reference's model classes for the B200-native ones without touching the reference tree.
+
+    import disconet_b200.patch as p; p.patch_coperception()
+    # or run an unmodified reference tool:
+    python -m disconet_b200.patch /path/to/coperception/tools/det/test_codet.py --com disco ...
+
+`tools/det/train_codet.py:12` / `test_codet.py:14` do `from coperception.models.det import *`, so the
+classes are replaced on the already-imported `coperception.models.det` package before the tool runs.
+"""
+from __future__ import annotations
+
+import importlib
+import runpy
+import sys
+
+
+def patch_coperception(classes=("DiscoNet", "FaFNet", "TeacherNet")) -> None:
+    from . import det as ours
+    pkg = importlib.import_module("coperception.models.det")
+    for name in classes:
+        setattr(pkg, name, getattr(ours, name))
+        sub = sys.modules.get(f"coperception.models.det.{name}")
+        if sub is not None:
+            setattr(sub, name, getattr(ours, name))
+
+
+if __name__ == "__main__":
+    if len(sys.argv) < 2:
+        raise SystemExit("usage: python -m disconet_b200.patch <reference tool .py> [tool args...]")
+    patch_coperception()
+    tool = sys.argv[1]
+    sys.argv = sys.argv[1:]
+    runpy.run_path(tool, run_name="__main__")
