@@ -1,55 +1,72 @@
-// Implicit-GEMM 3x3 / 1x1 convolution on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators).
+// Persistent, warp-specialised implicit-GEMM 3x3 / 1x1 convolution on the 5th-gen tensor cores
+// (tcgen05.mma, TMEM accumulators) for sm_100a.
 //
 // Replaces, for the DiscoNet hot path, every F.conv2d/conv3d + BatchNorm(eval) + ReLU of the reference
 // (Backbone.py:102-136 encode, :173-237 decode incl. the nearest-x2 upsample + channel concat on the
 // *load* side, DetModelBase.py:283-351 heads, DiscoNet.py:148 PWF conv1_1) -- BN is folded into the
 // packed weights / bias on the host (disconet_b200/plan.py).
 //
-// One CTA computes a 128-pixel x block_n-channel output tile:
-//   M = 128 output pixels = 16 rows x 8 cols of one image (or 128 consecutive pixels for 1x1)
-//   N = block_n output channels (<= 256), K = taps * C_in, fp32 accumulation in TMEM.
+// Work item = (n_tile, m_tile): MSUB x 128 output pixels (MSUB sub-tiles of 16 rows x 8 cols of one
+// image, side by side; or 128 consecutive pixels each for 1x1) x block_n output channels,
+// K = taps * C_in, fp32 accumulation in TMEM.  One CTA per SM loops over its items (static
+// round-robin), so barrier set-up, TMEM allocation and pipeline fill are paid once per launch and the
+// gather of item i+1 / epilogue of item i-1 overlap the MMAs of item i:
 //
-// Data staging (this is the B200-specific part):
-//   * A operand: the input patch needed by the tile (18x10 pixels for 3x3/s1, 33x17 for s2) is
-//     gathered ONCE per channel block into shared memory in the UMMA "no-swizzle K-major" layout
-//     [channel/8][pixel][8 ch] (16-byte core-matrix rows).  In that layout a filter tap (kh,kw) is
-//     just a different 16-byte-aligned *start address* of the same patch, so the nine taps reuse one
-//     staged patch: L2->SMEM traffic for activations is ~1.4x the input instead of 9x.
-//     Stride-2 convs de-interleave even/odd columns into two sub-planes at gather time so the 8 rows
-//     of a core matrix stay 16 B apart.  Nearest-upsample + concat are address arithmetic in the
-//     gather (src_up / two sources), zero padding is cp.async zero-fill.
-//   * B operand: host-packed weight images, one contiguous block per (channel block, tap), streamed
-//     by the bulk-copy (TMA) engine (cp.async.bulk + mbarrier complete_tx).
-//   * Warp roles: warps 0-3 gather A (cp.async) then run the epilogue (tcgen05.ld -> bias/ReLU ->
-//     16-bit hi[/lo] or fp32 stores); warp 4 streams B; warp 5 allocates TMEM and issues the MMAs.
+//   warps 0-3  epilogue: tcgen05.ld accumulator -> bias/ReLU -> 16-bit hi[/lo] or fp32 16-byte stores,
+//              then release the accumulator buffer (TMEM is double buffered: 2 x MSUB x block_n cols)
+//   warps 4-7  A producers, one *stage per warp* in flight (4 independent cp.async streams):
+//              the input patch of a sub-tile (18x10 px for 3x3/s1, 33x17 for s2) is gathered ONCE per
+//              channel block into shared memory in the UMMA "no-swizzle K-major" layout
+//              [channel/8][pixel][8 ch] (16-byte core-matrix rows).  In that layout a filter tap (kh,kw)
+//              is just a different 16-byte-aligned descriptor start address, so the nine taps reuse one
+//              staged patch (L2->SMEM activation traffic ~1.4x the input instead of 9x).  Stride-2
+//              convs de-interleave even/odd columns into two sub-planes; nearest-upsample + concat are
+//              address arithmetic (src_up / two sources); zero padding is cp.async zero-fill.
+//   warp 8     B loader (bulk-copy/TMA engine, cp.async.bulk + mbarrier complete_tx): host-packed
+//              weight images, one contiguous block per (channel block, tap).  If the whole weight set
+//              of the n_tile fits next to the A stages it is loaded ONCE and stays resident
+//              ("stationary": all C_out<=64 layers); otherwise it is streamed through a ring, and
+//              MSUB=2 halves that stream per MAC.
+//   warp 9     TMEM allocation + single-thread MMA issue; tcgen05.commit releases smem stages and
+//              publishes accumulators.
 //
 // precision DISCO_PREC_BF16X3 keeps activations/weights as bf16 hi+lo pairs and issues three MMAs
 // per k-step (hi*hi + lo*hi + hi*lo) -> ~16 mantissa bits, which is what the <=1e-3 parity gate
-// against the fp32 reference needs (plain fp16/bf16 operands measure 2.5e-3 / 2e-2).
+// against the fp32 reference needs (plain fp16 operands measure 2-3e-3).
 #include "common.cuh"
 #include "conv.h"
 
 namespace {
 
-constexpr int kProducerThreads = 128;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 4, kProdWarps = 4;
+constexpr int kThreads = (kEpiWarps + kProdWarps + 2) * 32;  // 320
 constexpr int kMaxStages = 8;
+constexpr int kCtlBytes = 512;
 
 struct ConvGeom {
     disco_conv_desc d;
     int ncb, ncb0;            // K stages total / from source 0
     int chunks, chunk_shift;  // c_blk/8
     int nparts;               // 1 (fp16) | 2 (bf16 hi+lo)
-    int PH, PW, PIX;          // staged patch (rows, cols, pixels)
+    int PIX;                  // staged patch pixels per sub-tile
     int plane, parplane;      // bytes
     int a_part_bytes, a_stage_bytes;
     int b_part_bytes, b_stage_bytes;
     int SA, SB;
     int sbo_a;
+    int msub;                 // 128-pixel sub-tiles per item (1|2)
+    int nacc;                 // accumulator buffers in TMEM (1|2)
+    int acc_stride;           // TMEM columns per accumulator (block_n rounded up to 32)
+    int nprod;                // active producer warps: min(4, SA) (a ring with fewer slots than independent
+                              // producers would let one warp lap another through the parity alias)
+    int stationary;           // weights resident in smem
+    int w_bytes;              // stationary: bytes of one n_tile's weights
     int tiles_h, tiles_w;
+    int m_tiles, n_tiles, items;
     long long total_pix;      // n*h_out*w_out
     int tmem_cols;
     int smem_bytes;
+    int grid;
 };
 
 struct __align__(8) SmemCtl {
@@ -57,12 +74,15 @@ struct __align__(8) SmemCtl {
     uint64_t a_empty[kMaxStages];
     uint64_t b_full[kMaxStages];
     uint64_t b_empty[kMaxStages];
-    uint64_t acc_full;
+    uint64_t acc_full[2];
+    uint64_t acc_empty[2];
+    uint64_t w_full;
     uint32_t tmem_base;
     uint32_t pad;
 };
+static_assert(sizeof(SmemCtl) <= kCtlBytes, "control block");
 
-__device__ __forceinline__ uint4 pack_bf16_hi8(const float* v) {
+__device__ __forceinline__ uint4 pack_bf16x8(const float* v) {
     uint32_t w[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -70,47 +90,65 @@ __device__ __forceinline__ uint4 pack_bf16_hi8(const float* v) {
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvGeom g) {
+struct Item {
+    int n_tile, img, h0, w0;
+    long long p0;
+};
+
+template <int MODE>
+__device__ __forceinline__ Item decode_item(const ConvGeom& g, int item) {
+    Item it;
+    it.n_tile = item / g.m_tiles;  // n-major: concurrently running CTAs stream the same weights
+    const int m_tile = item - it.n_tile * g.m_tiles;
+    it.img = 0; it.h0 = 0; it.w0 = 0; it.p0 = 0;
+    if (MODE != 2) {
+        const int per_img = g.tiles_h * g.tiles_w;
+        it.img = m_tile / per_img;
+        const int rem = m_tile - it.img * per_img;
+        const int th = rem / g.tiles_w;
+        it.h0 = th * 16;
+        it.w0 = (rem - th * g.tiles_w) * 8 * g.msub;
+    } else {
+        it.p0 = (long long)m_tile * 128 * g.msub;
+    }
+    return it;
+}
+
+// MODE 0: 3x3 stride 1 (patch 18x10) | MODE 1: 3x3 stride 2 (patch 33x17) | MODE 2: 1x1
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_raw);
     const uint32_t smem_base = smem_u32(smem_raw);
-    const uint32_t a_base = smem_base + 384;  // SmemCtl (272 B) rounded up to 128-byte multiple
+    const uint32_t a_base = smem_base + kCtlBytes;
     const uint32_t b_base = a_base + g.SA * g.a_stage_bytes;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
     const disco_conv_desc& d = g.d;
-
-    // ---- tile coordinates --------------------------------------------------------------------
-    const int m_tile = blockIdx.x;
-    const int n_tile = blockIdx.y;
-    int img = 0, h0 = 0, w0 = 0;
-    long long p0 = 0;
-    if (d.taps == 9) {
-        const int per_img = g.tiles_h * g.tiles_w;
-        img = m_tile / per_img;
-        const int rem = m_tile - img * per_img;
-        h0 = (rem / g.tiles_w) * 16;
-        w0 = (rem % g.tiles_w) * 8;
-    } else {
-        p0 = (long long)m_tile * 128;
-    }
+    constexpr int PW = (MODE == 0) ? 10 : (MODE == 1) ? 17 : 128;
+    constexpr int TAPS = (MODE == 2) ? 1 : 9;
+    constexpr int STRIDE = (MODE == 1) ? 2 : 1;
 
     // ---- one-time setup ------------------------------------------------------------------------
     if (tid == 0) {
         for (int s = 0; s < g.SA; ++s) {
-            mbar_init(smem_u32(&ctl->a_full[s]), kProducerThreads);
+            mbar_init(smem_u32(&ctl->a_full[s]), 32);
             mbar_init(smem_u32(&ctl->a_empty[s]), 1);
         }
         for (int s = 0; s < g.SB; ++s) {
             mbar_init(smem_u32(&ctl->b_full[s]), 1);
             mbar_init(smem_u32(&ctl->b_empty[s]), 1);
         }
-        mbar_init(smem_u32(&ctl->acc_full), 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&ctl->acc_full[s]), 1);
+            mbar_init(smem_u32(&ctl->acc_empty[s]), kEpiWarps * 32);
+        }
+        mbar_init(smem_u32(&ctl->w_full), 1);
         fence_mbar_init();
     }
-    if (warp == 5) {
+    if (warp == 9) {
         tmem_alloc(smem_u32(&ctl->tmem_base), (uint32_t)g.tmem_cols);
         tmem_relinquish();
     }
@@ -118,134 +156,166 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvGeom g) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = ctl->tmem_base;
+    const int stages_per_item = g.ncb * g.msub;
 
-    const int n_iters_b = g.ncb * d.taps;
-
-    if (warp < 4) {
-        // =========================== A producer (gather) ==========================================
-        const int per_part = g.PIX << g.chunk_shift;
-        for (int cb = 0; cb < g.ncb; ++cb) {
-            const int sa = cb % g.SA;
-            const uint32_t ph = (uint32_t)(cb / g.SA) & 1u;
-            mbar_wait(smem_u32(&ctl->a_empty[sa]), ph ^ 1u);
-            const int s = (cb < g.ncb0) ? 0 : 1;
-            const int cbl = (s == 0) ? cb : cb - g.ncb0;
-            const uint16_t* __restrict__ src = reinterpret_cast<const uint16_t*>(s ? d.src[1] : d.src[0]);
-            const int Cs = s ? d.src_c[1] : d.src_c[0];
-            const int up = s ? d.src_up[1] : d.src_up[0];
-            const int Hs = d.h_in >> up, Ws = d.w_in >> up;
-            const long long lo_off = s ? d.src_lo_off[1] : d.src_lo_off[0];
-            const uint32_t stage = a_base + sa * g.a_stage_bytes;
-            const int cofs = cbl * d.c_blk;
-            for (int e = tid; e < per_part; e += kProducerThreads) {
-                const int chunk = e & (g.chunks - 1);
-                const int pix = e >> g.chunk_shift;
-                long long goff;
-                uint32_t soff;
-                bool valid;
-                if (d.taps == 9) {
-                    const int r = pix / g.PW;
-                    const int c = pix - r * g.PW;
-                    const int hi = h0 * d.stride - 1 + r;
-                    const int wi = w0 * d.stride - 1 + c;
-                    valid = (hi >= 0) && (hi < d.h_in) && (wi >= 0) && (wi < d.w_in);
-                    goff = (((long long)img * Hs + (hi >> up)) * Ws + (wi >> up)) * Cs + cofs + chunk * 8;
-                    if (d.stride == 1) soff = (uint32_t)(r * 10 + c) * 16u;
-                    else soff = (uint32_t)(c & 1) * g.parplane + (uint32_t)(r * 9 + (c >> 1)) * 16u;
-                } else {
-                    const long long p = p0 + pix;
-                    valid = p < g.total_pix;
-                    goff = p * Cs + cofs + chunk * 8;
-                    soff = (uint32_t)pix * 16u;
-                }
-                const uint32_t dst = stage + chunk * g.plane + soff;
-                const uint16_t* gp = valid ? (src + goff) : src;
-                cp_async16(dst, gp, valid ? 16u : 0u);
-                if (g.nparts == 2) cp_async16(dst + g.a_part_bytes, valid ? (gp + lo_off) : src, valid ? 16u : 0u);
-            }
-            cp_async_commit();
-            if (cb >= 1) {  // keep one gather in flight while publishing the previous one
-                cp_async_wait<1>();
-                fence_proxy_async_smem();
-                mbar_arrive(smem_u32(&ctl->a_full[(cb - 1) % g.SA]));
-            }
-        }
-        cp_async_wait<0>();
-        fence_proxy_async_smem();
-        mbar_arrive(smem_u32(&ctl->a_full[(g.ncb - 1) % g.SA]));
-
+    if (warp < kEpiWarps) {
         // =========================== epilogue =====================================================
-        mbar_wait(smem_u32(&ctl->acc_full), 0);
-        tc_fence_after();
-        const int m = warp * 32 + lane;
-        bool valid;
-        long long pixel;
-        if (d.taps == 9) {
-            const int oh = h0 + (m >> 3), ow = w0 + (m & 7);
-            valid = (oh < d.h_out) && (ow < d.w_out);
-            pixel = ((long long)img * d.h_out + oh) * d.w_out + ow;
-        } else {
-            pixel = p0 + m;
-            valid = pixel < g.total_pix;
-        }
-        const uint32_t t_lane = tmem_d + ((uint32_t)(warp * 32) << 16);
-        for (int j = 0; j < d.block_n / 16; ++j) {
-            uint32_t raw[16];
-            tmem_ld16(t_lane + (uint32_t)(j * 16), raw);
-            tmem_ld_wait();
-            const int nb = n_tile * d.block_n + j * 16;
-            float v[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                float x = __uint_as_float(raw[i]) + __ldg(d.bias + nb + i);
-                v[i] = d.relu ? fmaxf(x, 0.f) : x;
-            }
-            // stores are predicated per lane; the tcgen05.ld above must stay warp-convergent
-            if (valid && d.out_mode == DISCO_OUT_ACT && nb < d.c_out) {
-                uint16_t* oh_ = reinterpret_cast<uint16_t*>(d.out[0]) + pixel * d.c_out + nb;
-                if (d.precision == DISCO_PREC_BF16X3) {
-                    float lo[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) lo[i] = v[i] - bf16_bits_to_f32(f32_to_bf16_bits(v[i]));
-                    reinterpret_cast<uint4*>(oh_)[0] = pack_bf16_hi8(v);
-                    reinterpret_cast<uint4*>(oh_)[1] = pack_bf16_hi8(v + 8);
-                    uint16_t* ol_ = oh_ + d.out_lo_off;
-                    reinterpret_cast<uint4*>(ol_)[0] = pack_bf16_hi8(lo);
-                    reinterpret_cast<uint4*>(ol_)[1] = pack_bf16_hi8(lo + 8);
+        int iacc = 0;
+        for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++iacc) {
+            const Item it = decode_item<MODE>(g, item);
+            const int buf = iacc % g.nacc;
+            mbar_wait(smem_u32(&ctl->acc_full[buf]), (uint32_t)(iacc / g.nacc) & 1u);
+            tc_fence_after();
+            const int m = warp * 32 + lane;
+            for (int sub = 0; sub < g.msub; ++sub) {
+                bool valid;
+                long long pixel;
+                if (MODE != 2) {
+                    const int oh = it.h0 + (m >> 3), ow = it.w0 + sub * 8 + (m & 7);
+                    valid = (oh < d.h_out) && (ow < d.w_out);
+                    pixel = ((long long)it.img * d.h_out + oh) * d.w_out + ow;
                 } else {
-                    uint32_t w[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        w[i] = (uint32_t)f32_to_f16_bits(v[2 * i]) | ((uint32_t)f32_to_f16_bits(v[2 * i + 1]) << 16);
-                    reinterpret_cast<uint4*>(oh_)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                    reinterpret_cast<uint4*>(oh_)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                    pixel = it.p0 + sub * 128 + m;
+                    valid = pixel < g.total_pix;
                 }
-            } else if (valid && d.out_mode == DISCO_OUT_F32) {
-                const int c1 = d.c_out - d.out_split;
+                const uint32_t t_lane = tmem_d + ((uint32_t)(warp * 32) << 16) +
+                                        (uint32_t)((buf * g.msub + sub) * g.acc_stride);
+                for (int j = 0; j < d.block_n / 16; ++j) {
+                    uint32_t raw[16];
+                    tmem_ld16(t_lane + (uint32_t)(j * 16), raw);
+                    tmem_ld_wait();
+                    const int nb = it.n_tile * d.block_n + j * 16;
+                    float v[16];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int c = nb + 4 * q;
-                    if (c >= d.c_out) continue;
-                    float* dst = (c < d.out_split)
-                                     ? reinterpret_cast<float*>(d.out[0]) + pixel * d.out_split + c
-                                     : reinterpret_cast<float*>(d.out[1]) + pixel * c1 + (c - d.out_split);
-                    *reinterpret_cast<float4*>(dst) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    for (int i = 0; i < 16; ++i) {
+                        const float x = __uint_as_float(raw[i]) + __ldg(d.bias + nb + i);
+                        v[i] = d.relu ? fmaxf(x, 0.f) : x;
+                    }
+                    // stores are predicated per lane; the tcgen05.ld above must stay warp-convergent
+                    if (valid && d.out_mode == DISCO_OUT_ACT && nb < d.c_out) {
+                        uint16_t* oh_ = reinterpret_cast<uint16_t*>(d.out[0]) + pixel * d.c_out + nb;
+                        if (d.precision == DISCO_PREC_BF16X3) {
+                            float lo[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) lo[i] = v[i] - bf16_bits_to_f32(f32_to_bf16_bits(v[i]));
+                            reinterpret_cast<uint4*>(oh_)[0] = pack_bf16x8(v);
+                            reinterpret_cast<uint4*>(oh_)[1] = pack_bf16x8(v + 8);
+                            uint16_t* ol_ = oh_ + d.out_lo_off;
+                            reinterpret_cast<uint4*>(ol_)[0] = pack_bf16x8(lo);
+                            reinterpret_cast<uint4*>(ol_)[1] = pack_bf16x8(lo + 8);
+                        } else {
+                            uint32_t w[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                w[i] = (uint32_t)f32_to_f16_bits(v[2 * i]) |
+                                       ((uint32_t)f32_to_f16_bits(v[2 * i + 1]) << 16);
+                            reinterpret_cast<uint4*>(oh_)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                            reinterpret_cast<uint4*>(oh_)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                        }
+                    } else if (valid && d.out_mode == DISCO_OUT_F32) {
+                        const int c1 = d.c_out - d.out_split;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int c = nb + 4 * q;
+                            if (c >= d.c_out) continue;
+                            float* dst = (c < d.out_split)
+                                             ? reinterpret_cast<float*>(d.out[0]) + pixel * d.out_split + c
+                                             : reinterpret_cast<float*>(d.out[1]) + pixel * c1 + (c - d.out_split);
+                            *reinterpret_cast<float4*>(dst) =
+                                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        }
+                    }
                 }
             }
+            tc_fence_before();
+            mbar_arrive(smem_u32(&ctl->acc_empty[buf]));
         }
-    } else if (warp == 4) {
+    } else if (warp < kEpiWarps + kProdWarps) {
+        // =========================== A producers: warp p owns stages p, p+4, p+8, ... ===============
+        const int pw = warp - kEpiWarps;
+        const int per_part = g.PIX << g.chunk_shift;
+        int ia_base = 0;  // global stage index of the first stage of the current item
+        for (int item = blockIdx.x; item < g.items; item += gridDim.x, ia_base += stages_per_item) {
+            const Item it = decode_item<MODE>(g, item);
+            if (pw >= g.nprod) break;
+            // first local stage s (0 <= s < stages_per_item) with (ia_base + s) % nprod == pw
+            const int s0 = (pw - (ia_base % g.nprod) + g.nprod) % g.nprod;
+            for (int s = s0; s < stages_per_item; s += g.nprod) {
+                const int ia = ia_base + s;
+                const int cb = s / g.msub, sub = s - cb * g.msub;
+                const int sa = ia % g.SA;
+                mbar_wait(smem_u32(&ctl->a_empty[sa]), ((uint32_t)(ia / g.SA) & 1u) ^ 1u);
+                const int sidx = (cb < g.ncb0) ? 0 : 1;
+                const int cbl = sidx ? cb - g.ncb0 : cb;
+                const uint16_t* __restrict__ src = reinterpret_cast<const uint16_t*>(sidx ? d.src[1] : d.src[0]);
+                const int Cs = sidx ? d.src_c[1] : d.src_c[0];
+                const int up = sidx ? d.src_up[1] : d.src_up[0];
+                const int Hs = d.h_in >> up, Ws = d.w_in >> up;
+                const long long lo_off = sidx ? d.src_lo_off[1] : d.src_lo_off[0];
+                const uint32_t stage = a_base + sa * g.a_stage_bytes;
+                const int cofs = cbl * d.c_blk;
+                const int hi0 = it.h0 * STRIDE - 1, wi0 = (it.w0 + sub * 8) * STRIDE - 1;
+                const long long pbase = it.p0 + sub * 128;
+                for (int e = lane; e < per_part; e += 32) {
+                    const int chunk = e & (g.chunks - 1);
+                    const int pix = e >> g.chunk_shift;
+                    long long goff;
+                    uint32_t soff;
+                    bool valid;
+                    if (MODE != 2) {
+                        const int r = pix / PW;
+                        const int c = pix - r * PW;
+                        const int hi = hi0 + r, wi = wi0 + c;
+                        valid = (hi >= 0) && (hi < d.h_in) && (wi >= 0) && (wi < d.w_in);
+                        goff = (((long long)it.img * Hs + (hi >> up)) * Ws + (wi >> up)) * Cs + cofs + chunk * 8;
+                        if (MODE == 0) soff = (uint32_t)(r * 10 + c) * 16u;
+                        else soff = (uint32_t)(c & 1) * g.parplane + (uint32_t)(r * 9 + (c >> 1)) * 16u;
+                    } else {
+                        const long long p = pbase + pix;
+                        valid = p < g.total_pix;
+                        goff = p * Cs + cofs + chunk * 8;
+                        soff = (uint32_t)pix * 16u;
+                    }
+                    const uint32_t dst = stage + chunk * g.plane + soff;
+                    const uint16_t* gp = valid ? (src + goff) : src;
+                    cp_async16(dst, gp, valid ? 16u : 0u);
+                    if (g.nparts == 2)
+                        cp_async16(dst + g.a_part_bytes, valid ? (gp + lo_off) : src, valid ? 16u : 0u);
+                }
+                cp_async_commit();
+                cp_async_wait<0>();
+                fence_proxy_async_smem();
+                mbar_arrive(smem_u32(&ctl->a_full[sa]));
+            }
+        }
+    } else if (warp == 8) {
         // =========================== B loader (bulk copy engine) ===================================
         if (lane == 0) {
-            const uint8_t* wp = reinterpret_cast<const uint8_t*>(d.wpack) +
-                                (size_t)n_tile * n_iters_b * g.b_stage_bytes;
-            for (int it = 0; it < n_iters_b; ++it) {
-                const int sb = it % g.SB;
-                const uint32_t ph = (uint32_t)(it / g.SB) & 1u;
-                mbar_wait(smem_u32(&ctl->b_empty[sb]), ph ^ 1u);
-                const uint32_t bar = smem_u32(&ctl->b_full[sb]);
-                mbar_arrive_expect_tx(bar, (uint32_t)g.b_stage_bytes);
-                bulk_g2s(b_base + sb * g.b_stage_bytes, wp + (size_t)it * g.b_stage_bytes, (uint32_t)g.b_stage_bytes,
-                         bar);
+            const int iters_per_tile = g.ncb * TAPS;
+            if (g.stationary) {
+                // n_tiles == 1: the whole packed weight set becomes resident
+                const uint8_t* wp = reinterpret_cast<const uint8_t*>(d.wpack);
+                const uint32_t bar = smem_u32(&ctl->w_full);
+                mbar_arrive_expect_tx(bar, (uint32_t)g.w_bytes);
+                for (int off = 0; off < g.w_bytes; off += 32768) {
+                    const int n = (g.w_bytes - off < 32768) ? g.w_bytes - off : 32768;
+                    bulk_g2s(b_base + off, wp + off, (uint32_t)n, bar);
+                }
+            } else {
+                int ib = 0;
+                for (int item = blockIdx.x; item < g.items; item += gridDim.x) {
+                    const int n_tile = item / g.m_tiles;
+                    const uint8_t* wp = reinterpret_cast<const uint8_t*>(d.wpack) +
+                                        (size_t)n_tile * iters_per_tile * g.b_stage_bytes;
+                    for (int t = 0; t < iters_per_tile; ++t, ++ib) {
+                        const int sb = ib % g.SB;
+                        mbar_wait(smem_u32(&ctl->b_empty[sb]), ((uint32_t)(ib / g.SB) & 1u) ^ 1u);
+                        const uint32_t bar = smem_u32(&ctl->b_full[sb]);
+                        mbar_arrive_expect_tx(bar, (uint32_t)g.b_stage_bytes);
+                        bulk_g2s(b_base + sb * g.b_stage_bytes, wp + (size_t)t * g.b_stage_bytes,
+                                 (uint32_t)g.b_stage_bytes, bar);
+                    }
+                }
             }
         }
     } else {
@@ -254,51 +324,86 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvGeom g) {
             const uint32_t idesc = umma_idesc_f16(d.precision == DISCO_PREC_BF16X3, 128, d.block_n);
             const uint32_t lbo_b = (uint32_t)d.block_n * 16u;
             const int ksteps = d.c_blk / 16;
-            uint32_t acc = 0;
-            int it = 0;
-            for (int cb = 0; cb < g.ncb; ++cb) {
-                const int sa = cb % g.SA;
-                mbar_wait(smem_u32(&ctl->a_full[sa]), (uint32_t)(cb / g.SA) & 1u);
+            int ia = 0, ib = 0, iacc = 0;
+            if (g.stationary) {
+                mbar_wait(smem_u32(&ctl->w_full), 0);
                 tc_fence_after();
-                const uint32_t a_stage = a_base + sa * g.a_stage_bytes;
-                for (int tap = 0; tap < d.taps; ++tap, ++it) {
-                    const int sb = it % g.SB;
-                    mbar_wait(smem_u32(&ctl->b_full[sb]), (uint32_t)(it / g.SB) & 1u);
-                    tc_fence_after();
-                    uint32_t a_tap = a_stage;
-                    if (d.taps == 9) {
-                        const int kh = tap / 3, kw = tap - kh * 3;
-                        a_tap += (d.stride == 1) ? (uint32_t)(kh * 10 + kw) * 16u
-                                                 : (uint32_t)(kw & 1) * g.parplane + (uint32_t)(kh * 9 + (kw >> 1)) * 16u;
+            }
+            for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++iacc) {
+                const int buf = iacc % g.nacc;
+                mbar_wait(smem_u32(&ctl->acc_empty[buf]), ((uint32_t)(iacc / g.nacc) & 1u) ^ 1u);
+                tc_fence_after();
+                uint32_t acc0 = 0, acc1 = 0;
+                for (int cb = 0; cb < g.ncb; ++cb) {
+                    uint32_t a_stage0 = 0, a_stage1 = 0;
+                    for (int sub = 0; sub < g.msub; ++sub) {
+                        const int sa = (ia + sub) % g.SA;
+                        mbar_wait(smem_u32(&ctl->a_full[sa]), (uint32_t)((ia + sub) / g.SA) & 1u);
+                        if (sub) a_stage1 = a_base + sa * g.a_stage_bytes;
+                        else a_stage0 = a_base + sa * g.a_stage_bytes;
                     }
-                    const uint32_t b_stage = b_base + sb * g.b_stage_bytes;
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint32_t a_hi = a_tap + (uint32_t)(2 * ks) * g.plane;
-                        const uint32_t b_hi = b_stage + (uint32_t)(2 * ks) * lbo_b;
-                        const uint64_t da = umma_desc_kmajor_noswizzle(a_hi, (uint32_t)g.plane, (uint32_t)g.sbo_a);
-                        const uint64_t db = umma_desc_kmajor_noswizzle(b_hi, lbo_b, 128u);
-                        umma_f16(tmem_d, da, db, idesc, acc);
-                        acc = 1;
-                        if (g.nparts == 2) {
-                            const uint64_t da_lo = umma_desc_kmajor_noswizzle(a_hi + g.a_part_bytes, (uint32_t)g.plane,
-                                                                              (uint32_t)g.sbo_a);
-                            const uint64_t db_lo = umma_desc_kmajor_noswizzle(b_hi + g.b_part_bytes, lbo_b, 128u);
-                            umma_f16(tmem_d, da_lo, db, idesc, 1);
-                            umma_f16(tmem_d, da, db_lo, idesc, 1);
+                    tc_fence_after();
+                    for (int tap = 0; tap < TAPS; ++tap) {
+                        uint32_t b_stage;
+                        int sb = 0;
+                        if (g.stationary) {
+                            b_stage = b_base + (uint32_t)(cb * TAPS + tap) * g.b_stage_bytes;
+                        } else {
+                            sb = ib % g.SB;
+                            mbar_wait(smem_u32(&ctl->b_full[sb]), (uint32_t)(ib / g.SB) & 1u);
+                            tc_fence_after();
+                            b_stage = b_base + sb * g.b_stage_bytes;
+                        }
+                        uint32_t a_tap = 0;
+                        if (MODE == 0) {
+                            const int kh = tap / 3, kw = tap - kh * 3;
+                            a_tap = (uint32_t)(kh * 10 + kw) * 16u;
+                        } else if (MODE == 1) {
+                            const int kh = tap / 3, kw = tap - kh * 3;
+                            a_tap = (uint32_t)(kw & 1) * g.parplane + (uint32_t)(kh * 9 + (kw >> 1)) * 16u;
+                        }
+                        for (int sub = 0; sub < g.msub; ++sub) {
+                            const uint32_t td = tmem_d + (uint32_t)((buf * g.msub + sub) * g.acc_stride);
+                            const uint32_t a_st = sub ? a_stage1 : a_stage0;
+                            uint32_t acc = sub ? acc1 : acc0;
+                            for (int ks = 0; ks < ksteps; ++ks) {
+                                const uint32_t a_hi = a_st + a_tap + (uint32_t)(2 * ks) * g.plane;
+                                const uint32_t b_hi = b_stage + (uint32_t)(2 * ks) * lbo_b;
+                                const uint64_t da =
+                                    umma_desc_kmajor_noswizzle(a_hi, (uint32_t)g.plane, (uint32_t)g.sbo_a);
+                                const uint64_t db = umma_desc_kmajor_noswizzle(b_hi, lbo_b, 128u);
+                                umma_f16(td, da, db, idesc, acc);
+                                acc = 1;
+                                if (g.nparts == 2) {
+                                    const uint64_t da_lo = umma_desc_kmajor_noswizzle(
+                                        a_hi + g.a_part_bytes, (uint32_t)g.plane, (uint32_t)g.sbo_a);
+                                    const uint64_t db_lo =
+                                        umma_desc_kmajor_noswizzle(b_hi + g.b_part_bytes, lbo_b, 128u);
+                                    umma_f16(td, da_lo, db, idesc, 1);
+                                    umma_f16(td, da, db_lo, idesc, 1);
+                                }
+                            }
+                            if (sub) acc1 = acc; else acc0 = acc;
+                        }
+                        if (!g.stationary) {
+                            umma_commit(smem_u32(&ctl->b_empty[sb]));
+                            ++ib;
                         }
                     }
-                    umma_commit(smem_u32(&ctl->b_empty[sb]));
+                    for (int sub = 0; sub < g.msub; ++sub) umma_commit(smem_u32(&ctl->a_empty[(ia + sub) % g.SA]));
+                    ia += g.msub;
                 }
-                umma_commit(smem_u32(&ctl->a_empty[sa]));
+                umma_commit(smem_u32(&ctl->acc_full[buf]));
             }
-            umma_commit(smem_u32(&ctl->acc_full));
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_d, (uint32_t)g.tmem_cols);
+    if (warp == 9) tmem_dealloc(tmem_d, (uint32_t)g.tmem_cols);
 }
+
+int g_num_sms = 0;
 
 int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     DISCO_REQUIRE(d->taps == 9 || d->taps == 1, "conv: taps must be 9 or 1 (got %d)", d->taps);
@@ -325,6 +430,11 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     else
         DISCO_REQUIRE(d->out_split % 4 == 0 && (d->c_out - d->out_split) % 4 == 0 && d->out_split <= d->c_out,
                       "conv: fp32 output split must be a multiple of 4");
+    if (g_num_sms == 0) {
+        int dev = 0;
+        DISCO_CHECK_CUDA(cudaGetDevice(&dev));
+        DISCO_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
 
     g->d = *d;
     g->ncb0 = d->src_c[0] / d->c_blk;
@@ -333,11 +443,11 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     g->chunk_shift = (g->chunks == 2) ? 1 : (g->chunks == 4) ? 2 : 3;
     g->nparts = (d->precision == DISCO_PREC_BF16X3) ? 2 : 1;
     if (d->taps == 1) {
-        g->PH = 1; g->PW = 128; g->PIX = 128; g->parplane = 0; g->sbo_a = 128;
+        g->PIX = 128; g->parplane = 0; g->sbo_a = 128;
     } else if (d->stride == 1) {
-        g->PH = 18; g->PW = 10; g->PIX = 180; g->parplane = 0; g->sbo_a = 160;
+        g->PIX = 180; g->parplane = 0; g->sbo_a = 160;
     } else {
-        g->PH = 33; g->PW = 17; g->PIX = 33 * 17; g->parplane = 33 * 9 * 16; g->sbo_a = 2 * 9 * 16;
+        g->PIX = 33 * 17; g->parplane = 33 * 9 * 16; g->sbo_a = 2 * 9 * 16;
     }
     int plane = (d->taps == 9 && d->stride == 2) ? 2 * g->parplane : g->PIX * 16;
     // pad so that the `chunks` 16-byte writes of one pixel land in distinct bank groups
@@ -348,25 +458,70 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     g->a_stage_bytes = ((g->nparts * g->a_part_bytes + 127) / 128) * 128;
     g->b_part_bytes = d->c_blk * d->block_n * 2;
     g->b_stage_bytes = g->nparts * g->b_part_bytes;
-    g->SA = (g->ncb >= 2) ? 2 : 1;
-    const int budget = 200 * 1024 - 384 - g->SA * g->a_stage_bytes;
-    int sb = budget / g->b_stage_bytes;
-    if (sb > kMaxStages) sb = kMaxStages;
-    const int iters = g->ncb * d->taps;
-    if (sb > iters) sb = iters;
-    DISCO_REQUIRE(sb >= 1, "conv: tile does not fit shared memory (a_stage %d, b_stage %d)", g->a_stage_bytes,
-                  g->b_stage_bytes);
-    // small-tile layers: keep the footprint low enough for several CTAs per SM (epilogue/mainloop overlap)
-    if (g->SA * g->a_stage_bytes + 4 * g->b_stage_bytes <= 70 * 1024 && sb > 4) sb = 4;
-    g->SB = sb;
-    g->smem_bytes = 384 + g->SA * g->a_stage_bytes + g->SB * g->b_stage_bytes;
-    g->tiles_h = (d->h_out + 15) / 16;
-    g->tiles_w = (d->w_out + 7) / 8;
+    g->n_tiles = (d->c_out + d->block_n - 1) / d->block_n;
     g->total_pix = (long long)d->n * d->h_out * d->w_out;
+
+    const int budget = 224 * 1024 - kCtlBytes;
+    g->w_bytes = g->ncb * d->taps * g->b_stage_bytes;
+    // MSUB = 2 (256-pixel items) when the N tile leaves room for double-buffered accumulators and the
+    // image is wide enough; it halves the weight stream per MAC.
+    const bool wide = (d->taps == 1) ? (g->total_pix >= 256) : (d->w_out >= 16);
+    g->msub = (wide && 4 * d->block_n <= 512) ? 2 : 1;
+    g->stationary = (g->n_tiles == 1 && g->w_bytes + 3 * g->a_stage_bytes <= budget) ? 1 : 0;
+    if (g->stationary) g->msub = 1;  // nothing to amortise; smaller items balance better
+    g->nacc = (2 * g->msub * d->block_n <= 512) ? 2 : 1;
+    g->acc_stride = (d->block_n + 31) / 32 * 32;
+    if (2 * g->msub * g->acc_stride > 512) g->acc_stride = d->block_n;
     int cols = 32;
-    while (cols < d->block_n) cols *= 2;
+    while (cols < g->nacc * g->msub * g->acc_stride) cols *= 2;
     g->tmem_cols = cols;
-    DISCO_REQUIRE((g->plane >> 4) < 16384 && (g->a_part_bytes + g->a_stage_bytes) < (1 << 18), "conv: descriptor range");
+    if (g->stationary) {
+        int sa = (budget - g->w_bytes) / g->a_stage_bytes;
+        if (sa > kMaxStages) sa = kMaxStages;
+        g->SA = sa;
+        g->SB = 1;
+        g->smem_bytes = kCtlBytes + g->SA * g->a_stage_bytes + g->w_bytes;
+    } else {
+        int sa = 2 * g->msub;  // current + next channel block
+        if (sa < 4 && 4 * g->a_stage_bytes <= budget / 3) sa = 4;
+        int sb = (budget - sa * g->a_stage_bytes) / g->b_stage_bytes;
+        while (sb < 2 && sa > g->msub) {
+            --sa;
+            sb = (budget - sa * g->a_stage_bytes) / g->b_stage_bytes;
+        }
+        if (sb > kMaxStages) sb = kMaxStages;
+        DISCO_REQUIRE(sb >= 1 && sa >= g->msub, "conv: tile does not fit shared memory (a_stage %d, b_stage %d)",
+                      g->a_stage_bytes, g->b_stage_bytes);
+        g->SA = sa;
+        g->SB = sb;
+        g->smem_bytes = kCtlBytes + g->SA * g->a_stage_bytes + g->SB * g->b_stage_bytes;
+    }
+    DISCO_REQUIRE(g->SA >= g->msub && g->SA >= 1, "conv: not enough A stages");
+    g->nprod = g->SA < kProdWarps ? g->SA : kProdWarps;
+    g->tiles_h = (d->h_out + 15) / 16;
+    g->tiles_w = (d->w_out + 8 * g->msub - 1) / (8 * g->msub);
+    const long long m_tiles = (d->taps == 9) ? (long long)d->n * g->tiles_h * g->tiles_w
+                                             : (g->total_pix + 128 * g->msub - 1) / (128 * g->msub);
+    DISCO_REQUIRE(m_tiles > 0 && m_tiles * g->n_tiles < (1ll << 30), "conv: bad tile count");
+    g->m_tiles = (int)m_tiles;
+    g->items = g->m_tiles * g->n_tiles;
+    g->grid = g->items < g_num_sms ? g->items : g_num_sms;
+    DISCO_REQUIRE((g->plane >> 4) < 16384 && g->smem_bytes <= 227 * 1024, "conv: descriptor / smem range");
+    return DISCO_OK;
+}
+
+template <int MODE>
+int launch_mode(const ConvGeom& g, cudaStream_t stream) {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    DISCO_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !attr_set[dev]) {
+        DISCO_CHECK_CUDA(
+            cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set[dev] = true;
+    }
+    conv_tc_kernel<MODE><<<g.grid, kThreads, g.smem_bytes, stream>>>(g);
+    DISCO_CHECK_CUDA(cudaGetLastError());
     return DISCO_OK;
 }
 
@@ -382,18 +537,7 @@ int disco_conv_tc_launch(const disco_conv_desc* d, void* stream) {
     ConvGeom g;
     int rc = build_geom(d, &g);
     if (rc < 0) return rc;
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    DISCO_CHECK_CUDA(cudaGetDevice(&dev));
-    if (dev < 64 && !attr_set[dev]) {
-        DISCO_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set[dev] = true;
-    }
-    const long long m_tiles = (d->taps == 9) ? (long long)d->n * g.tiles_h * g.tiles_w : (g.total_pix + 127) / 128;
-    const int n_tiles = (d->c_out + d->block_n - 1) / d->block_n;
-    DISCO_REQUIRE(m_tiles > 0 && m_tiles < (1ll << 31), "conv: bad tile count");
-    dim3 grid((unsigned)m_tiles, (unsigned)n_tiles);
-    conv_tc_kernel<<<grid, kThreads, g.smem_bytes, (cudaStream_t)stream>>>(g);
-    DISCO_CHECK_CUDA(cudaGetLastError());
-    return DISCO_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (d->taps == 1) return launch_mode<2>(g, s);
+    return d->stride == 1 ? launch_mode<0>(g, s) : launch_mode<1>(g, s);
 }

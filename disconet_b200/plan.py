@@ -81,7 +81,7 @@ def pack_conv(wf: torch.Tensor, bf: torch.Tensor, *, src_channels, stride: int =
     c_blk = choose_c_blk(src_channels, precision, stride)
     c_out_pad16 = (c_out + 15) // 16 * 16
     if block_n is None:
-        block_n = min(c_out_pad16, 256)
+        block_n = min(c_out_pad16, 128)   # <=128 leaves TMEM room for 2 sub-tiles x 2 accumulator buffers
     n_tiles = (c_out + block_n - 1) // block_n
     n_rows = n_tiles * block_n
     dev = wf.device

@@ -23,6 +23,11 @@ CASES = [
     ("c512_16x16", 2, 16, 16, [(512, 512, 0)], 512, 3, 1, "act"),
     ("partial_tiles_24x20", 1, 24, 20, [(64, 64, 0)], 64, 3, 1, "act"),
     ("tiny_8x8_s2", 1, 8, 8, [(64, 64, 0)], 128, 3, 2, "act"),
+    ("persistent_many_items_stationary", 8, 64, 64, [(32, 32, 0)], 32, 3, 1, "act"),
+    ("persistent_many_items_streamed_msub2", 12, 64, 64, [(128, 128, 0)], 128, 3, 1, "act"),
+    ("persistent_s2_many_items", 6, 128, 128, [(32, 32, 0)], 64, 3, 2, "act"),
+    ("persistent_upcat_many_items", 6, 64, 64, [(256, 256, 1), (128, 128, 0)], 128, 3, 1, "act"),
+    ("pw_many_items_msub2", 4, 128, 128, [(128, 128, 0)], 128, 1, 1, "act"),
     ("pw_64to64", 2, 32, 32, [(64, 64, 0)], 64, 1, 1, "act"),
     ("pw_256to256_f32", 2, 32, 32, [(256, 256, 0)], 256, 1, 1, "f32"),
     ("pw_heads_64to48_split", 1, 32, 24, [(64, 64, 0)], 48, 1, 1, (12,)),
