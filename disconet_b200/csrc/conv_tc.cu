@@ -115,7 +115,7 @@ __device__ __forceinline__ Item decode_item(const ConvGeom& g, int item) {
 }
 
 // MODE 0: 3x3 stride 1 (patch 18x10) | MODE 1: 3x3 stride 2 (patch 33x17) | MODE 2: 1x1
-template <int MODE>
+template <int MODE, int KSTEPS, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_raw);
@@ -320,11 +320,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
         }
     } else {
         // =========================== MMA issuer ===================================================
-        if (lane == 0) {
+        // The MMA stream must be straight-line code with distinct descriptor registers: a rolled loop
+        // serialises on the uniform-register hazards at ~100-150 cycles per tcgen05.mma, an unrolled one
+        // issues every ~47 cycles (tools/mma_rate.cu, profiles/r01_mma_issue_rate.txt).  So taps, k-steps
+        // and the three split passes are compile-time unrolled (KSTEPS, SPLIT template parameters) and
+        // every descriptor is base + precomputed offset.  The whole warp runs the warp-uniform control
+        // flow; one elected lane issues.
+        {
             const uint32_t idesc = umma_idesc_f16(d.precision == DISCO_PREC_BF16X3, 128, d.block_n);
-            const uint32_t lbo_b = (uint32_t)d.block_n * 16u;
-            const int ksteps = d.c_blk / 16;
-            int ia = 0, ib = 0, iacc = 0;
+            // descriptor halves (see umma_desc_kmajor_noswizzle): lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version
+            const uint32_t lbo_b16 = (uint32_t)d.block_n;                 // block_n*16 bytes >> 4
+            const uint32_t a_hi = ((uint32_t)g.sbo_a >> 4) | (1u << 14);
+            const uint32_t b_hi = (128u >> 4) | (1u << 14);
+            const uint32_t a_lo_c = ((uint32_t)g.plane >> 4) << 16;
+            const uint32_t b_lo_c = lbo_b16 << 16;
+            const uint32_t a_part16 = (uint32_t)g.a_part_bytes >> 4, b_part16 = (uint32_t)g.b_part_bytes >> 4;
+            const uint32_t a_base16 = (a_base >> 4) + a_lo_c, b_base16 = (b_base >> 4) + b_lo_c;  // LBO folded in
+            const uint32_t a_stage16 = (uint32_t)g.a_stage_bytes >> 4, b_stage16 = (uint32_t)g.b_stage_bytes >> 4;
+            const uint32_t bar_a_full = smem_u32(&ctl->a_full[0]), bar_a_empty = smem_u32(&ctl->a_empty[0]);
+            const uint32_t bar_b_full = smem_u32(&ctl->b_full[0]), bar_b_empty = smem_u32(&ctl->b_empty[0]);
+            uint32_t a_ks[KSTEPS], b_ks[KSTEPS];
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+                a_ks[ks] = ((uint32_t)(2 * ks) * (uint32_t)g.plane) >> 4;   // two channel chunks per k-step
+                b_ks[ks] = (uint32_t)(2 * ks) * lbo_b16;
+            }
+            const uint32_t par16 = (uint32_t)g.parplane >> 4;
+            int iacc = 0;
+            int sa_slot = 0, sb_slot = 0;            // stage ring positions maintained incrementally
+            uint32_t sa_phase = 0, sb_phase = 0;
             if (g.stationary) {
                 mbar_wait(smem_u32(&ctl->w_full), 0);
                 tc_fence_after();
@@ -333,67 +357,72 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                 const int buf = iacc % g.nacc;
                 mbar_wait(smem_u32(&ctl->acc_empty[buf]), ((uint32_t)(iacc / g.nacc) & 1u) ^ 1u);
                 tc_fence_after();
-                uint32_t acc0 = 0, acc1 = 0;
+                const uint32_t td0 = tmem_d + (uint32_t)(buf * g.msub * g.acc_stride);
+                const uint32_t td1 = td0 + (uint32_t)g.acc_stride;
                 for (int cb = 0; cb < g.ncb; ++cb) {
-                    uint32_t a_stage0 = 0, a_stage1 = 0;
-                    for (int sub = 0; sub < g.msub; ++sub) {
-                        const int sa = (ia + sub) % g.SA;
-                        mbar_wait(smem_u32(&ctl->a_full[sa]), (uint32_t)((ia + sub) / g.SA) & 1u);
-                        if (sub) a_stage1 = a_base + sa * g.a_stage_bytes;
-                        else a_stage0 = a_base + sa * g.a_stage_bytes;
+                    // wait for the MSUB patches of this channel block
+                    const int slot0 = sa_slot;
+                    mbar_wait(bar_a_full + 8u * slot0, sa_phase);
+                    const uint32_t a0_16 = a_base16 + (uint32_t)slot0 * a_stage16;
+                    int slot1 = slot0;
+                    uint32_t a1_16 = a0_16;
+                    if (g.msub == 2) {
+                        slot1 = slot0 + 1;
+                        uint32_t phase1 = sa_phase;
+                        if (slot1 == g.SA) { slot1 = 0; phase1 ^= 1u; }
+                        mbar_wait(bar_a_full + 8u * slot1, phase1);
+                        a1_16 = a_base16 + (uint32_t)slot1 * a_stage16;
                     }
                     tc_fence_after();
+                    const uint32_t first = (cb > 0) ? 1u : 0u;   // accumulate flag of the first MMA of the item
+#pragma unroll
                     for (int tap = 0; tap < TAPS; ++tap) {
-                        uint32_t b_stage;
-                        int sb = 0;
+                        uint32_t b16;
                         if (g.stationary) {
-                            b_stage = b_base + (uint32_t)(cb * TAPS + tap) * g.b_stage_bytes;
+                            b16 = b_base16 + (uint32_t)(cb * TAPS + tap) * b_stage16;
                         } else {
-                            sb = ib % g.SB;
-                            mbar_wait(smem_u32(&ctl->b_full[sb]), (uint32_t)(ib / g.SB) & 1u);
+                            mbar_wait(bar_b_full + 8u * sb_slot, sb_phase);
                             tc_fence_after();
-                            b_stage = b_base + sb * g.b_stage_bytes;
+                            b16 = b_base16 + (uint32_t)sb_slot * b_stage16;
                         }
-                        uint32_t a_tap = 0;
-                        if (MODE == 0) {
-                            const int kh = tap / 3, kw = tap - kh * 3;
-                            a_tap = (uint32_t)(kh * 10 + kw) * 16u;
-                        } else if (MODE == 1) {
-                            const int kh = tap / 3, kw = tap - kh * 3;
-                            a_tap = (uint32_t)(kw & 1) * g.parplane + (uint32_t)(kh * 9 + (kw >> 1)) * 16u;
-                        }
-                        for (int sub = 0; sub < g.msub; ++sub) {
-                            const uint32_t td = tmem_d + (uint32_t)((buf * g.msub + sub) * g.acc_stride);
-                            const uint32_t a_st = sub ? a_stage1 : a_stage0;
-                            uint32_t acc = sub ? acc1 : acc0;
-                            for (int ks = 0; ks < ksteps; ++ks) {
-                                const uint32_t a_hi = a_st + a_tap + (uint32_t)(2 * ks) * g.plane;
-                                const uint32_t b_hi = b_stage + (uint32_t)(2 * ks) * lbo_b;
-                                const uint64_t da =
-                                    umma_desc_kmajor_noswizzle(a_hi, (uint32_t)g.plane, (uint32_t)g.sbo_a);
-                                const uint64_t db = umma_desc_kmajor_noswizzle(b_hi, lbo_b, 128u);
-                                umma_f16(td, da, db, idesc, acc);
-                                acc = 1;
-                                if (g.nparts == 2) {
-                                    const uint64_t da_lo = umma_desc_kmajor_noswizzle(
-                                        a_hi + g.a_part_bytes, (uint32_t)g.plane, (uint32_t)g.sbo_a);
-                                    const uint64_t db_lo =
-                                        umma_desc_kmajor_noswizzle(b_hi + g.b_part_bytes, lbo_b, 128u);
-                                    umma_f16(td, da_lo, db, idesc, 1);
-                                    umma_f16(td, da, db_lo, idesc, 1);
+                        const int kh = tap / 3, kw = tap - kh * 3;
+                        const uint32_t toff = (MODE == 0) ? (uint32_t)(kh * 10 + kw)
+                                            : (MODE == 1) ? (uint32_t)(kw & 1) * par16 + (uint32_t)(kh * 9 + (kw >> 1))
+                                                          : 0u;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int sub = 0; sub < 2; ++sub) {
+                                if (sub < g.msub) {
+                                    const uint32_t td = sub ? td1 : td0;
+                                    const uint32_t a16 = (sub ? a1_16 : a0_16) + toff;
+#pragma unroll
+                                    for (int ks = 0; ks < KSTEPS; ++ks) {
+                                        const uint32_t alo = a16 + a_ks[ks], blo = b16 + b_ks[ks];
+                                        umma_f16_parts(td, alo, a_hi, blo, b_hi, idesc, (tap == 0 && ks == 0) ? first : 1u);
+                                        if (SPLIT) {
+                                            umma_f16_parts(td, alo + a_part16, a_hi, blo, b_hi, idesc, 1u);
+                                            umma_f16_parts(td, alo, a_hi, blo + b_part16, b_hi, idesc, 1u);
+                                        }
+                                    }
                                 }
                             }
-                            if (sub) acc1 = acc; else acc0 = acc;
+                            if (!g.stationary) umma_commit(bar_b_empty + 8u * sb_slot);
                         }
+                        __syncwarp();
                         if (!g.stationary) {
-                            umma_commit(smem_u32(&ctl->b_empty[sb]));
-                            ++ib;
+                            if (++sb_slot == g.SB) { sb_slot = 0; sb_phase ^= 1u; }
                         }
                     }
-                    for (int sub = 0; sub < g.msub; ++sub) umma_commit(smem_u32(&ctl->a_empty[(ia + sub) % g.SA]));
-                    ia += g.msub;
+                    if (elect_one()) {
+                        umma_commit(bar_a_empty + 8u * slot0);
+                        if (g.msub == 2) umma_commit(bar_a_empty + 8u * slot1);
+                    }
+                    __syncwarp();
+                    sa_slot += g.msub;
+                    if (sa_slot >= g.SA) { sa_slot -= g.SA; sa_phase ^= 1u; }
                 }
-                umma_commit(smem_u32(&ctl->acc_full[buf]));
+                if (elect_one()) umma_commit(smem_u32(&ctl->acc_full[buf]));
+                __syncwarp();
             }
         }
     }
@@ -475,8 +504,13 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     int cols = 32;
     while (cols < g->nacc * g->msub * g->acc_stride) cols *= 2;
     g->tmem_cols = cols;
+    int ctas_per_sm = 1;
+    g->acc_stride = (d->block_n + 31) / 32 * 32;
     if (g->stationary) {
-        int sa = (budget - g->w_bytes) / g->a_stage_bytes;
+        // small resident weight sets: aim for two CTAs per SM (two MMA issuers, 2x gather streams)
+        int sa = (110 * 1024 - kCtlBytes - g->w_bytes) / g->a_stage_bytes;
+        if (sa >= 3 && 2 * g->nacc * g->acc_stride <= 512) ctas_per_sm = 2;
+        else sa = (budget - g->w_bytes) / g->a_stage_bytes;
         if (sa > kMaxStages) sa = kMaxStages;
         g->SA = sa;
         g->SB = 1;
@@ -505,24 +539,34 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     DISCO_REQUIRE(m_tiles > 0 && m_tiles * g->n_tiles < (1ll << 30), "conv: bad tile count");
     g->m_tiles = (int)m_tiles;
     g->items = g->m_tiles * g->n_tiles;
-    g->grid = g->items < g_num_sms ? g->items : g_num_sms;
+    g->grid = g->items < ctas_per_sm * g_num_sms ? g->items : ctas_per_sm * g_num_sms;
     DISCO_REQUIRE((g->plane >> 4) < 16384 && g->smem_bytes <= 227 * 1024, "conv: descriptor / smem range");
+    return DISCO_OK;
+}
+
+template <int MODE, int KSTEPS, bool SPLIT>
+int launch_inst(const ConvGeom& g, cudaStream_t stream) {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    DISCO_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !attr_set[dev]) {
+        DISCO_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MODE, KSTEPS, SPLIT>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set[dev] = true;
+    }
+    conv_tc_kernel<MODE, KSTEPS, SPLIT><<<g.grid, kThreads, g.smem_bytes, stream>>>(g);
+    DISCO_CHECK_CUDA(cudaGetLastError());
     return DISCO_OK;
 }
 
 template <int MODE>
 int launch_mode(const ConvGeom& g, cudaStream_t stream) {
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    DISCO_CHECK_CUDA(cudaGetDevice(&dev));
-    if (dev < 64 && !attr_set[dev]) {
-        DISCO_CHECK_CUDA(
-            cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set[dev] = true;
+    const bool split = g.nparts == 2;
+    switch (g.d.c_blk) {
+        case 16: return split ? launch_inst<MODE, 1, true>(g, stream) : launch_inst<MODE, 1, false>(g, stream);
+        case 32: return split ? launch_inst<MODE, 2, true>(g, stream) : launch_inst<MODE, 2, false>(g, stream);
+        default: return split ? launch_inst<MODE, 4, true>(g, stream) : launch_inst<MODE, 4, false>(g, stream);
     }
-    conv_tc_kernel<MODE><<<g.grid, kThreads, g.smem_bytes, stream>>>(g);
-    DISCO_CHECK_CUDA(cudaGetLastError());
-    return DISCO_OK;
 }
 
 }  // namespace

@@ -81,7 +81,9 @@ def pack_conv(wf: torch.Tensor, bf: torch.Tensor, *, src_channels, stride: int =
     c_blk = choose_c_blk(src_channels, precision, stride)
     c_out_pad16 = (c_out + 15) // 16 * 16
     if block_n is None:
-        block_n = min(c_out_pad16, 128)   # <=128 leaves TMEM room for 2 sub-tiles x 2 accumulator buffers
+        # N=256 keeps the MMA's shared-memory operand reads (A 4 KB + B N*32 B per N/2 cycles) under the
+        # 128 B/clk SMEM port; smaller layers use <=128 so that two 128-pixel sub-tiles share one B stream
+        block_n = 256 if c_out_pad16 >= 256 else min(c_out_pad16, 128)
     n_tiles = (c_out + block_n - 1) // block_n
     n_rows = n_tiles * block_n
     dev = wf.device
