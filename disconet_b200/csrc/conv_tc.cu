@@ -255,32 +255,57 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                 const uint32_t stage = a_base + sa * g.a_stage_bytes;
                 const int cofs = cbl * d.c_blk;
                 const int hi0 = it.h0 * STRIDE - 1, wi0 = (it.w0 + sub * 8) * STRIDE - 1;
-                const long long pbase = it.p0 + sub * 128;
-                for (int e = lane; e < per_part; e += 32) {
-                    const int chunk = e & (g.chunks - 1);
-                    const int pix = e >> g.chunk_shift;
-                    long long goff;
-                    uint32_t soff;
-                    bool valid;
-                    if (MODE != 2) {
-                        const int r = pix / PW;
-                        const int c = pix - r * PW;
-                        const int hi = hi0 + r, wi = wi0 + c;
-                        valid = (hi >= 0) && (hi < d.h_in) && (wi >= 0) && (wi < d.w_in);
-                        goff = (((long long)it.img * Hs + (hi >> up)) * Ws + (wi >> up)) * Cs + cofs + chunk * 8;
-                        if (MODE == 0) soff = (uint32_t)(r * 10 + c) * 16u;
-                        else soff = (uint32_t)(c & 1) * g.parplane + (uint32_t)(r * 9 + (c >> 1)) * 16u;
-                    } else {
-                        const long long p = pbase + pix;
-                        valid = p < g.total_pix;
-                        goff = p * Cs + cofs + chunk * 8;
-                        soff = (uint32_t)pix * 16u;
+                if (MODE != 2) {
+                    // Row-wise gather: the (column, chunk) a lane handles is the same for every patch row, so
+                    // its shared/global offsets are computed once per stage and each row only adds its base.
+                    constexpr int PH = (MODE == 0) ? 18 : 33;
+                    constexpr int ROWPITCH = (MODE == 0) ? 160 : 144;
+                    constexpr int NJ = (MODE == 0) ? 3 : 5;     // ceil(PW * max chunks / 32)
+                    const int per_row = PW << g.chunk_shift;
+                    uint32_t soff[NJ];
+                    int goff[NJ];
+                    bool act[NJ], vcol[NJ];
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        const int e = lane + 32 * j;
+                        const int c = e >> g.chunk_shift, chunk = e & (g.chunks - 1);
+                        const int wi = wi0 + c;
+                        act[j] = e < per_row;
+                        vcol[j] = (wi >= 0) && (wi < d.w_in);
+                        soff[j] = (uint32_t)chunk * g.plane +
+                                  ((MODE == 0) ? (uint32_t)c * 16u
+                                               : (uint32_t)(c & 1) * g.parplane + (uint32_t)(c >> 1) * 16u);
+                        goff[j] = (wi >> up) * Cs + cofs + chunk * 8;
                     }
-                    const uint32_t dst = stage + chunk * g.plane + soff;
-                    const uint16_t* gp = valid ? (src + goff) : src;
-                    cp_async16(dst, gp, valid ? 16u : 0u);
-                    if (g.nparts == 2)
-                        cp_async16(dst + g.a_part_bytes, valid ? (gp + lo_off) : src, valid ? 16u : 0u);
+                    const long long img_base = (long long)it.img * Hs;
+                    const long long row_stride = (long long)Ws * Cs;
+#pragma unroll 2
+                    for (int r = 0; r < PH; ++r) {
+                        const int hi = hi0 + r;
+                        const bool rv = (hi >= 0) && (hi < d.h_in);
+                        const uint16_t* rowp = src + (img_base + (hi >> up)) * row_stride;
+                        const uint32_t drow = stage + (uint32_t)r * ROWPITCH;
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) {
+                            if (!act[j]) continue;
+                            const bool valid = rv && vcol[j];
+                            const uint16_t* gp = valid ? rowp + goff[j] : src;
+                            cp_async16(drow + soff[j], gp, valid ? 16u : 0u);
+                            if (SPLIT) cp_async16(drow + soff[j] + g.a_part_bytes, valid ? gp + lo_off : src, valid ? 16u : 0u);
+                        }
+                    }
+                } else {
+                    const long long pbase = it.p0 + sub * 128;
+                    for (int e = lane; e < per_part; e += 32) {
+                        const int chunk = e & (g.chunks - 1);
+                        const int pix = e >> g.chunk_shift;
+                        const long long p = pbase + pix;
+                        const bool valid = p < g.total_pix;
+                        const uint32_t dst = stage + chunk * g.plane + (uint32_t)pix * 16u;
+                        const uint16_t* gp = valid ? (src + p * Cs + cofs + chunk * 8) : src;
+                        cp_async16(dst, gp, valid ? 16u : 0u);
+                        if (SPLIT) cp_async16(dst + g.a_part_bytes, valid ? (gp + lo_off) : src, valid ? 16u : 0u);
+                    }
                 }
                 cp_async_commit();
                 cp_async_wait<0>();
