@@ -5,5 +5,6 @@ data-format entry points (`voxelize_occupy`, `bev_scatter`).  Everything compute
 """
 from .det import DiscoNet, FaFNet, TeacherNet, AgentWeightList  # noqa: F401
 from .voxel import voxelize_occupy, bev_scatter  # noqa: F401
+from .pipeline import HostPipeline  # noqa: F401
 
-__all__ = ["DiscoNet", "FaFNet", "TeacherNet", "voxelize_occupy", "bev_scatter"]
+__all__ = ["DiscoNet", "FaFNet", "TeacherNet", "voxelize_occupy", "bev_scatter", "HostPipeline"]

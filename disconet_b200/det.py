@@ -207,8 +207,8 @@ class DiscoNet(_DetBase):
         P = self.plans()
         ws = self._workspace(N, H, W, B, dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        trans = trans_matrices.detach().to(device=dev, dtype=torch.float64).contiguous()
-        num_agent = num_agent_tensor.detach()[:, 0].to(device=dev, dtype=torch.int32).contiguous()
+        trans = trans_matrices.detach().to(device=dev, dtype=torch.float64, non_blocking=True).contiguous()
+        num_agent = num_agent_tensor.detach().to(device=dev, non_blocking=True)[:, 0].to(torch.int32).contiguous()
 
         self._pack_input(bevs, ws)
         for c in ws.enc_calls:
