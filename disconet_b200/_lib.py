@@ -50,6 +50,7 @@ class FusionDesc(C.Structure):
         ("only_v2i", C.c_int), ("trans_scale", C.c_float),
         ("out_hi", C.c_void_p), ("out_lo_off", C.c_longlong),
         ("weights", C.c_void_p),
+        ("row_begin", C.c_int), ("row_end", C.c_int),
     ]
 
 

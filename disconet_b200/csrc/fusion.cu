@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kWarps * 32) fusion_kernel(const disco_fusion_
     const int C = d.C, h = d.h, w = d.w, A = d.A, B = d.B;
     const uint16_t* feat = reinterpret_cast<const uint16_t*>(d.feat_hi);
     uint16_t* out = reinterpret_cast<uint16_t*>(d.out_hi);
-    const long long cells = (long long)B * A * h * w;
+    const long long cells = (long long)(d.row_end - d.row_begin) * h * w;
     const int cpl = 8 * VEC;  // channels per lane
 
     for (int t = 0; t < kCellsPerWarp; ++t) {
@@ -78,10 +78,11 @@ __global__ void __launch_bounds__(kWarps * 32) fusion_kernel(const disco_fusion_
         if (cell >= cells) break;  // warp-uniform
         const int x = (int)(cell % w);
         const int y = (int)((cell / w) % h);
-        const int i = (int)((cell / ((long long)w * h)) % A);
-        const int b = (int)(cell / ((long long)w * h * A));
+        const int n_i = d.row_begin + (int)(cell / ((long long)w * h));   // agent-major row of the ego map
+        const int i = n_i / B, b = n_i - i * B;
         const int n_ag = d.num_agent[b];
-        const long long row_i = (((long long)(i * B + b) * h + y) * w + x);
+        const long long row_i = (((long long)n_i * h + y) * w + x);
+        const long long row_o = (((long long)(n_i - d.row_begin) * h + y) * w + x);
 
         float acc[8 * VEC];
 #pragma unroll
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(kWarps * 32) fusion_kernel(const disco_fusion_
         }
         // ---- normalise and store -------------------------------------------------------------------
         const float inv = 1.f / esum;
-        uint16_t* o = out + row_i * C + lane * cpl;
+        uint16_t* o = out + row_o * C + lane * cpl;
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             uint32_t hi[4], lo[4];
@@ -212,7 +213,9 @@ int disco_fusion_launch(const disco_fusion_desc* d, void* stream) {
     DISCO_REQUIRE(d->hid == kHid, "fusion: PWF hidden width must be %d (got %d)", kHid, d->hid);
     DISCO_REQUIRE(d->C == 256 || d->C == 512, "fusion: C must be 256 or 512 (got %d)", d->C);
     DISCO_REQUIRE(d->A >= 1 && d->A <= 32 && d->B >= 1 && d->h > 0 && d->w > 0, "fusion: bad scene shape");
-    const long long cells = (long long)d->B * d->A * d->h * d->w;
+    DISCO_REQUIRE(d->row_begin >= 0 && d->row_begin < d->row_end && d->row_end <= d->A * d->B,
+                  "fusion: bad ego row range [%d,%d)", d->row_begin, d->row_end);
+    const long long cells = (long long)(d->row_end - d->row_begin) * d->h * d->w;
     const long long per_block = kWarps * kCellsPerWarp;
     const long long blocks = (cells + per_block - 1) / per_block;
     DISCO_REQUIRE(blocks < (1ll << 31), "fusion: too many cells");

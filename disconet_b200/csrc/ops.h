@@ -27,6 +27,9 @@ struct disco_fusion_desc {
     void* out_hi;              // fused features, same layout as feat
     long long out_lo_off;
     float* weights;            // optional [B, A(ego), A(neighbour id), h, w] softmax weights, unflipped frame
+    // ego rows (n = a*B + b) computed by this call: [row_begin, row_end); output row = n - row_begin.
+    // (0, A*B) = everything; a rank of an agent-sharded run passes its own slice.
+    int row_begin, row_end;
 };
 
 int disco_fusion_launch(const disco_fusion_desc* d, void* stream);

@@ -184,6 +184,46 @@ class DiscoNet(_DetBase):
             self._ws[key] = ws
         return ws
 
+    def forward_sharded(self, bevs_local, trans_matrices, num_agent_tensor, batch_size=1, group=None):
+        """Agent-sharded eval forward (BASELINE config 4): this rank holds the contiguous slice
+        `parallel.shard_rows(A*B, world, rank)` of the agent-major image rows.  It encodes them, takes part
+        in ONE all-gather of the collaboration-layer maps, fuses its own ego rows against every agent's
+        map and decodes them.  Returns `result` for the local rows (kd_flag-style extras are not returned).
+        """
+        import torch.distributed as dist
+        from . import parallel
+        self._check_inputs(bevs_local)
+        dev = bevs_local.device
+        A, B = self.agent_num, int(batch_size)
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        r0, r1 = parallel.shard_rows(A * B, world, rank)
+        n_loc, _, H, W, _ = bevs_local.shape
+        if n_loc != r1 - r0:
+            raise ValueError(f"rank {rank} must hold rows [{r0},{r1}) = {r1 - r0} images, got {n_loc}")
+        if n_loc == 0:
+            raise ValueError("agent-sharded forward needs at least one image row per rank")
+        P = self.plans()
+        key = ("shard", n_loc, H, W, B, r0, A * B, str(dev))
+        ws = self._ws.get(key)
+        if ws is None:
+            ws = engine.Workspace(n_loc, H, W, self.precision, dev, P["enc"], P["dec"], P["heads"], P["pwf"],
+                                  batch_size=B, agents=A, shard=(r0, A * B))
+            self._ws[key] = ws
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        trans = trans_matrices.detach().to(device=dev, dtype=torch.float64, non_blocking=True).contiguous()
+        num_agent = num_agent_tensor.detach().to(device=dev, non_blocking=True)[:, 0].to(torch.int32).contiguous()
+        self._pack_input(bevs_local, ws)
+        for c in ws.enc_calls:
+            c.launch(stream)
+        parallel.all_gather_rows(ws.buf[ws.x3_key], ws.buf["x3g"], group)     # the path's one exchange step
+        ws.en_call.launch(stream)
+        f = ws.fusion
+        f.trans, f.num_agent, f.only_v2i, f.weights = trans.data_ptr(), num_agent.data_ptr(), int(bool(self.only_v2i)), None
+        ops.fusion_forward(f, stream)
+        for c in ws.dec_calls:
+            c.launch(stream)
+        return self._run_heads(ws, stream)
+
     def outage(self) -> bool:
         """DetModelBase.py:129-137 (consumes the numpy RNG exactly like the reference)."""
         return bool(np.random.choice([True, False], p=[self.p_com_outage, 1 - self.p_com_outage]))

@@ -132,7 +132,11 @@ class Workspace:
     """NHWC activation buffers + prebuilt launches for one (N, H, W) problem size."""
 
     def __init__(self, n: int, h: int, w: int, precision: int, device, enc: Dict[str, ConvPlan],
-                 dec: Dict[str, ConvPlan], heads=None, pwf=None, batch_size: int = 1, agents: int = 1):
+                 dec: Dict[str, ConvPlan], heads=None, pwf=None, batch_size: int = 1, agents: int = 1,
+                 shard=None):
+        """`n` = image rows held by this process.  `shard = (row_begin, n_global)` for the agent-sharded
+        mode: encoder/decoder/heads run on the local rows, the fusion reads the gathered `x3g` of all
+        `n_global` rows and produces only the local ego rows."""
         if h % 16 or w % 16:
             raise ValueError(f"BEV size {h}x{w} must be a multiple of 16 (4 stride-2 stages)")
         self.n, self.h, self.w, self.precision, self.device = n, h, w, precision, device
@@ -175,13 +179,18 @@ class Workspace:
         # collaboration-layer fusion (DiscoNet only)
         self.fusion: Optional[FusionDesc] = None
         x3_dec = b[self.x3_key]
+        self.shard = shard
         if pwf is not None:
-            b["en"] = torch.empty((n, h3, w3, 256), dtype=torch.float32, device=device)
+            row_begin, n_glob = (0, n) if shard is None else shard
+            feat = b[self.x3_key]
+            if shard is not None:
+                feat = b["x3g"] = ops.alloc_act(n_glob, h3, w3, 256, precision, device)
+            b["en"] = torch.empty((n_glob, h3, w3, 256), dtype=torch.float32, device=device)
             b["x3f"] = A(h3, w3, 256)
-            self.en_call = mk(pwf["en"], [b[self.x3_key]], [0], (b["en"],), h3, w3)
+            self.en_call = ops.ConvCall(pwf["en"], [feat], [0], (b["en"],), n=n_glob, h_in=h3, w_in=w3)
             f = FusionDesc()
-            f.feat_hi = b[self.x3_key].data_ptr()
-            f.feat_lo_off = ops._lo_off(b[self.x3_key])
+            f.feat_hi = feat.data_ptr()
+            f.feat_lo_off = ops._lo_off(feat)
             f.precision = precision
             f.en = b["en"].data_ptr()
             f.hid = 128
@@ -191,6 +200,7 @@ class Workspace:
             f.trans_scale = 4.0 / 128.0
             f.out_hi = b["x3f"].data_ptr()
             f.out_lo_off = ops._lo_off(b["x3f"])
+            f.row_begin, f.row_end = row_begin, row_begin + n
             self.fusion = f
             self._pwf_keep = pwf
             x3_dec = b["x3f"]

@@ -113,6 +113,7 @@ typedef struct disco_fusion_desc {
     void* out_hi;          /* fused features, same layout as feat                                    */
     long long out_lo_off;
     float* weights;        /* optional [B, A(ego), A(neighbour id), h, w] softmax weights (unflipped) */
+    int row_begin, row_end; /* ego rows n = a*B+b computed by this call; output row = n - row_begin      */
 } disco_fusion_desc;
 
 int disco_fusion_forward(const disco_fusion_desc* d /* host */, void* stream);
