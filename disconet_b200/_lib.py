@@ -28,7 +28,7 @@ class ConvDesc(C.Structure):
         ("h_out", C.c_int), ("w_out", C.c_int),
         ("stride", C.c_int), ("taps", C.c_int), ("c_blk", C.c_int),
         ("c_out", C.c_int), ("block_n", C.c_int),
-        ("wpack", C.c_void_p), ("wref", C.c_void_p), ("bias", C.c_void_p),
+        ("wpack", C.c_void_p), ("wpack_stacked", C.c_int), ("wref", C.c_void_p), ("bias", C.c_void_p),
         ("relu", C.c_int), ("precision", C.c_int),
         ("out_mode", C.c_int),
         ("out", C.c_void_p * 2),

@@ -28,6 +28,8 @@ struct disco_conv_desc {
     int c_out;               // real output channels
     int block_n;             // N tile (multiple of 16, <= 256); weights are padded to n_tiles*block_n rows
     const void* wpack;       // [n_tile][c_block][tap][part][c_blk/8][block_n][8] 16-bit (part: hi, lo)
+    int wpack_stacked;       // 1: [n_tile][c_block][tap][c_blk/8][part][block_n][8] -- hi and lo rows of a chunk are
+                             // adjacent, so A_hi*[W_hi;W_lo] is ONE MMA of N = 2*block_n (2 MMAs per k-step, not 3)
     const float* wref;       // validator only: [c_out][tap][c_in] fp32 (BN already folded)
     const float* bias;       // [n_tiles*block_n] fp32 (BN folded; zero padded)
     int relu;

@@ -115,7 +115,7 @@ __device__ __forceinline__ Item decode_item(const ConvGeom& g, int item) {
 }
 
 // MODE 0: 3x3 stride 1 (patch 18x10) | MODE 1: 3x3 stride 2 (patch 33x17) | MODE 2: 1x1
-template <int MODE, int KSTEPS, bool SPLIT>
+template <int MODE, int KSTEPS, int PASSES>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_raw);
@@ -130,6 +130,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
     constexpr int PW = (MODE == 0) ? 10 : (MODE == 1) ? 17 : 128;
     constexpr int TAPS = (MODE == 2) ? 1 : 9;
     constexpr int STRIDE = (MODE == 1) ? 2 : 1;
+    constexpr bool SPLIT = PASSES != 1;     // bf16 hi+lo operands
+    constexpr bool STACKED = PASSES == 2;   // B image = [chunk][hi rows | lo rows][8]: hi*hi and hi*lo in ONE MMA of N = 2*block_n
+    const int acc_cols = STACKED ? 2 * g.d.block_n : g.d.block_n;   // TMEM columns written per accumulator
+    (void)acc_cols;
 
     // ---- one-time setup ------------------------------------------------------------------------
     if (tid == 0) {
@@ -183,6 +187,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                 for (int j = 0; j < d.block_n / 16; ++j) {
                     uint32_t raw[16];
                     tmem_ld16(t_lane + (uint32_t)(j * 16), raw);
+                    if (STACKED) {   // columns [N, 2N) hold A_hi * W_lo
+                        uint32_t raw2[16];
+                        tmem_ld16(t_lane + (uint32_t)(d.block_n + j * 16), raw2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            raw[i] = __float_as_uint(__uint_as_float(raw[i]) + __uint_as_float(raw2[i]));
+                    }
                     tmem_ld_wait();
                     const int nb = it.n_tile * d.block_n + j * 16;
                     float v[16];
@@ -353,13 +365,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
         // flow; one elected lane issues.
         {
             const uint32_t idesc = umma_idesc_f16(d.precision == DISCO_PREC_BF16X3, 128, d.block_n);
+            const uint32_t idesc2 = umma_idesc_f16(1, 128, 2 * d.block_n);   // STACKED: [W_hi; W_lo]
             // descriptor halves (see umma_desc_kmajor_noswizzle): lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version
-            const uint32_t lbo_b16 = (uint32_t)d.block_n;                 // block_n*16 bytes >> 4
+            const uint32_t lbo_b16 = (uint32_t)d.block_n * (STACKED ? 2u : 1u);   // rows per chunk * 16 B, >> 4
             const uint32_t a_hi = ((uint32_t)g.sbo_a >> 4) | (1u << 14);
             const uint32_t b_hi = (128u >> 4) | (1u << 14);
             const uint32_t a_lo_c = ((uint32_t)g.plane >> 4) << 16;
             const uint32_t b_lo_c = lbo_b16 << 16;
-            const uint32_t a_part16 = (uint32_t)g.a_part_bytes >> 4, b_part16 = (uint32_t)g.b_part_bytes >> 4;
+            const uint32_t a_part16 = (uint32_t)g.a_part_bytes >> 4;
+            const uint32_t b_part16 = STACKED ? (uint32_t)d.block_n : ((uint32_t)g.b_part_bytes >> 4);
             const uint32_t a_base16 = (a_base >> 4) + a_lo_c, b_base16 = (b_base >> 4) + b_lo_c;  // LBO folded in
             const uint32_t a_stage16 = (uint32_t)g.a_stage_bytes >> 4, b_stage16 = (uint32_t)g.b_stage_bytes >> 4;
             const uint32_t bar_a_full = smem_u32(&ctl->a_full[0]), bar_a_empty = smem_u32(&ctl->a_empty[0]);
@@ -423,10 +437,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
 #pragma unroll
                                     for (int ks = 0; ks < KSTEPS; ++ks) {
                                         const uint32_t alo = a16 + a_ks[ks], blo = b16 + b_ks[ks];
-                                        umma_f16_parts(td, alo, a_hi, blo, b_hi, idesc, (tap == 0 && ks == 0) ? first : 1u);
-                                        if (SPLIT) {
-                                            umma_f16_parts(td, alo + a_part16, a_hi, blo, b_hi, idesc, 1u);
-                                            umma_f16_parts(td, alo, a_hi, blo + b_part16, b_hi, idesc, 1u);
+                                        const uint32_t accf = (tap == 0 && ks == 0) ? first : 1u;
+                                        if (STACKED) {
+                                            umma_f16_parts(td, alo, a_hi, blo, b_hi, idesc2, accf);            // hi*[hi|lo]
+                                            umma_f16_parts(td, alo + a_part16, a_hi, blo, b_hi, idesc, 1u);   // lo*hi
+                                        } else {
+                                            umma_f16_parts(td, alo, a_hi, blo, b_hi, idesc, accf);
+                                            if (SPLIT) {
+                                                umma_f16_parts(td, alo + a_part16, a_hi, blo, b_hi, idesc, 1u);
+                                                umma_f16_parts(td, alo, a_hi, blo + b_part16, b_hi, idesc, 1u);
+                                            }
                                         }
                                     }
                                 }
@@ -467,6 +487,8 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     DISCO_REQUIRE(d->src_c[0] > 0 && d->src_c[0] % d->c_blk == 0 && d->src_c[1] % d->c_blk == 0,
                   "conv: source channels (%d,%d) must be multiples of c_blk %d", d->src_c[0], d->src_c[1], d->c_blk);
     DISCO_REQUIRE(d->precision == DISCO_PREC_FP16 || d->precision == DISCO_PREC_BF16X3, "conv: bad precision");
+    DISCO_REQUIRE(!d->wpack_stacked || (d->precision == DISCO_PREC_BF16X3 && d->block_n <= 128),
+                  "conv: stacked weight images need bf16x3 and block_n <= 128");
     DISCO_REQUIRE(d->taps == 9 || (d->src_up[0] == 0 && d->src_up[1] == 0), "conv: 1x1 cannot upsample");
     DISCO_REQUIRE(d->n > 0 && d->h_in > 0 && d->w_in > 0, "conv: empty input");
     if (d->taps == 9) {
@@ -520,21 +542,21 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     // MSUB = 2 (256-pixel items) when the N tile leaves room for double-buffered accumulators and the
     // image is wide enough; it halves the weight stream per MAC.
     const bool wide = (d->taps == 1) ? (g->total_pix >= 256) : (d->w_out >= 16);
-    g->msub = (wide && 4 * d->block_n <= 512) ? 2 : 1;
+    const int acc_cols = (d->wpack_stacked ? 2 : 1) * d->block_n;   // TMEM columns one accumulator writes
+    g->msub = (wide && 4 * acc_cols <= 512) ? 2 : 1;
     g->stationary = (g->n_tiles == 1 && g->w_bytes + 3 * g->a_stage_bytes <= budget) ? 1 : 0;
     if (g->stationary) g->msub = 1;  // nothing to amortise; smaller items balance better
-    g->nacc = (2 * g->msub * d->block_n <= 512) ? 2 : 1;
-    g->acc_stride = (d->block_n + 31) / 32 * 32;
-    if (2 * g->msub * g->acc_stride > 512) g->acc_stride = d->block_n;
+    g->nacc = (2 * g->msub * acc_cols <= 512) ? 2 : 1;
+    g->acc_stride = (acc_cols + 31) / 32 * 32;
+    if (g->nacc * g->msub * g->acc_stride > 512) g->acc_stride = acc_cols;
     int cols = 32;
     while (cols < g->nacc * g->msub * g->acc_stride) cols *= 2;
     g->tmem_cols = cols;
     int ctas_per_sm = 1;
-    g->acc_stride = (d->block_n + 31) / 32 * 32;
     if (g->stationary) {
         // small resident weight sets: aim for two CTAs per SM (two MMA issuers, 2x gather streams)
         int sa = (110 * 1024 - kCtlBytes - g->w_bytes) / g->a_stage_bytes;
-        if (sa >= 3 && 2 * g->nacc * g->acc_stride <= 512) ctas_per_sm = 2;
+        if (sa >= 3 && 2 * g->tmem_cols <= 512) ctas_per_sm = 2;
         else sa = (budget - g->w_bytes) / g->a_stage_bytes;
         if (sa > kMaxStages) sa = kMaxStages;
         g->SA = sa;
@@ -569,29 +591,33 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     return DISCO_OK;
 }
 
-template <int MODE, int KSTEPS, bool SPLIT>
+template <int MODE, int KSTEPS, int PASSES>
 int launch_inst(const ConvGeom& g, cudaStream_t stream) {
     static bool attr_set[64] = {false};
     int dev = 0;
     DISCO_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && !attr_set[dev]) {
-        DISCO_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MODE, KSTEPS, SPLIT>,
+        DISCO_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MODE, KSTEPS, PASSES>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set[dev] = true;
     }
-    conv_tc_kernel<MODE, KSTEPS, SPLIT><<<g.grid, kThreads, g.smem_bytes, stream>>>(g);
+    conv_tc_kernel<MODE, KSTEPS, PASSES><<<g.grid, kThreads, g.smem_bytes, stream>>>(g);
     DISCO_CHECK_CUDA(cudaGetLastError());
     return DISCO_OK;
 }
 
 template <int MODE>
 int launch_mode(const ConvGeom& g, cudaStream_t stream) {
-    const bool split = g.nparts == 2;
+    const int passes = (g.nparts == 2) ? (g.d.wpack_stacked ? 2 : 3) : 1;
+#define DISCO_LAUNCH_K(KS)                                                      \
+    (passes == 1 ? launch_inst<MODE, KS, 1>(g, stream)                          \
+                 : passes == 2 ? launch_inst<MODE, KS, 2>(g, stream) : launch_inst<MODE, KS, 3>(g, stream))
     switch (g.d.c_blk) {
-        case 16: return split ? launch_inst<MODE, 1, true>(g, stream) : launch_inst<MODE, 1, false>(g, stream);
-        case 32: return split ? launch_inst<MODE, 2, true>(g, stream) : launch_inst<MODE, 2, false>(g, stream);
-        default: return split ? launch_inst<MODE, 4, true>(g, stream) : launch_inst<MODE, 4, false>(g, stream);
+        case 16: return DISCO_LAUNCH_K(1);
+        case 32: return DISCO_LAUNCH_K(2);
+        default: return DISCO_LAUNCH_K(4);
     }
+#undef DISCO_LAUNCH_K
 }
 
 }  // namespace

@@ -64,6 +64,7 @@ def conv_forward(plan: ConvPlan, srcs: Sequence[torch.Tensor], ups: Sequence[int
     d.w_out = (w_in - 1) // plan.stride + 1
     d.c_out, d.block_n = plan.c_out, plan.block_n
     d.wpack = plan.wpack.data_ptr()
+    d.wpack_stacked = int(plan.stacked)
     d.wref = plan.wref.data_ptr() if plan.wref is not None else None
     d.bias = plan.bias.data_ptr()
     d.relu = int(plan.relu)
@@ -133,6 +134,7 @@ class ConvCall:
         d.w_out = (w_in - 1) // plan.stride + 1
         d.c_out, d.block_n = plan.c_out, plan.block_n
         d.wpack = plan.wpack.data_ptr()
+        d.wpack_stacked = int(plan.stacked)
         d.wref = plan.wref.data_ptr() if plan.wref is not None else None
         d.bias = plan.bias.data_ptr()
         d.relu = int(plan.relu)

@@ -61,6 +61,7 @@ class ConvPlan:
     wpack: torch.Tensor       # int16 storage
     bias: torch.Tensor        # fp32 [n_tiles*block_n]
     wref: Optional[torch.Tensor] = None   # fp32 [c_out, taps, c_in] (validator only)
+    stacked: bool = False     # weight image layout [..][chunk][part][n][8] (see conv.h wpack_stacked)
     name: str = ""
     flops_per_pixel: int = field(default=0)
 
@@ -94,13 +95,16 @@ def pack_conv(wf: torch.Tensor, bf: torch.Tensor, *, src_channels, stride: int =
     ncb = c_in // c_blk
     # [n_tile, n, cb, chunk, 8, tap] -> [n_tile, cb, tap, chunk, n, 8]
     w6 = w.view(n_tiles, block_n, ncb, c_blk // 8, 8, taps).permute(0, 2, 5, 3, 1, 4).contiguous()
+    # N <= 64 layers are MMA-issue-bound (~47 cycles per tcgen05.mma whatever N): stacking W_hi and W_lo
+    # as one 2N-row operand turns the three split passes into two instructions per k-step
+    stacked = precision == PREC_BF16X3 and block_n <= 64
     if precision == PREC_BF16X3:
         hi, lo = split_bf16(w6)
-        parts = torch.stack((hi, lo), dim=3)          # [n_tile, cb, tap, part, chunk, n, 8]
+        parts = torch.stack((hi, lo), dim=4 if stacked else 3)   # [.., tap, chunk, part, n, 8] | [.., tap, part, chunk, n, 8]
         wpack = parts.contiguous().view(torch.int16)
     else:
         wpack = w6.to(torch.float16).contiguous().view(torch.int16)
     wref = w[:c_out].permute(0, 2, 1).contiguous() if keep_ref else None   # [c_out, taps, c_in]
     return ConvPlan(taps=taps, stride=stride, c_in=c_in, c_out=c_out, c_blk=c_blk, block_n=block_n, relu=relu,
-                    precision=precision, wpack=wpack.reshape(-1), bias=bias, wref=wref, name=name,
+                    precision=precision, wpack=wpack.reshape(-1), bias=bias, wref=wref, name=name, stacked=stacked,
                     flops_per_pixel=2 * taps * c_in_real * c_out)

@@ -53,6 +53,7 @@ typedef struct disco_conv_desc {
     int c_out;               /* real output channels                                                   */
     int block_n;             /* N tile, multiple of 16, <= 256                                         */
     const void* wpack;       /* [n_tile][c_block][tap][part][c_blk/8][block_n][8] 16-bit               */
+    int wpack_stacked;       /* 1: [..][tap][c_blk/8][part][block_n][8] (hi|lo rows adjacent; bf16x3, N<=128) */
     const float* wref;       /* disco_conv_reference only: [c_out][tap][c_in] fp32                     */
     const float* bias;       /* [n_tiles*block_n] fp32                                                 */
     int relu;

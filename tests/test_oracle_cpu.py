@@ -137,7 +137,10 @@ def test_fold_bn_and_pack_roundtrip():
         assert plan.c_blk == 16 and plan.block_n == 32 and plan.bias.numel() == 64
         parts = 2 if prec == PREC_BF16X3 else 1
         dt = torch.bfloat16 if prec == PREC_BF16X3 else torch.float16
-        wp = plan.wpack.view(dt).view(2, 3, 9, parts, 2, 32, 8).float().sum(3)   # [nt, cb, tap, chunk, n, 8]
+        if plan.stacked:
+            wp = plan.wpack.view(dt).view(2, 3, 9, 2, parts, 32, 8).float().sum(4)
+        else:
+            wp = plan.wpack.view(dt).view(2, 3, 9, parts, 2, 32, 8).float().sum(3)   # [nt, cb, tap, chunk, n, 8]
         dec = wp.permute(0, 4, 1, 3, 5, 2).reshape(64, 48, 9)                      # [n, c_in, tap]
         tol = (2.0 ** -16 if prec == PREC_BF16X3 else 2.0 ** -10) * wpad.abs().max().item()
         assert (dec[:48] - wpad.reshape(48, 48, 9)).abs().max() < tol
