@@ -33,15 +33,20 @@
 // precision DISCO_PREC_BF16X3 keeps activations/weights as bf16 hi+lo pairs and issues three MMAs
 // per k-step (hi*hi + lo*hi + hi*lo) -> ~16 mantissa bits, which is what the <=1e-3 parity gate
 // against the fp32 reference needs (plain fp16 operands measure 2-3e-3).
+#include <stdlib.h>
 #include "common.cuh"
 #include "conv.h"
 
 namespace {
 
-constexpr int kEpiWarps = 4, kProdWarps = 4;
-constexpr int kThreads = (kEpiWarps + kProdWarps + 2) * 32;  // 320
+constexpr int kEpiWarps = 8, kProdWarps = 4;   // epilogue: two groups of 4 warps split the channel chunks of every item
+constexpr int kMmaWarps = 2;   // two independent issue streams (each owns alternate items) when weights are stationary
+constexpr int kThreads = (kEpiWarps + kProdWarps + 1 + kMmaWarps) * 32;  // 480
+constexpr int kWarpB = kEpiWarps + kProdWarps, kWarpMma = kWarpB + 1;
+constexpr int kMaxAcc = 4;
 constexpr int kMaxStages = 8;
 constexpr int kCtlBytes = 512;
+constexpr int kBiasBytes = 2048;   // bias staged in shared memory (<= 512 output channels)
 
 struct ConvGeom {
     disco_conv_desc d;
@@ -55,7 +60,9 @@ struct ConvGeom {
     int SA, SB;
     int sbo_a;
     int msub;                 // 128-pixel sub-tiles per item (1|2)
-    int nacc;                 // accumulator buffers in TMEM (1|2)
+    int nacc;                 // accumulator buffers in TMEM (1|2|4)
+    int nmma;                 // MMA issuing warps (2 when stationary: the single-thread issue stream, ~80 cycles per
+                              // tcgen05.mma here, is the bottleneck of the small-N layers; the SMEM operand port allows ~40)
     int acc_stride;           // TMEM columns per accumulator (block_n rounded up to 32)
     int nprod;                // active producer warps: min(4, SA) (a ring with fewer slots than independent
                               // producers would let one warp lap another through the parity alias)
@@ -67,6 +74,7 @@ struct ConvGeom {
     int tmem_cols;
     int smem_bytes;
     int grid;
+    long long* trace;         // debug: per-role clock64 stamps of CTA 0 (DISCO_CONV_TRACE), else null
 };
 
 struct __align__(8) SmemCtl {
@@ -74,8 +82,8 @@ struct __align__(8) SmemCtl {
     uint64_t a_empty[kMaxStages];
     uint64_t b_full[kMaxStages];
     uint64_t b_empty[kMaxStages];
-    uint64_t acc_full[2];
-    uint64_t acc_empty[2];
+    uint64_t acc_full[kMaxAcc];
+    uint64_t acc_empty[kMaxAcc];
     uint64_t w_full;
     uint32_t tmem_base;
     uint32_t pad;
@@ -120,7 +128,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_raw);
     const uint32_t smem_base = smem_u32(smem_raw);
-    const uint32_t a_base = smem_base + kCtlBytes;
+    const uint32_t a_base = smem_base + kCtlBytes + kBiasBytes;
+    const float* s_bias = reinterpret_cast<const float*>(smem_raw + kCtlBytes);
     const uint32_t b_base = a_base + g.SA * g.a_stage_bytes;
 
     const int tid = threadIdx.x;
@@ -145,14 +154,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
             mbar_init(smem_u32(&ctl->b_full[s]), 1);
             mbar_init(smem_u32(&ctl->b_empty[s]), 1);
         }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < kMaxAcc; ++s) {
             mbar_init(smem_u32(&ctl->acc_full[s]), 1);
             mbar_init(smem_u32(&ctl->acc_empty[s]), kEpiWarps * 32);
         }
         mbar_init(smem_u32(&ctl->w_full), 1);
         fence_mbar_init();
     }
-    if (warp == 9) {
+    for (int i = tid; i < g.n_tiles * g.d.block_n; i += kThreads)
+        reinterpret_cast<float*>(smem_raw + kCtlBytes)[i] = g.d.bias[i];
+    if (warp == kWarpMma) {
         tmem_alloc(smem_u32(&ctl->tmem_base), (uint32_t)g.tmem_cols);
         tmem_relinquish();
     }
@@ -161,6 +172,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
     tc_fence_after();
     const uint32_t tmem_d = ctl->tmem_base;
     const int stages_per_item = g.ncb * g.msub;
+    // trace layout: [role 0..3][item 0..63][4 stamps]; roles: 0 epilogue, 1 producer warp 0, 2 MMA, 3 B loader
+#define TRACE(role, it_, k) do { if (g.trace && blockIdx.x == 0 && (it_) < 64 && lane == 0) g.trace[((role) * 64 + (it_)) * 4 + (k)] = clock64(); } while (0)
 
     if (warp < kEpiWarps) {
         // =========================== epilogue =====================================================
@@ -168,9 +181,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
         for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++iacc) {
             const Item it = decode_item<MODE>(g, item);
             const int buf = iacc % g.nacc;
+            if (warp == 0) TRACE(0, iacc, 0);
             mbar_wait(smem_u32(&ctl->acc_full[buf]), (uint32_t)(iacc / g.nacc) & 1u);
             tc_fence_after();
-            const int m = warp * 32 + lane;
+            if (warp == 0) TRACE(0, iacc, 1);
+            const int m = (warp & 3) * 32 + lane;   // TMEM lane == pixel row of the tile; warp w may touch lanes 32*(w%4)..+31
+            const int egrp = warp >> 2;             // group 0 takes the even 16-channel chunks, group 1 the odd ones
             for (int sub = 0; sub < g.msub; ++sub) {
                 bool valid;
                 long long pixel;
@@ -182,26 +198,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                     pixel = it.p0 + sub * 128 + m;
                     valid = pixel < g.total_pix;
                 }
-                const uint32_t t_lane = tmem_d + ((uint32_t)(warp * 32) << 16) +
+                const uint32_t t_lane = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) +
                                         (uint32_t)((buf * g.msub + sub) * g.acc_stride);
-                for (int j = 0; j < d.block_n / 16; ++j) {
+                const int nchunks = d.block_n / 16;
+                uint32_t nxt[16], nxt2[16];
+                if (egrp < nchunks) {
+                    tmem_ld16(t_lane + (uint32_t)(egrp * 16), nxt);
+                    if (STACKED) tmem_ld16(t_lane + (uint32_t)(d.block_n + egrp * 16), nxt2);
+                }
+                for (int j = egrp; j < nchunks; j += 2) {
                     uint32_t raw[16];
-                    tmem_ld16(t_lane + (uint32_t)(j * 16), raw);
-                    if (STACKED) {   // columns [N, 2N) hold A_hi * W_lo
-                        uint32_t raw2[16];
-                        tmem_ld16(t_lane + (uint32_t)(d.block_n + j * 16), raw2);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            raw[i] = __float_as_uint(__uint_as_float(raw[i]) + __uint_as_float(raw2[i]));
-                    }
                     tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        raw[i] = STACKED ? __float_as_uint(__uint_as_float(nxt[i]) + __uint_as_float(nxt2[i])) : nxt[i];
+                    if (j + 2 < nchunks) {   // software pipeline: next chunk's TMEM read overlaps this chunk's math/stores
+                        tmem_ld16(t_lane + (uint32_t)((j + 2) * 16), nxt);
+                        if (STACKED) tmem_ld16(t_lane + (uint32_t)(d.block_n + (j + 2) * 16), nxt2);
+                    }
                     const int nb = it.n_tile * d.block_n + j * 16;
                     float v[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float x = __uint_as_float(raw[i]) + __ldg(d.bias + nb + i);
-                        v[i] = d.relu ? fmaxf(x, 0.f) : x;
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + nb + 4 * q);
+                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float x = __uint_as_float(raw[4 * q + i]) + bb[i];
+                            v[4 * q + i] = d.relu ? fmaxf(x, 0.f) : x;
+                        }
                     }
                     // stores are predicated per lane; the tcgen05.ld above must stay warp-convergent
                     if (valid && d.out_mode == DISCO_OUT_ACT && nb < d.c_out) {
@@ -240,6 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                 }
             }
             tc_fence_before();
+            if (warp == 0) TRACE(0, iacc, 2);
             mbar_arrive(smem_u32(&ctl->acc_empty[buf]));
         }
     } else if (warp < kEpiWarps + kProdWarps) {
@@ -256,7 +282,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                 const int ia = ia_base + s;
                 const int cb = s / g.msub, sub = s - cb * g.msub;
                 const int sa = ia % g.SA;
+                if (pw == 0) TRACE(1, ia / g.nprod, 0);
                 mbar_wait(smem_u32(&ctl->a_empty[sa]), ((uint32_t)(ia / g.SA) & 1u) ^ 1u);
+                if (pw == 0) TRACE(1, ia / g.nprod, 1);
                 const int sidx = (cb < g.ncb0) ? 0 : 1;
                 const int cbl = sidx ? cb - g.ncb0 : cb;
                 const uint16_t* __restrict__ src = reinterpret_cast<const uint16_t*>(sidx ? d.src[1] : d.src[0]);
@@ -320,12 +348,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                     }
                 }
                 cp_async_commit();
+                if (pw == 0) TRACE(1, ia / g.nprod, 2);
                 cp_async_wait<0>();
                 fence_proxy_async_smem();
+                if (pw == 0) TRACE(1, ia / g.nprod, 3);
                 mbar_arrive(smem_u32(&ctl->a_full[sa]));
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == kWarpB) {
         // =========================== B loader (bulk copy engine) ===================================
         if (lane == 0) {
             const int iters_per_tile = g.ncb * TAPS;
@@ -385,22 +415,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                 b_ks[ks] = (uint32_t)(2 * ks) * lbo_b16;
             }
             const uint32_t par16 = (uint32_t)g.parplane >> 4;
+            const int mw = warp - kWarpMma;              // issuing warp index; owns items with iacc % nmma == mw
             int iacc = 0;
-            int sa_slot = 0, sb_slot = 0;            // stage ring positions maintained incrementally
-            uint32_t sa_phase = 0, sb_phase = 0;
-            if (g.stationary) {
+            int sb_slot = 0;                             // B ring position (streamed weights: single issuer)
+            uint32_t sb_phase = 0;
+            if (g.stationary && mw < g.nmma) {
                 mbar_wait(smem_u32(&ctl->w_full), 0);
                 tc_fence_after();
             }
             for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++iacc) {
+                if (mw >= g.nmma || (iacc % g.nmma) != mw) continue;
+                int ia = iacc * stages_per_item;         // linear index of this item's first A stage
                 const int buf = iacc % g.nacc;
+                if (mw == 0) TRACE(2, iacc, 0);
                 mbar_wait(smem_u32(&ctl->acc_empty[buf]), ((uint32_t)(iacc / g.nacc) & 1u) ^ 1u);
                 tc_fence_after();
+                if (mw == 0) TRACE(2, iacc, 1);
                 const uint32_t td0 = tmem_d + (uint32_t)(buf * g.msub * g.acc_stride);
                 const uint32_t td1 = td0 + (uint32_t)g.acc_stride;
                 for (int cb = 0; cb < g.ncb; ++cb) {
                     // wait for the MSUB patches of this channel block
-                    const int slot0 = sa_slot;
+                    const int slot0 = ia % g.SA;
+                    const uint32_t sa_phase = (uint32_t)(ia / g.SA) & 1u;
                     mbar_wait(bar_a_full + 8u * slot0, sa_phase);
                     const uint32_t a0_16 = a_base16 + (uint32_t)slot0 * a_stage16;
                     int slot1 = slot0;
@@ -413,6 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                         a1_16 = a_base16 + (uint32_t)slot1 * a_stage16;
                     }
                     tc_fence_after();
+                    if (cb == 0 && mw == 0) TRACE(2, iacc, 2);
                     const uint32_t first = (cb > 0) ? 1u : 0u;   // accumulate flag of the first MMA of the item
 #pragma unroll
                     for (int tap = 0; tap < TAPS; ++tap) {
@@ -463,18 +500,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                         if (g.msub == 2) umma_commit(bar_a_empty + 8u * slot1);
                     }
                     __syncwarp();
-                    sa_slot += g.msub;
-                    if (sa_slot >= g.SA) { sa_slot -= g.SA; sa_phase ^= 1u; }
+                    ia += g.msub;
                 }
                 if (elect_one()) umma_commit(smem_u32(&ctl->acc_full[buf]));
                 __syncwarp();
+                if (mw == 0) TRACE(2, iacc, 3);
             }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem_d, (uint32_t)g.tmem_cols);
+    if (warp == kWarpMma) tmem_dealloc(tmem_d, (uint32_t)g.tmem_cols);
 }
 
 int g_num_sms = 0;
@@ -491,6 +528,7 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
                   "conv: stacked weight images need bf16x3 and block_n <= 128");
     DISCO_REQUIRE(d->taps == 9 || (d->src_up[0] == 0 && d->src_up[1] == 0), "conv: 1x1 cannot upsample");
     DISCO_REQUIRE(d->n > 0 && d->h_in > 0 && d->w_in > 0, "conv: empty input");
+    DISCO_REQUIRE(((d->c_out + d->block_n - 1) / d->block_n) * d->block_n * 4 <= kBiasBytes, "conv: c_out %d too large", d->c_out);
     if (d->taps == 9) {
         DISCO_REQUIRE(d->h_out == (d->h_in - 1) / d->stride + 1 && d->w_out == (d->w_in - 1) / d->stride + 1,
                       "conv: output size %dx%d inconsistent with input %dx%d stride %d", d->h_out, d->w_out, d->h_in,
@@ -513,6 +551,10 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     }
 
     g->d = *d;
+    {
+        const char* tr = getenv("DISCO_CONV_TRACE");
+        g->trace = tr ? (long long*)strtoull(tr, nullptr, 0) : nullptr;
+    }
     g->ncb0 = d->src_c[0] / d->c_blk;
     g->ncb = g->ncb0 + d->src_c[1] / d->c_blk;
     g->chunks = d->c_blk / 8;
@@ -537,7 +579,7 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     g->n_tiles = (d->c_out + d->block_n - 1) / d->block_n;
     g->total_pix = (long long)d->n * d->h_out * d->w_out;
 
-    const int budget = 224 * 1024 - kCtlBytes;
+    const int budget = 224 * 1024 - kCtlBytes - kBiasBytes;
     g->w_bytes = g->ncb * d->taps * g->b_stage_bytes;
     // MSUB = 2 (256-pixel items) when the N tile leaves room for double-buffered accumulators and the
     // image is wide enough; it halves the weight stream per MAC.
@@ -547,6 +589,11 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     g->stationary = (g->n_tiles == 1 && g->w_bytes + 3 * g->a_stage_bytes <= budget) ? 1 : 0;
     if (g->stationary) g->msub = 1;  // nothing to amortise; smaller items balance better
     g->nacc = (2 * g->msub * acc_cols <= 512) ? 2 : 1;
+    g->nmma = 1;
+    if (g->stationary && g->nacc == 2) {
+        g->nmma = kMmaWarps;
+        if (kMaxAcc * g->msub * ((acc_cols + 31) / 32 * 32) <= 256) g->nacc = kMaxAcc;   // two buffers per issuer
+    }
     g->acc_stride = (acc_cols + 31) / 32 * 32;
     if (g->nacc * g->msub * g->acc_stride > 512) g->acc_stride = acc_cols;
     int cols = 32;
@@ -555,13 +602,12 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     int ctas_per_sm = 1;
     if (g->stationary) {
         // small resident weight sets: aim for two CTAs per SM (two MMA issuers, 2x gather streams)
-        int sa = (110 * 1024 - kCtlBytes - g->w_bytes) / g->a_stage_bytes;
-        if (sa >= 3 && 2 * g->tmem_cols <= 512) ctas_per_sm = 2;
-        else sa = (budget - g->w_bytes) / g->a_stage_bytes;
+        int sa;
+        sa = (budget - g->w_bytes) / g->a_stage_bytes;   // one CTA per SM: the MMA issue port is per SM anyway
         if (sa > kMaxStages) sa = kMaxStages;
         g->SA = sa;
         g->SB = 1;
-        g->smem_bytes = kCtlBytes + g->SA * g->a_stage_bytes + g->w_bytes;
+        g->smem_bytes = kCtlBytes + kBiasBytes + g->SA * g->a_stage_bytes + g->w_bytes;
     } else {
         int sa = 2 * g->msub;  // current + next channel block
         if (sa < 4 && 4 * g->a_stage_bytes <= budget / 3) sa = 4;
@@ -575,7 +621,7 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
                       g->a_stage_bytes, g->b_stage_bytes);
         g->SA = sa;
         g->SB = sb;
-        g->smem_bytes = kCtlBytes + g->SA * g->a_stage_bytes + g->SB * g->b_stage_bytes;
+        g->smem_bytes = kCtlBytes + kBiasBytes + g->SA * g->a_stage_bytes + g->SB * g->b_stage_bytes;
     }
     DISCO_REQUIRE(g->SA >= g->msub && g->SA >= 1, "conv: not enough A stages");
     g->nprod = g->SA < kProdWarps ? g->SA : kProdWarps;
