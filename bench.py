@@ -176,7 +176,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--scenes", type=int, default=8, help="scenes per step per GPU (batch in flight)")
+    ap.add_argument("--scenes", type=int, default=16, help="scenes per step per GPU (batch in flight)")
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "fp16"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

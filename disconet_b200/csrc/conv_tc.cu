@@ -39,7 +39,7 @@
 
 namespace {
 
-constexpr int kEpiWarps = 8, kProdWarps = 4;   // epilogue: two groups of 4 warps split the channel chunks of every item
+constexpr int kEpiWarps = 8, kProdWarps = 4;   // two epilogue groups of 4 warps, each owning alternate items
 constexpr int kMmaWarps = 2;   // two independent issue streams (each owns alternate items) when weights are stationary
 constexpr int kThreads = (kEpiWarps + kProdWarps + 1 + kMmaWarps) * 32;  // 480
 constexpr int kWarpB = kEpiWarps + kProdWarps, kWarpMma = kWarpB + 1;
@@ -47,6 +47,9 @@ constexpr int kMaxAcc = 4;
 constexpr int kMaxStages = 8;
 constexpr int kCtlBytes = 512;
 constexpr int kBiasBytes = 2048;   // bias staged in shared memory (<= 512 output channels)
+constexpr int kStageRow = 80;      // epilogue staging: per pixel 16 ch hi (32 B) + lo (32 B) + 16 B pad (bank spread)
+constexpr int kStagePerWarp = 32 * kStageRow;
+constexpr int kStageBytes = kEpiWarps * kStagePerWarp;   // 20 KB
 
 struct ConvGeom {
     disco_conv_desc d;
@@ -64,8 +67,9 @@ struct ConvGeom {
     int nmma;                 // MMA issuing warps (2 when stationary: the single-thread issue stream, ~80 cycles per
                               // tcgen05.mma here, is the bottleneck of the small-N layers; the SMEM operand port allows ~40)
     int acc_stride;           // TMEM columns per accumulator (block_n rounded up to 32)
-    int nprod;                // active producer warps: min(4, SA) (a ring with fewer slots than independent
+    int nprod;                // producer warps per A ring: min(4 / nmma, SAr) (a ring with fewer slots than independent
                               // producers would let one warp lap another through the parity alias)
+    int SAr;                  // slots per A ring = SA / nmma
     int stationary;           // weights resident in smem
     int w_bytes;              // stationary: bytes of one n_tile's weights
     int tiles_h, tiles_w;
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_raw);
     const uint32_t smem_base = smem_u32(smem_raw);
-    const uint32_t a_base = smem_base + kCtlBytes + kBiasBytes;
+    const uint32_t a_base = smem_base + kCtlBytes + kBiasBytes + kStageBytes;
     const float* s_bias = reinterpret_cast<const float*>(smem_raw + kCtlBytes);
     const uint32_t b_base = a_base + g.SA * g.a_stage_bytes;
 
@@ -156,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
         }
         for (int s = 0; s < kMaxAcc; ++s) {
             mbar_init(smem_u32(&ctl->acc_full[s]), 1);
-            mbar_init(smem_u32(&ctl->acc_empty[s]), kEpiWarps * 32);
+            mbar_init(smem_u32(&ctl->acc_empty[s]), 4 * 32);   // one epilogue group (4 warps) drains a buffer
         }
         mbar_init(smem_u32(&ctl->w_full), 1);
         fence_mbar_init();
@@ -178,7 +182,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
     if (warp < kEpiWarps) {
         // =========================== epilogue =====================================================
         int iacc = 0;
+        const int egrp = warp >> 2;   // the epilogue of one item is latency-bound (~3000 cycles); two groups overlap two items
         for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++iacc) {
+            if ((iacc & 1) != egrp) continue;
             const Item it = decode_item<MODE>(g, item);
             const int buf = iacc % g.nacc;
             if (warp == 0) TRACE(0, iacc, 0);
@@ -186,7 +192,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
             tc_fence_after();
             if (warp == 0) TRACE(0, iacc, 1);
             const int m = (warp & 3) * 32 + lane;   // TMEM lane == pixel row of the tile; warp w may touch lanes 32*(w%4)..+31
-            const int egrp = warp >> 2;             // group 0 takes the even 16-channel chunks, group 1 the odd ones
             for (int sub = 0; sub < g.msub; ++sub) {
                 bool valid;
                 long long pixel;
@@ -202,19 +207,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                                         (uint32_t)((buf * g.msub + sub) * g.acc_stride);
                 const int nchunks = d.block_n / 16;
                 uint32_t nxt[16], nxt2[16];
-                if (egrp < nchunks) {
-                    tmem_ld16(t_lane + (uint32_t)(egrp * 16), nxt);
-                    if (STACKED) tmem_ld16(t_lane + (uint32_t)(d.block_n + egrp * 16), nxt2);
-                }
-                for (int j = egrp; j < nchunks; j += 2) {
+                tmem_ld16(t_lane, nxt);
+                if (STACKED) tmem_ld16(t_lane + (uint32_t)d.block_n, nxt2);
+                for (int j = 0; j < nchunks; ++j) {
                     uint32_t raw[16];
                     tmem_ld_wait();
+                    if (warp == 0 && sub == 0 && j == 0) TRACE(0, iacc, 3);
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
                         raw[i] = STACKED ? __float_as_uint(__uint_as_float(nxt[i]) + __uint_as_float(nxt2[i])) : nxt[i];
-                    if (j + 2 < nchunks) {   // software pipeline: next chunk's TMEM read overlaps this chunk's math/stores
-                        tmem_ld16(t_lane + (uint32_t)((j + 2) * 16), nxt);
-                        if (STACKED) tmem_ld16(t_lane + (uint32_t)(d.block_n + (j + 2) * 16), nxt2);
+                    if (j + 1 < nchunks) {   // software pipeline: next chunk's TMEM read overlaps this chunk's math/stores
+                        tmem_ld16(t_lane + (uint32_t)((j + 1) * 16), nxt);
+                        if (STACKED) tmem_ld16(t_lane + (uint32_t)(d.block_n + (j + 1) * 16), nxt2);
                     }
                     const int nb = it.n_tile * d.block_n + j * 16;
                     float v[16];
@@ -228,28 +232,55 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                             v[4 * q + i] = d.relu ? fmaxf(x, 0.f) : x;
                         }
                     }
-                    // stores are predicated per lane; the tcgen05.ld above must stay warp-convergent
-                    if (valid && d.out_mode == DISCO_OUT_ACT && nb < d.c_out) {
-                        uint16_t* oh_ = reinterpret_cast<uint16_t*>(d.out[0]) + pixel * d.c_out + nb;
-                        if (d.precision == DISCO_PREC_BF16X3) {
+                    if (d.out_mode == DISCO_OUT_ACT) {
+                        // Stage the warp's 32 pixels x 16 channels in shared memory, then store row-wise: each
+                        // store instruction writes 8 neighbouring pixels x 32 B (full sectors; one contiguous 512 B
+                        // run per two chunks when c_out == 32) instead of 32 half-filled sectors 2*c_out bytes apart.
+                        uint8_t* st = smem_raw + kCtlBytes + kBiasBytes + warp * kStagePerWarp;
+                        uint4 h0v, h1v, l0v, l1v;
+                        if (SPLIT) {
                             float lo[16];
 #pragma unroll
                             for (int i = 0; i < 16; ++i) lo[i] = v[i] - bf16_bits_to_f32(f32_to_bf16_bits(v[i]));
-                            reinterpret_cast<uint4*>(oh_)[0] = pack_bf16x8(v);
-                            reinterpret_cast<uint4*>(oh_)[1] = pack_bf16x8(v + 8);
-                            uint16_t* ol_ = oh_ + d.out_lo_off;
-                            reinterpret_cast<uint4*>(ol_)[0] = pack_bf16x8(lo);
-                            reinterpret_cast<uint4*>(ol_)[1] = pack_bf16x8(lo + 8);
+                            h0v = pack_bf16x8(v); h1v = pack_bf16x8(v + 8);
+                            l0v = pack_bf16x8(lo); l1v = pack_bf16x8(lo + 8);
                         } else {
                             uint32_t w[8];
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
-                                w[i] = (uint32_t)f32_to_f16_bits(v[2 * i]) |
-                                       ((uint32_t)f32_to_f16_bits(v[2 * i + 1]) << 16);
-                            reinterpret_cast<uint4*>(oh_)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                            reinterpret_cast<uint4*>(oh_)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                                w[i] = (uint32_t)f32_to_f16_bits(v[2 * i]) | ((uint32_t)f32_to_f16_bits(v[2 * i + 1]) << 16);
+                            h0v = make_uint4(w[0], w[1], w[2], w[3]); h1v = make_uint4(w[4], w[5], w[6], w[7]);
+                            l0v = h0v; l1v = h1v;
                         }
-                    } else if (valid && d.out_mode == DISCO_OUT_F32) {
+                        __syncwarp();   // previous chunk's read-back is done
+                        uint4* row = reinterpret_cast<uint4*>(st + lane * kStageRow);
+                        row[0] = h0v; row[1] = h1v;
+                        if (SPLIT) { row[2] = l0v; row[3] = l1v; }
+                        __syncwarp();
+                        if (nb < d.c_out) {
+#pragma unroll
+                            for (int r = 0; r < 2; ++r) {   // 2 passes x 16 pixels x 2 pieces of 16 B
+                                const int px = r * 16 + (lane >> 1), piece = lane & 1;
+                                const int m2 = (warp & 3) * 32 + px;
+                                bool ok;
+                                long long pix2;
+                                if (MODE != 2) {
+                                    const int oh = it.h0 + (m2 >> 3), ow = it.w0 + sub * 8 + (m2 & 7);
+                                    ok = (oh < d.h_out) && (ow < d.w_out);
+                                    pix2 = ((long long)it.img * d.h_out + oh) * d.w_out + ow;
+                                } else {
+                                    pix2 = it.p0 + sub * 128 + m2;
+                                    ok = pix2 < g.total_pix;
+                                }
+                                if (ok) {
+                                    const uint4* srow = reinterpret_cast<const uint4*>(st + px * kStageRow);
+                                    uint16_t* o = reinterpret_cast<uint16_t*>(d.out[0]) + pix2 * d.c_out + nb + piece * 8;
+                                    *reinterpret_cast<uint4*>(o) = srow[piece];
+                                    if (SPLIT) *reinterpret_cast<uint4*>(o + d.out_lo_off) = srow[2 + piece];
+                                }
+                            }
+                        }
+                    } else if (valid) {
                         const int c1 = d.c_out - d.out_split;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
@@ -272,19 +303,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
         // =========================== A producers: warp p owns stages p, p+4, p+8, ... ===============
         const int pw = warp - kEpiWarps;
         const int per_part = g.PIX << g.chunk_shift;
-        int ia_base = 0;  // global stage index of the first stage of the current item
-        for (int item = blockIdx.x; item < g.items; item += gridDim.x, ia_base += stages_per_item) {
+        // A-stage rings: with two MMA issuers every issuer owns a private ring (slots [r*SAr, (r+1)*SAr)) fed with
+        // the stages of "its" items only -- an mbarrier ring is only safe with ONE in-order consumer (a second
+        // consumer could be a full wrap ahead and pass the parity wait on a stale phase).  Producer warp pw serves
+        // ring pw % nmma and, inside it, the stages q with q % nprod == pw / nmma (nprod <= SAr, same argument).
+        const int ring = pw % g.nmma, pr = pw / g.nmma;
+        int iacc_p = 0;
+        for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++iacc_p) {
+            if (pr >= g.nprod) break;
+            if ((iacc_p % g.nmma) != ring) continue;
             const Item it = decode_item<MODE>(g, item);
-            if (pw >= g.nprod) break;
-            // first local stage s (0 <= s < stages_per_item) with (ia_base + s) % nprod == pw
-            const int s0 = (pw - (ia_base % g.nprod) + g.nprod) % g.nprod;
+            const int q0 = (iacc_p / g.nmma) * stages_per_item;   // ring-local index of this item's first stage
+            const int s0 = (pr - (q0 % g.nprod) + g.nprod) % g.nprod;
             for (int s = s0; s < stages_per_item; s += g.nprod) {
-                const int ia = ia_base + s;
+                const int q = q0 + s;
                 const int cb = s / g.msub, sub = s - cb * g.msub;
-                const int sa = ia % g.SA;
-                if (pw == 0) TRACE(1, ia / g.nprod, 0);
-                mbar_wait(smem_u32(&ctl->a_empty[sa]), ((uint32_t)(ia / g.SA) & 1u) ^ 1u);
-                if (pw == 0) TRACE(1, ia / g.nprod, 1);
+                const int sa = ring * g.SAr + q % g.SAr;
+                if (pw == 0) TRACE(1, q / g.nprod, 0);
+                mbar_wait(smem_u32(&ctl->a_empty[sa]), ((uint32_t)(q / g.SAr) & 1u) ^ 1u);
+                if (pw == 0) TRACE(1, q / g.nprod, 1);
                 const int sidx = (cb < g.ncb0) ? 0 : 1;
                 const int cbl = sidx ? cb - g.ncb0 : cb;
                 const uint16_t* __restrict__ src = reinterpret_cast<const uint16_t*>(sidx ? d.src[1] : d.src[0]);
@@ -348,10 +385,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                     }
                 }
                 cp_async_commit();
-                if (pw == 0) TRACE(1, ia / g.nprod, 2);
+                if (pw == 0) TRACE(1, q / g.nprod, 2);
                 cp_async_wait<0>();
                 fence_proxy_async_smem();
-                if (pw == 0) TRACE(1, ia / g.nprod, 3);
+                if (pw == 0) TRACE(1, q / g.nprod, 3);
                 mbar_arrive(smem_u32(&ctl->a_full[sa]));
             }
         }
@@ -425,7 +462,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
             }
             for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++iacc) {
                 if (mw >= g.nmma || (iacc % g.nmma) != mw) continue;
-                int ia = iacc * stages_per_item;         // linear index of this item's first A stage
+                int ia = (iacc / g.nmma) * stages_per_item;   // ring-local index of this item's first A stage
+                const int ring0 = mw * g.SAr;                  // this issuer's private A ring
                 const int buf = iacc % g.nacc;
                 if (mw == 0) TRACE(2, iacc, 0);
                 mbar_wait(smem_u32(&ctl->acc_empty[buf]), ((uint32_t)(iacc / g.nacc) & 1u) ^ 1u);
@@ -435,8 +473,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                 const uint32_t td1 = td0 + (uint32_t)g.acc_stride;
                 for (int cb = 0; cb < g.ncb; ++cb) {
                     // wait for the MSUB patches of this channel block
-                    const int slot0 = ia % g.SA;
-                    const uint32_t sa_phase = (uint32_t)(ia / g.SA) & 1u;
+                    const int slot0 = ring0 + ia % g.SAr;
+                    const uint32_t sa_phase = (uint32_t)(ia / g.SAr) & 1u;
                     mbar_wait(bar_a_full + 8u * slot0, sa_phase);
                     const uint32_t a0_16 = a_base16 + (uint32_t)slot0 * a_stage16;
                     int slot1 = slot0;
@@ -444,7 +482,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                     if (g.msub == 2) {
                         slot1 = slot0 + 1;
                         uint32_t phase1 = sa_phase;
-                        if (slot1 == g.SA) { slot1 = 0; phase1 ^= 1u; }
+                        if (slot1 == ring0 + g.SAr) { slot1 = ring0; phase1 ^= 1u; }
                         mbar_wait(bar_a_full + 8u * slot1, phase1);
                         a1_16 = a_base16 + (uint32_t)slot1 * a_stage16;
                     }
@@ -579,7 +617,7 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     g->n_tiles = (d->c_out + d->block_n - 1) / d->block_n;
     g->total_pix = (long long)d->n * d->h_out * d->w_out;
 
-    const int budget = 224 * 1024 - kCtlBytes - kBiasBytes;
+    const int budget = 224 * 1024 - kCtlBytes - kBiasBytes - kStageBytes;
     g->w_bytes = g->ncb * d->taps * g->b_stage_bytes;
     // MSUB = 2 (256-pixel items) when the N tile leaves room for double-buffered accumulators and the
     // image is wide enough; it halves the weight stream per MAC.
@@ -587,12 +625,12 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     const int acc_cols = (d->wpack_stacked ? 2 : 1) * d->block_n;   // TMEM columns one accumulator writes
     g->msub = (wide && 4 * acc_cols <= 512) ? 2 : 1;
     g->stationary = (g->n_tiles == 1 && g->w_bytes + 3 * g->a_stage_bytes <= budget) ? 1 : 0;
-    if (g->stationary) g->msub = 1;  // nothing to amortise; smaller items balance better
+    if (g->stationary) g->msub = 1;  // nothing to amortise (measured: MSUB=2 is 5-15% slower on the stationary layers)
     g->nacc = (2 * g->msub * acc_cols <= 512) ? 2 : 1;
     g->nmma = 1;
     if (g->stationary && g->nacc == 2) {
         g->nmma = kMmaWarps;
-        if (kMaxAcc * g->msub * ((acc_cols + 31) / 32 * 32) <= 256) g->nacc = kMaxAcc;   // two buffers per issuer
+        if (kMaxAcc * g->msub * ((acc_cols + 31) / 32 * 32) <= 512) g->nacc = kMaxAcc;   // two buffers per issuer
     }
     g->acc_stride = (acc_cols + 31) / 32 * 32;
     if (g->nacc * g->msub * g->acc_stride > 512) g->acc_stride = acc_cols;
@@ -607,7 +645,7 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
         if (sa > kMaxStages) sa = kMaxStages;
         g->SA = sa;
         g->SB = 1;
-        g->smem_bytes = kCtlBytes + kBiasBytes + g->SA * g->a_stage_bytes + g->w_bytes;
+        g->smem_bytes = kCtlBytes + kBiasBytes + kStageBytes + g->SA * g->a_stage_bytes + g->w_bytes;
     } else {
         int sa = 2 * g->msub;  // current + next channel block
         if (sa < 4 && 4 * g->a_stage_bytes <= budget / 3) sa = 4;
@@ -621,10 +659,14 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
                       g->a_stage_bytes, g->b_stage_bytes);
         g->SA = sa;
         g->SB = sb;
-        g->smem_bytes = kCtlBytes + kBiasBytes + g->SA * g->a_stage_bytes + g->SB * g->b_stage_bytes;
+        g->smem_bytes = kCtlBytes + kBiasBytes + kStageBytes + g->SA * g->a_stage_bytes + g->SB * g->b_stage_bytes;
     }
     DISCO_REQUIRE(g->SA >= g->msub && g->SA >= 1, "conv: not enough A stages");
-    g->nprod = g->SA < kProdWarps ? g->SA : kProdWarps;
+    if (g->nmma == 2 && g->SA / 2 < g->msub) g->nmma = 1;   // not enough stages for two private rings
+    g->SAr = g->SA / g->nmma;
+    g->nprod = kProdWarps / g->nmma;
+    if (g->nprod > g->SAr) g->nprod = g->SAr;
+    DISCO_REQUIRE(g->SAr >= g->msub && g->nprod >= 1, "conv: A ring too small");
     g->tiles_h = (d->h_out + 15) / 16;
     g->tiles_w = (d->w_out + 8 * g->msub - 1) / (8 * g->msub);
     const long long m_tiles = (d->taps == 9) ? (long long)d->n * g->tiles_h * g->tiles_w

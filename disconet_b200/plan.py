@@ -97,7 +97,7 @@ def pack_conv(wf: torch.Tensor, bf: torch.Tensor, *, src_channels, stride: int =
     w6 = w.view(n_tiles, block_n, ncb, c_blk // 8, 8, taps).permute(0, 2, 5, 3, 1, 4).contiguous()
     # N <= 64 layers are MMA-issue-bound (~47 cycles per tcgen05.mma whatever N): stacking W_hi and W_lo
     # as one 2N-row operand turns the three split passes into two instructions per k-step
-    stacked = precision == PREC_BF16X3 and block_n <= 64 and taps * c_in >= 512
+    stacked = precision == PREC_BF16X3 and block_n <= 64
     if precision == PREC_BF16X3:
         hi, lo = split_bf16(w6)
         parts = torch.stack((hi, lo), dim=4 if stacked else 3)   # [.., tap, chunk, part, n, 8] | [.., tap, part, chunk, n, 8]

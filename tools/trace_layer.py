@@ -23,7 +23,7 @@ for name in sys.argv[1:]:
     t = tr.cpu().view(4, 64, 4)
     t0 = t[t > 0].min().item()
     print(f"== {name}: stamps in cycles since first stamp (CTA 0)")
-    print("item | epi: wait_start got_acc done | mma: wait_accempty got start_issue committed | prod0(stage): wait_empty got issued landed")
+    print("item | epi: wait_start got_acc done first_ld_done | mma: wait_accempty got start_issue committed | prod0(stage): wait_empty got issued landed")
     for i in range(12):
         f = lambda r: " ".join(f"{(x - t0) if x > 0 else -1:7d}" for x in t[r, i].tolist())
         print(f"{i:3d} | {f(0)} | {f(2)} | {f(1)}")
