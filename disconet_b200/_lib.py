@@ -51,6 +51,7 @@ class FusionDesc(C.Structure):
         ("out_hi", C.c_void_p), ("out_lo_off", C.c_longlong),
         ("weights", C.c_void_p),
         ("row_begin", C.c_int), ("row_end", C.c_int),
+        ("outage", C.c_void_p),
     ]
 
 

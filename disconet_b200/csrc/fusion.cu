@@ -89,9 +89,12 @@ __global__ void __launch_bounds__(kWarps * 32) fusion_kernel(const disco_fusion_
         for (int c = 0; c < 8 * VEC; ++c) acc[c] = 0.f;
         float esum = 0.f;
 
-        if (i >= n_ag) {  // absent agent: features pass through unchanged
+        const bool passthrough = (i >= n_ag) || (d.outage && d.outage[b * A + i]);
+        if (passthrough) {  // absent agent / communication outage: features pass through unchanged
             load_feat<VEC>(feat + row_i * C + lane * cpl, d.feat_lo_off, d.precision, 1.f, acc);
             esum = 1.f;
+            if (d.weights && lane < A && i < n_ag)   // outage: the ego is its own (only) contributor
+                d.weights[((((long long)b * A + i) * A + lane) * h + y) * w + x] = (lane == i) ? 1.f : 0.f;
         } else {
             const float4 e4 = __ldg(reinterpret_cast<const float4*>(d.en + row_i * (2 * kHid)) + lane);
             const int yf = h - 1 - y;  // row in the H-flipped frame the reference warps in
@@ -185,8 +188,8 @@ __global__ void __launch_bounds__(kWarps * 32) fusion_kernel(const disco_fusion_
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float a = (i >= n_ag) ? acc[8 * v + 2 * q] : acc[8 * v + 2 * q] * inv;
-                const float c2 = (i >= n_ag) ? acc[8 * v + 2 * q + 1] : acc[8 * v + 2 * q + 1] * inv;
+                const float a = passthrough ? acc[8 * v + 2 * q] : acc[8 * v + 2 * q] * inv;
+                const float c2 = passthrough ? acc[8 * v + 2 * q + 1] : acc[8 * v + 2 * q + 1] * inv;
                 if (d.precision == DISCO_PREC_BF16X3) {
                     uint16_t h0, l0, h1_, l1;
                     split_bf16(a, h0, l0);

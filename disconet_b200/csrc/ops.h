@@ -30,6 +30,8 @@ struct disco_fusion_desc {
     // ego rows (n = a*B + b) computed by this call: [row_begin, row_end); output row = n - row_begin.
     // (0, A*B) = everything; a rank of an agent-sharded run passes its own slice.
     int row_begin, row_end;
+    const int* outage;         // optional [B, A] int32: 1 = communication outage for that ego (DetModelBase.py:129-137,
+                               // DiscoNet.py:68-69): the ego keeps its own features
 };
 
 int disco_fusion_launch(const disco_fusion_desc* d, void* stream);

@@ -28,8 +28,8 @@ class AgentWeightList(collections.abc.Sequence):
     the list of [h, w] softmax weight maps in neighbour order [ego, j0, j1, ...] (H-flipped frame, as the
     reference computes them).  Materialised lazily so that the forward itself needs no host sync."""
 
-    def __init__(self, weights: torch.Tensor, num_agent: torch.Tensor, only_v2i: bool):
-        self._w, self._na, self._v2i, self._items = weights, num_agent, only_v2i, None
+    def __init__(self, weights: torch.Tensor, num_agent: torch.Tensor, only_v2i: bool, outage=None):
+        self._w, self._na, self._v2i, self._items, self._out = weights, num_agent, only_v2i, None, outage
 
     def _build(self):
         if self._items is None:
@@ -38,7 +38,10 @@ class AgentWeightList(collections.abc.Sequence):
             wf = torch.flip(self._w, (3,))
             for b, n in enumerate(na):
                 for i in range(n):
-                    js = [i] + [j for j in range(n) if j != i and not (self._v2i and i != 0 and j != 0)]
+                    if self._out is not None and int(self._out[b, i]):
+                        js = [i]   # outage: the ego alone (the reference re-appends a stale list here, DiscoNet.py:113)
+                    else:
+                        js = [i] + [j for j in range(n) if j != i and not (self._v2i and i != 0 and j != 0)]
                     items.append([wf[b, i, j] for j in js])
             self._items = items
         return self._items
@@ -235,8 +238,6 @@ class DiscoNet(_DetBase):
         Returns (result, x_8, x_7, x_6, x_5, feat_fuse_mat) if kd_flag == 1 else (result, weight list).
         """
         self._check_inputs(bevs)
-        if self.p_com_outage != 0.0:
-            raise NotImplementedError("communication outage (p_com_outage > 0) is not implemented yet")
         dev = bevs.device
         N, _, H, W, _ = bevs.shape
         A, B = self.agent_num, int(batch_size)
@@ -258,6 +259,18 @@ class DiscoNet(_DetBase):
         f.trans = trans.data_ptr()
         f.num_agent = num_agent.data_ptr()
         f.only_v2i = int(bool(self.only_v2i))
+        outage_host = None
+        f.outage = None
+        if self.p_com_outage != 0.0:
+            # the reference draws np.random.choice once per (scene, present ego) inside its loops
+            # (DiscoNet.py:59-69); same order and RNG consumption here (needs num_agent on the host)
+            na_host = num_agent_tensor.detach()[:, 0].tolist()
+            outage_host = torch.zeros((B, A), dtype=torch.int32)
+            for b in range(B):
+                for i in range(int(na_host[b])):
+                    outage_host[b, i] = int(self.outage())
+            outage_dev = outage_host.to(dev)
+            f.outage = outage_dev.data_ptr()
         weights = None
         if self.kd_flag != 1:
             weights = torch.empty((B, A, A, ws.h // 8, ws.w // 8), dtype=torch.float32, device=dev)
@@ -273,7 +286,7 @@ class DiscoNet(_DetBase):
         if self.kd_flag == 1:
             return (result, self._nchw(ws, "x8"), self._nchw(ws, "x7"), self._nchw(ws, "x6"), self._nchw(ws, "x5"),
                     self._nchw(ws, "x3f"))
-        return result, AgentWeightList(weights, num_agent, bool(self.only_v2i))
+        return result, AgentWeightList(weights, num_agent, bool(self.only_v2i), outage_host)
 
 
 class _StpnModel(_DetBase):

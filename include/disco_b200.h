@@ -115,6 +115,7 @@ typedef struct disco_fusion_desc {
     long long out_lo_off;
     float* weights;        /* optional [B, A(ego), A(neighbour id), h, w] softmax weights (unflipped) */
     int row_begin, row_end; /* ego rows n = a*B+b computed by this call; output row = n - row_begin      */
+    const int* outage;     /* optional [B, A] int32 (device): 1 = outage, ego keeps its own features    */
 } disco_fusion_desc;
 
 int disco_fusion_forward(const disco_fusion_desc* d /* host */, void* stream);

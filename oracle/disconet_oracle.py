@@ -112,7 +112,7 @@ def warp_to_ego(nb_feat, tfm_ji):
                          align_corners=False)[0]
 
 
-def fuse(sd, x3, trans_matrices, num_agent_tensor, batch_size, agent_num, only_v2i=False):
+def fuse(sd, x3, trans_matrices, num_agent_tensor, batch_size, agent_num, only_v2i=False, outage=None):
     """DiscoGraph fusion of the collaboration layer.
 
     x3 [A*B,C,h,w] agent-major (row a*B+b) -> (fused [A*B,C,h,w], weights[b][i] = list of [h,w]).
@@ -131,6 +131,9 @@ def fuse(sd, x3, trans_matrices, num_agent_tensor, batch_size, agent_num, only_v
         for i in range(n_ag):
             ego = com[b, i]
             nbs = [ego]
+            if outage is not None and bool(outage[b][i]):   # DiscoNet.py:68-69: ego keeps its own features
+                per_b.append([torch.ones(h, w)])
+                continue
             for j in range(n_ag):
                 if j == i:
                     continue
@@ -161,14 +164,14 @@ def heads(sd, x8, category_num=2, anchors=6, box_code=6):
 
 @torch.no_grad()
 def disconet_forward(sd, bevs, trans_matrices, num_agent_tensor, batch_size, agent_num=5,
-                     layer=3, only_v2i=False, return_all=False):
+                     layer=3, only_v2i=False, return_all=False, outage=None):
     """Eval-mode DiscoNet.forward (DiscoNet.py:28-129).  bevs [A*B,1,H,W,13]."""
     if layer != 3:
         raise NotImplementedError("oracle restates the CLI default --layer 3")
     bev = bevs.permute(0, 1, 4, 2, 3)
     bev = bev.reshape(-1, bev.shape[2], bev.shape[3], bev.shape[4])
     x, x1, x2, x3, x4 = encode(sd, "u_encoder.", bev)
-    fused, weights = fuse(sd, x3, trans_matrices, num_agent_tensor, batch_size, agent_num, only_v2i)
+    fused, weights = fuse(sd, x3, trans_matrices, num_agent_tensor, batch_size, agent_num, only_v2i, outage)
     x8, x7, x6, x5 = decode(sd, "decoder.", x, x1, x2, fused, x4)
     cls, loc = heads(sd, x8)
     out = {"cls": cls, "loc": loc}

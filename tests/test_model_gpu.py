@@ -171,3 +171,26 @@ def test_voxelize_and_scatter_bit_exact(cuda_dev):
         voxelize_occupy(torch.zeros(4, 2, device=cuda_dev), V.VOXEL_SIZE, V.EXTENTS)
     with pytest.raises(ValueError):
         voxelize_occupy(torch.zeros(4, 4), V.VOXEL_SIZE, V.EXTENTS)   # CPU tensor: no fallback
+
+
+def test_communication_outage_matches_reference_semantics(cuda_dev):
+    """p_com_outage > 0: same numpy RNG consumption order as the reference (one draw per present ego) and
+    ego features kept for the agents that drew an outage (DetModelBase.py:129-137, DiscoNet.py:68-69)."""
+    case = dict(A=3, B=2, num_agent=[3, 2], kd_flag=0, only_v2i=False, compress_level=0, seed=61)
+    from disconet_b200 import DiscoNet
+    tmpl = DiscoNet(_Cfg(), kd_flag=0, num_agent=3).state_dict()
+    sd, bev, T, na = golden_case_inputs(case, tmpl)
+    m = _ours(case, sd, cuda_dev, "bf16x3")
+    m.p_com_outage = 0.5
+    np.random.seed(1234)
+    expect = [[bool(np.random.choice([True, False], p=[0.5, 0.5])) for _ in range(n)] + [False] * (3 - n)
+              for n in case["num_agent"]]
+    assert any(any(r) for r in expect) and not all(all(r[:n]) for r, n in zip(expect, case["num_agent"]))
+    np.random.seed(1234)
+    with torch.no_grad():
+        res, wl = m(bev.to(cuda_dev), T, na, batch_size=2)
+    ref = O.disconet_forward(sd, bev, T, na, 2, agent_num=3, return_all=True, outage=expect)
+    for k in ("cls", "loc"):
+        assert rel_max(res[k].cpu(), ref[k]) <= 1e-3, k
+    ref_w = [e for per_b in ref["weights"] for e in per_b]
+    assert [len(e) for e in wl] == [len(e) for e in ref_w]
