@@ -69,7 +69,11 @@ struct ConvGeom {
     int acc_stride;           // TMEM columns per accumulator (block_n rounded up to 32)
     int nprod;                // producer warps per A ring: min(4 / nmma, SAr) (a ring with fewer slots than independent
                               // producers would let one warp lap another through the parity alias)
-    int SAr;                  // slots per A ring = SA / nmma
+    int SAr;                  // slots per A ring = SA / nrings
+    int nrings;               // A rings: 2 = one private ring per issuer (issuers split ITEMS, stationary weights),
+                              //          1 = one ring (single issuer, or issuers split the two SUB-TILES of each item)
+    int by_sub;               // 1: streamed weights, MSUB = 2, N <= 64: issuer m handles sub-tile m of every item; both
+                              //    read the same B stage (b_empty / acc_full count 2)
     int stationary;           // weights resident in smem
     int w_bytes;              // stationary: bytes of one n_tile's weights
     int tiles_h, tiles_w;
@@ -156,10 +160,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
         }
         for (int s = 0; s < g.SB; ++s) {
             mbar_init(smem_u32(&ctl->b_full[s]), 1);
-            mbar_init(smem_u32(&ctl->b_empty[s]), 1);
+            mbar_init(smem_u32(&ctl->b_empty[s]), g.by_sub ? 2 : 1);
         }
         for (int s = 0; s < kMaxAcc; ++s) {
-            mbar_init(smem_u32(&ctl->acc_full[s]), 1);
+            mbar_init(smem_u32(&ctl->acc_full[s]), g.by_sub ? 2 : 1);
             mbar_init(smem_u32(&ctl->acc_empty[s]), 4 * 32);   // one epilogue group (4 warps) drains a buffer
         }
         mbar_init(smem_u32(&ctl->w_full), 1);
@@ -307,13 +311,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
         // the stages of "its" items only -- an mbarrier ring is only safe with ONE in-order consumer (a second
         // consumer could be a full wrap ahead and pass the parity wait on a stale phase).  Producer warp pw serves
         // ring pw % nmma and, inside it, the stages q with q % nprod == pw / nmma (nprod <= SAr, same argument).
-        const int ring = pw % g.nmma, pr = pw / g.nmma;
+        const int ring = pw % g.nrings, pr = pw / g.nrings;
         int iacc_p = 0;
         for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++iacc_p) {
             if (pr >= g.nprod) break;
-            if ((iacc_p % g.nmma) != ring) continue;
+            if ((iacc_p % g.nrings) != ring) continue;
             const Item it = decode_item<MODE>(g, item);
-            const int q0 = (iacc_p / g.nmma) * stages_per_item;   // ring-local index of this item's first stage
+            const int q0 = (iacc_p / g.nrings) * stages_per_item;   // ring-local index of this item's first stage
             const int s0 = (pr - (q0 % g.nprod) + g.nprod) % g.nprod;
             for (int s = s0; s < stages_per_item; s += g.nprod) {
                 const int q = q0 + s;
@@ -461,9 +465,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                 tc_fence_after();
             }
             for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++iacc) {
-                if (mw >= g.nmma || (iacc % g.nmma) != mw) continue;
-                int ia = (iacc / g.nmma) * stages_per_item;   // ring-local index of this item's first A stage
-                const int ring0 = mw * g.SAr;                  // this issuer's private A ring
+                if (mw >= g.nmma || (!g.by_sub && (iacc % g.nmma) != mw)) continue;
+                int ia = (iacc / g.nrings) * stages_per_item;  // ring-local index of this item's first A stage
+                const int ring0 = (g.nrings == 2) ? mw * g.SAr : 0;   // private ring when issuers split items
+                const int sub_lo = g.by_sub ? mw : 0, sub_hi = g.by_sub ? mw + 1 : g.msub;
                 const int buf = iacc % g.nacc;
                 if (mw == 0) TRACE(2, iacc, 0);
                 mbar_wait(smem_u32(&ctl->acc_empty[buf]), ((uint32_t)(iacc / g.nacc) & 1u) ^ 1u);
@@ -475,7 +480,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                     // wait for the MSUB patches of this channel block
                     const int slot0 = ring0 + ia % g.SAr;
                     const uint32_t sa_phase = (uint32_t)(ia / g.SAr) & 1u;
-                    mbar_wait(bar_a_full + 8u * slot0, sa_phase);
+                    if (sub_lo == 0) mbar_wait(bar_a_full + 8u * slot0, sa_phase);
                     const uint32_t a0_16 = a_base16 + (uint32_t)slot0 * a_stage16;
                     int slot1 = slot0;
                     uint32_t a1_16 = a0_16;
@@ -483,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                         slot1 = slot0 + 1;
                         uint32_t phase1 = sa_phase;
                         if (slot1 == ring0 + g.SAr) { slot1 = ring0; phase1 ^= 1u; }
-                        mbar_wait(bar_a_full + 8u * slot1, phase1);
+                        if (sub_hi == 2) mbar_wait(bar_a_full + 8u * slot1, phase1);
                         a1_16 = a_base16 + (uint32_t)slot1 * a_stage16;
                     }
                     tc_fence_after();
@@ -506,7 +511,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                         if (elect_one()) {
 #pragma unroll
                             for (int sub = 0; sub < 2; ++sub) {
-                                if (sub < g.msub) {
+                                if (sub >= sub_lo && sub < sub_hi) {
                                     const uint32_t td = sub ? td1 : td0;
                                     const uint32_t a16 = (sub ? a1_16 : a0_16) + toff;
 #pragma unroll
@@ -534,8 +539,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                         }
                     }
                     if (elect_one()) {
-                        umma_commit(bar_a_empty + 8u * slot0);
-                        if (g.msub == 2) umma_commit(bar_a_empty + 8u * slot1);
+                        if (sub_lo == 0) umma_commit(bar_a_empty + 8u * slot0);
+                        if (sub_hi == 2) umma_commit(bar_a_empty + 8u * slot1);
                     }
                     __syncwarp();
                     ia += g.msub;
@@ -662,9 +667,18 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
         g->smem_bytes = kCtlBytes + kBiasBytes + kStageBytes + g->SA * g->a_stage_bytes + g->SB * g->b_stage_bytes;
     }
     DISCO_REQUIRE(g->SA >= g->msub && g->SA >= 1, "conv: not enough A stages");
-    if (g->nmma == 2 && g->SA / 2 < g->msub) g->nmma = 1;   // not enough stages for two private rings
-    g->SAr = g->SA / g->nmma;
-    g->nprod = kProdWarps / g->nmma;
+    g->by_sub = 0;
+    g->nrings = 1;
+    if (g->nmma == 2 && g->SA / 2 >= g->msub) g->nrings = 2;   // stationary: issuers split items, private rings
+    else g->nmma = 1;
+    if (!g->stationary && g->msub == 2 && acc_cols <= 128 && g->SA >= 4) {
+        // streamed N <= 64 layers are issue-bound too: two issuers, one per sub-tile, sharing every B stage
+        g->by_sub = 1;
+        g->nmma = 2;
+        g->SA &= ~1;   // even ring: slot parity == sub-tile, i.e. one consumer per slot
+    }
+    g->SAr = g->SA / g->nrings;
+    g->nprod = kProdWarps / g->nrings;
     if (g->nprod > g->SAr) g->nprod = g->SAr;
     DISCO_REQUIRE(g->SAr >= g->msub && g->nprod >= 1, "conv: A ring too small");
     g->tiles_h = (d->h_out + 15) / 16;

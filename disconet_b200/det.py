@@ -21,6 +21,7 @@ from ._lib import DiscoError, load
 from .modules import (BackboneParams, ClassificationHeadParams, PixelWeightedFusionParams, RegressionHeadParams)
 
 DEFAULT_PRECISION = os.environ.get("DISCO_B200_PRECISION", "bf16x3")
+USE_GRAPH = os.environ.get("DISCO_B200_GRAPH", "1") != "0"
 
 
 class AgentWeightList(collections.abc.Sequence):
@@ -134,11 +135,12 @@ class _DetBase(nn.Module):
             bev = bev.float()
         ops.bev_pack(bev.contiguous(), ws.buf["a0"], self.precision)
 
-    def _run_heads(self, ws: engine.Workspace, stream):
+    def _run_heads(self, ws: engine.Workspace, stream, skip_first: bool = False):
         n, h, w = ws.n, ws.h, ws.w
         cls = torch.empty((n, h, w, ws.n_cls), dtype=torch.float32, device=ws.device)
         loc = torch.empty((n, h, w, ws.n_reg), dtype=torch.float32, device=ws.device)
-        ws.head_calls[0].launch(stream)
+        if not skip_first:
+            ws.head_calls[0].launch(stream)
         ws.head_calls[1].set_output((cls, loc), ws.n_cls)
         ws.head_calls[1].launch(stream)
         # NHWC is already the reference's permute(0,2,3,1) layout (DetModelBase.py:239-252)
@@ -248,19 +250,24 @@ class DiscoNet(_DetBase):
         P = self.plans()
         ws = self._workspace(N, H, W, B, dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        trans = trans_matrices.detach().to(device=dev, dtype=torch.float64, non_blocking=True).contiguous()
-        num_agent = num_agent_tensor.detach().to(device=dev, non_blocking=True)[:, 0].to(torch.int32).contiguous()
-
-        self._pack_input(bevs, ws)
-        for c in ws.enc_calls:
-            c.launch(stream)
-        ws.en_call.launch(stream)
-        f = ws.fusion
-        f.trans = trans.data_ptr()
-        f.num_agent = num_agent.data_ptr()
-        f.only_v2i = int(bool(self.only_v2i))
+        h3, w3 = ws.h // 8, ws.w // 8
+        if getattr(ws, "static", None) is None:
+            # static device-side arguments of the fusion kernel (so the launch sequence can be graph-captured)
+            ws.static = {
+                "trans": torch.empty((B, A, A, 4, 4), dtype=torch.float64, device=dev),
+                "na": torch.empty((B,), dtype=torch.int32, device=dev),
+                "outage": torch.zeros((B, A), dtype=torch.int32, device=dev),
+                "weights": torch.zeros((B, A, A, h3, w3), dtype=torch.float32, device=dev),
+            }
+            f = ws.fusion
+            f.trans, f.num_agent = ws.static["trans"].data_ptr(), ws.static["na"].data_ptr()
+            f.outage, f.weights = ws.static["outage"].data_ptr(), ws.static["weights"].data_ptr()
+            ws.graph, ws.calls_done = None, 0
+        st = ws.static
+        st["trans"].copy_(trans_matrices.detach(), non_blocking=True)
+        st["na"].copy_(num_agent_tensor.detach()[:, 0], non_blocking=True)
+        ws.fusion.only_v2i = int(bool(self.only_v2i))
         outage_host = None
-        f.outage = None
         if self.p_com_outage != 0.0:
             # the reference draws np.random.choice once per (scene, present ego) inside its loops
             # (DiscoNet.py:59-69); same order and RNG consumption here (needs num_agent on the host)
@@ -269,20 +276,42 @@ class DiscoNet(_DetBase):
             for b in range(B):
                 for i in range(int(na_host[b])):
                     outage_host[b, i] = int(self.outage())
-            outage_dev = outage_host.to(dev)
-            f.outage = outage_dev.data_ptr()
-        weights = None
-        if self.kd_flag != 1:
-            weights = torch.empty((B, A, A, ws.h // 8, ws.w // 8), dtype=torch.float32, device=dev)
-            f.weights = weights.data_ptr()
+            st["outage"].copy_(outage_host, non_blocking=True)
+            ws.outage_dirty = True
+        elif getattr(ws, "outage_dirty", False):
+            st["outage"].zero_()
+            ws.outage_dirty = False
+
+        self._pack_input(bevs, ws)
+        body = ws.enc_calls + [ws.en_call, ws.fusion] + ws.dec_calls + ws.head_calls[:1]
+
+        def run_body(sp):
+            for c in body:
+                if c is ws.fusion:
+                    ops.fusion_forward(c, sp)
+                else:
+                    c.launch(sp)
+
+        # The 23 middle launches have fixed arguments -> replay them as one CUDA graph (removes ~25 ctypes
+        # launches of host latency per step; the first call per workspace runs eagerly as warm-up).
+        use_graph = USE_GRAPH and ws.fusion.only_v2i == getattr(ws, "graph_v2i", ws.fusion.only_v2i) \
+            and not torch.cuda.is_current_stream_capturing()
+        if use_graph and ws.graph is None and ws.calls_done >= 1:
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    run_body(torch.cuda.current_stream(dev).cuda_stream)
+                ws.graph, ws.graph_v2i = g, ws.fusion.only_v2i
+            except Exception:   # capture unsupported in this context: keep launching eagerly
+                ws.graph = False
+        if use_graph and ws.graph:
+            ws.graph.replay()
         else:
-            f.weights = None
-        ops.fusion_forward(f, stream)
-        for c in ws.dec_calls:
-            c.launch(stream)
-        result = self._run_heads(ws, stream)
-        # `trans`/`num_agent` are consumed by kernels already enqueued on this stream; the caching allocator
-        # keeps stream order, so releasing them here is safe.
+            run_body(stream)
+        ws.calls_done += 1
+        result = self._run_heads(ws, stream, skip_first=True)
+        weights = st["weights"].clone() if self.kd_flag != 1 else None
+        num_agent = st["na"].clone() if self.kd_flag != 1 else None
         if self.kd_flag == 1:
             return (result, self._nchw(ws, "x8"), self._nchw(ws, "x7"), self._nchw(ws, "x6"), self._nchw(ws, "x5"),
                     self._nchw(ws, "x3f"))
