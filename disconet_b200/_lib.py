@@ -34,6 +34,7 @@ class ConvDesc(C.Structure):
         ("out", C.c_void_p * 2),
         ("out_lo_off", C.c_longlong),
         ("out_split", C.c_int),
+        ("chain_wpack", C.c_void_p), ("chain_bias", C.c_void_p), ("chain_c_out", C.c_int), ("chain_relu", C.c_int),
     ]
 
 

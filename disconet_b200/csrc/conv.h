@@ -39,6 +39,14 @@ struct disco_conv_desc {
     void* out[2];            // OUT_ACT: out[0] = hi; OUT_F32: out[0] (channels < out_split), out[1] (rest)
     long long out_lo_off;    // OUT_ACT + BF16X3: elements from hi to lo
     int out_split;           // OUT_F32: first channel of out[1]; == c_out when out[1] unused
+    // ---- optional chained 1x1 conv on the (ReLU'd) result, computed in the same kernel -------------
+    // out = [relu](W2 * relu(conv(x) + bias) + bias2): the intermediate never leaves the SM (heads:
+    // DetModelBase.py:295-296,319-330).  With a chain, out/out_split/out_mode describe the CHAIN output
+    // (OUT_F32) and c_out the intermediate width (<= 64, one N tile, stacked bf16x3 weights).
+    const void* chain_wpack; // [c_out/8][part][chain_block_n][8] bf16 (stacked layout, K = c_out)
+    const float* chain_bias; // [chain_block_n]
+    int chain_c_out;         // 0 = no chain
+    int chain_relu;
 };
 
 int disco_conv_tc_launch(const disco_conv_desc* d, void* stream);

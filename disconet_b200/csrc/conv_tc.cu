@@ -41,8 +41,10 @@ namespace {
 
 constexpr int kEpiWarps = 8, kProdWarps = 4;   // two epilogue groups of 4 warps, each owning alternate items
 constexpr int kMmaWarps = 2;   // two independent issue streams (each owns alternate items) when weights are stationary
-constexpr int kThreads = (kEpiWarps + kProdWarps + 1 + kMmaWarps) * 32;  // 480
+constexpr int kThreads = (kEpiWarps + kProdWarps + 1 + kMmaWarps + 1) * 32;  // 512
 constexpr int kWarpB = kEpiWarps + kProdWarps, kWarpMma = kWarpB + 1;
+constexpr int kWarpChain = kWarpMma + kMmaWarps;   // issues the chained 1x1 MMAs (heads)
+constexpr int kBias2Off = 384;                     // float index of the chain bias inside the bias region
 constexpr int kMaxAcc = 4;
 constexpr int kMaxStages = 8;
 constexpr int kCtlBytes = 512;
@@ -82,6 +84,10 @@ struct ConvGeom {
     int tmem_cols;
     int smem_bytes;
     int grid;
+    int chain;                // chained 1x1 conv active
+    int chain_bn;             // its N tile (chain_c_out rounded up to 16)
+    int a2_bytes, w2_bytes;   // per-group A2 staging / resident W2 image
+    int acc2_col, acc2_stride;// TMEM columns of the chain accumulators (one per epilogue group)
     long long* trace;         // debug: per-role clock64 stamps of CTA 0 (DISCO_CONV_TRACE), else null
 };
 
@@ -93,6 +99,9 @@ struct __align__(8) SmemCtl {
     uint64_t acc_full[kMaxAcc];
     uint64_t acc_empty[kMaxAcc];
     uint64_t w_full;
+    uint64_t w2_full;
+    uint64_t a2_full[2];
+    uint64_t acc2_full[2];
     uint32_t tmem_base;
     uint32_t pad;
 };
@@ -136,9 +145,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_raw);
     const uint32_t smem_base = smem_u32(smem_raw);
-    const uint32_t a_base = smem_base + kCtlBytes + kBiasBytes + kStageBytes;
+    // (chained layers never use the OUT_ACT store staging, so its 20 KB go to the A stages)
+    const uint32_t a_base = smem_base + kCtlBytes + kBiasBytes + (g.chain ? 0 : kStageBytes);
     const float* s_bias = reinterpret_cast<const float*>(smem_raw + kCtlBytes);
     const uint32_t b_base = a_base + g.SA * g.a_stage_bytes;
+    const uint32_t w2_base = b_base + (uint32_t)g.w_bytes;          // chain only (stationary layers)
+    const uint32_t a2_base = w2_base + (uint32_t)g.w2_bytes;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -167,10 +179,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
             mbar_init(smem_u32(&ctl->acc_empty[s]), 4 * 32);   // one epilogue group (4 warps) drains a buffer
         }
         mbar_init(smem_u32(&ctl->w_full), 1);
+        mbar_init(smem_u32(&ctl->w2_full), 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&ctl->a2_full[s]), 4 * 32);
+            mbar_init(smem_u32(&ctl->acc2_full[s]), 1);
+        }
         fence_mbar_init();
     }
     for (int i = tid; i < g.n_tiles * g.d.block_n; i += kThreads)
         reinterpret_cast<float*>(smem_raw + kCtlBytes)[i] = g.d.bias[i];
+    if (g.chain)
+        for (int i = tid; i < g.chain_bn; i += kThreads)
+            reinterpret_cast<float*>(smem_raw + kCtlBytes)[kBias2Off + i] = g.d.chain_bias[i];
     if (warp == kWarpMma) {
         tmem_alloc(smem_u32(&ctl->tmem_base), (uint32_t)g.tmem_cols);
         tmem_relinquish();
@@ -236,7 +256,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                             v[4 * q + i] = d.relu ? fmaxf(x, 0.f) : x;
                         }
                     }
-                    if (d.out_mode == DISCO_OUT_ACT) {
+                    if (g.chain) {
+                        // chained 1x1: the ReLU'd tile becomes the A operand of a second MMA -- write bf16 hi/lo
+                        // straight into the UMMA K-major layout [part][channel/8][pixel][8 ch] of this group's A2 buffer
+                        float lo[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) lo[i] = v[i] - bf16_bits_to_f32(f32_to_bf16_bits(v[i]));
+                        uint8_t* a2 = smem_raw + (a2_base - smem_base) + egrp * g.a2_bytes;
+                        const int part_b = (d.block_n / 8) * 2048;
+                        uint4* dsth = reinterpret_cast<uint4*>(a2 + (2 * j) * 2048 + m * 16);
+                        dsth[0] = pack_bf16x8(v);
+                        dsth[128] = pack_bf16x8(v + 8);              // next channel chunk: +2048 B
+                        uint4* dstl = reinterpret_cast<uint4*>(a2 + part_b + (2 * j) * 2048 + m * 16);
+                        dstl[0] = pack_bf16x8(lo);
+                        dstl[128] = pack_bf16x8(lo + 8);
+                    } else if (d.out_mode == DISCO_OUT_ACT) {
                         // Stage the warp's 32 pixels x 16 channels in shared memory, then store row-wise: each
                         // store instruction writes 8 neighbouring pixels x 32 B (full sectors; one contiguous 512 B
                         // run per two chunks when c_out == 32) instead of 32 half-filled sectors 2*c_out bytes apart.
@@ -302,6 +336,47 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
             tc_fence_before();
             if (warp == 0) TRACE(0, iacc, 2);
             mbar_arrive(smem_u32(&ctl->acc_empty[buf]));
+            if (g.chain) {
+                // hand the A2 tile to the chain issuer, then drain its accumulator: bias2, fp32 NHWC stores
+                fence_proxy_async_smem();
+                mbar_arrive(smem_u32(&ctl->a2_full[egrp]));
+                mbar_wait(smem_u32(&ctl->acc2_full[egrp]), (uint32_t)(iacc >> 1) & 1u);
+                tc_fence_after();
+                const int mrow = (warp & 3) * 32 + lane;
+                const int oh = it.h0 + (mrow >> 3), ow = it.w0 + (mrow & 7);
+                const bool ok = (MODE != 2) ? ((oh < d.h_out) && (ow < d.w_out)) : (it.p0 + mrow < g.total_pix);
+                const long long px = (MODE != 2) ? ((long long)it.img * d.h_out + oh) * d.w_out + ow : it.p0 + mrow;
+                const uint32_t t2 = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) +
+                                    (uint32_t)(g.acc2_col + egrp * g.acc2_stride);
+                const int c1 = d.chain_c_out - d.out_split;
+                for (int j = 0; j < g.chain_bn / 16; ++j) {
+                    uint32_t r0[16], r1[16];
+                    tmem_ld16(t2 + (uint32_t)(j * 16), r0);
+                    tmem_ld16(t2 + (uint32_t)(g.chain_bn + j * 16), r1);   // stacked: columns [N2, 2*N2) = A2_hi * W2_lo
+                    tmem_ld_wait();
+                    if (ok) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int c = j * 16 + 4 * q;
+                            if (c >= d.chain_c_out) continue;
+                            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + kBias2Off + c);
+                            float o4[4] = {__uint_as_float(r0[4 * q]) + __uint_as_float(r1[4 * q]) + b4.x,
+                                           __uint_as_float(r0[4 * q + 1]) + __uint_as_float(r1[4 * q + 1]) + b4.y,
+                                           __uint_as_float(r0[4 * q + 2]) + __uint_as_float(r1[4 * q + 2]) + b4.z,
+                                           __uint_as_float(r0[4 * q + 3]) + __uint_as_float(r1[4 * q + 3]) + b4.w};
+                            if (d.chain_relu) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) o4[i] = fmaxf(o4[i], 0.f);
+                            }
+                            float* dst = (c < d.out_split)
+                                             ? reinterpret_cast<float*>(d.out[0]) + px * d.out_split + c
+                                             : reinterpret_cast<float*>(d.out[1]) + px * c1 + (c - d.out_split);
+                            *reinterpret_cast<float4*>(dst) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+                        }
+                    }
+                }
+                tc_fence_before();
+            }
         }
     } else if (warp < kEpiWarps + kProdWarps) {
         // =========================== A producers: warp p owns stages p, p+4, p+8, ... ===============
@@ -400,6 +475,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
         // =========================== B loader (bulk copy engine) ===================================
         if (lane == 0) {
             const int iters_per_tile = g.ncb * TAPS;
+            if (g.chain) {
+                const uint32_t bar2 = smem_u32(&ctl->w2_full);
+                mbar_arrive_expect_tx(bar2, (uint32_t)g.w2_bytes);
+                bulk_g2s(w2_base, d.chain_wpack, (uint32_t)g.w2_bytes, bar2);
+            }
             if (g.stationary) {
                 // n_tiles == 1: the whole packed weight set becomes resident
                 const uint8_t* wp = reinterpret_cast<const uint8_t*>(d.wpack);
@@ -424,6 +504,39 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                                  (uint32_t)g.b_stage_bytes, bar);
                     }
                 }
+            }
+        }
+    } else if (warp == kWarpChain) {
+        // =========================== chained 1x1 issuer ==========================================
+        if (g.chain) {
+            const uint32_t idesc1 = umma_idesc_f16(1, 128, g.chain_bn);        // A2_lo * W2_hi
+            const uint32_t idesc2 = umma_idesc_f16(1, 128, 2 * g.chain_bn);    // A2_hi * [W2_hi; W2_lo]
+            const uint32_t a_hi = (128u >> 4) | (1u << 14);                      // SBO 128 B
+            const uint32_t b_hi = (128u >> 4) | (1u << 14);
+            const uint32_t lbo_b16 = 2u * (uint32_t)g.chain_bn;                  // chunk stride of W2: 2 parts * N2 rows * 16 B
+            const uint32_t a_lo_c = (2048u >> 4) << 16;                          // LBO: next channel chunk
+            const uint32_t b_lo_c = lbo_b16 << 16;
+            const uint32_t a_part16 = ((uint32_t)(g.d.block_n / 8) * 2048u) >> 4;
+            const int ks2 = g.d.block_n / 16;
+            mbar_wait(smem_u32(&ctl->w2_full), 0);
+            int iacc = 0;
+            for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++iacc) {
+                const int grp = iacc & 1;
+                mbar_wait(smem_u32(&ctl->a2_full[grp]), (uint32_t)(iacc >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t td = tmem_d + (uint32_t)(g.acc2_col + grp * g.acc2_stride);
+                const uint32_t a16 = ((a2_base + (uint32_t)(grp * g.a2_bytes)) >> 4) + a_lo_c;
+                const uint32_t b16 = (w2_base >> 4) + b_lo_c;
+                if (elect_one()) {
+                    for (int ks = 0; ks < ks2; ++ks) {
+                        const uint32_t alo = a16 + (uint32_t)(2 * ks) * (2048u >> 4);
+                        const uint32_t blo = b16 + (uint32_t)(2 * ks) * lbo_b16;
+                        umma_f16_parts(td, alo, a_hi, blo, b_hi, idesc2, ks > 0 ? 1u : 0u);
+                        umma_f16_parts(td, alo + a_part16, a_hi, blo, b_hi, idesc1, 1u);
+                    }
+                    umma_commit(smem_u32(&ctl->acc2_full[grp]));
+                }
+                __syncwarp();
             }
         }
     } else {
@@ -584,9 +697,11 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
             DISCO_REQUIRE(d->h_in % 2 == 0 && d->w_in % 2 == 0, "conv: upsampled source needs even H_in/W_in");
     if (d->out_mode == DISCO_OUT_ACT)
         DISCO_REQUIRE(d->c_out % 16 == 0, "conv: activation outputs need c_out %% 16 == 0");
-    else
-        DISCO_REQUIRE(d->out_split % 4 == 0 && (d->c_out - d->out_split) % 4 == 0 && d->out_split <= d->c_out,
+    else {
+        const int oc = d->chain_c_out > 0 ? d->chain_c_out : d->c_out;
+        DISCO_REQUIRE(d->out_split % 4 == 0 && (oc - d->out_split) % 4 == 0 && d->out_split <= oc,
                       "conv: fp32 output split must be a multiple of 4");
+    }
     if (g_num_sms == 0) {
         int dev = 0;
         DISCO_CHECK_CUDA(cudaGetDevice(&dev));
@@ -622,7 +737,8 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     g->n_tiles = (d->c_out + d->block_n - 1) / d->block_n;
     g->total_pix = (long long)d->n * d->h_out * d->w_out;
 
-    const int budget = 224 * 1024 - kCtlBytes - kBiasBytes - kStageBytes;
+    const int stage_region = d->chain_c_out > 0 ? 0 : kStageBytes;
+    const int budget = 224 * 1024 - kCtlBytes - kBiasBytes - stage_region;
     g->w_bytes = g->ncb * d->taps * g->b_stage_bytes;
     // MSUB = 2 (256-pixel items) when the N tile leaves room for double-buffered accumulators and the
     // image is wide enough; it halves the weight stream per MAC.
@@ -643,14 +759,38 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     while (cols < g->nacc * g->msub * g->acc_stride) cols *= 2;
     g->tmem_cols = cols;
     int ctas_per_sm = 1;
+    g->chain = d->chain_c_out > 0 ? 1 : 0;
+    g->chain_bn = 0; g->a2_bytes = 0; g->w2_bytes = 0; g->acc2_col = 0; g->acc2_stride = 0;
+    int chain_smem = 0;
+    if (g->chain) {
+        DISCO_REQUIRE(g->n_tiles == 1 && d->wpack_stacked && d->precision == DISCO_PREC_BF16X3 && d->block_n <= 64 &&
+                          d->out_mode == DISCO_OUT_F32 && d->chain_wpack && d->chain_bias && d->relu,
+                      "conv: chained 1x1 needs one stacked bf16x3 N tile (<= 64 channels), ReLU and fp32 output");
+        g->chain_bn = (d->chain_c_out + 15) / 16 * 16;
+        DISCO_REQUIRE(g->chain_bn <= 128 && g->chain_bn <= 4 * (kBiasBytes / 4 - kBias2Off) , "conv: chain too wide");
+        g->a2_bytes = 2 * (d->block_n / 8) * 2048;
+        g->w2_bytes = (d->block_n / 8) * 2 * g->chain_bn * 16;
+        chain_smem = 2 * g->a2_bytes + g->w2_bytes;
+        g->stationary = (g->w_bytes + 3 * g->a_stage_bytes + chain_smem <= budget) ? 1 : 0;
+        DISCO_REQUIRE(g->stationary, "conv: chained layer does not fit shared memory");
+        g->msub = 1;
+        g->nacc = 2;
+        g->nmma = kMmaWarps;
+        g->acc2_stride = (2 * g->chain_bn + 31) / 32 * 32;
+        g->acc2_col = g->nacc * g->acc_stride;
+        DISCO_REQUIRE(g->acc2_col + 2 * g->acc2_stride <= 512, "conv: chain accumulators exceed TMEM");
+        int cols2 = 32;
+        while (cols2 < g->acc2_col + 2 * g->acc2_stride) cols2 *= 2;
+        g->tmem_cols = cols2;
+    }
     if (g->stationary) {
         // small resident weight sets: aim for two CTAs per SM (two MMA issuers, 2x gather streams)
         int sa;
-        sa = (budget - g->w_bytes) / g->a_stage_bytes;   // one CTA per SM: the MMA issue port is per SM anyway
+        sa = (budget - g->w_bytes - chain_smem) / g->a_stage_bytes;   // one CTA per SM: the MMA issue port is per SM anyway
         if (sa > kMaxStages) sa = kMaxStages;
         g->SA = sa;
         g->SB = 1;
-        g->smem_bytes = kCtlBytes + kBiasBytes + kStageBytes + g->SA * g->a_stage_bytes + g->w_bytes;
+        g->smem_bytes = kCtlBytes + kBiasBytes + stage_region + g->SA * g->a_stage_bytes + g->w_bytes + chain_smem;
     } else {
         int sa = 2 * g->msub;  // current + next channel block
         if (sa < 4 && 4 * g->a_stage_bytes <= budget / 3) sa = 4;
@@ -664,7 +804,7 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
                       g->a_stage_bytes, g->b_stage_bytes);
         g->SA = sa;
         g->SB = sb;
-        g->smem_bytes = kCtlBytes + kBiasBytes + kStageBytes + g->SA * g->a_stage_bytes + g->SB * g->b_stage_bytes;
+        g->smem_bytes = kCtlBytes + kBiasBytes + stage_region + g->SA * g->a_stage_bytes + g->SB * g->b_stage_bytes;
     }
     DISCO_REQUIRE(g->SA >= g->msub && g->SA >= 1, "conv: not enough A stages");
     g->by_sub = 0;

@@ -50,7 +50,7 @@ __device__ __forceinline__ void load_feat(const uint16_t* p, long long lo_off, i
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(kWarps * 32) fusion_kernel(const disco_fusion_desc d) {
+__global__ void __launch_bounds__(kWarps * 32, 3) fusion_kernel(const disco_fusion_desc d) {
     __shared__ float s_w2[kH2][kHid + 1];
     __shared__ float s_b2[kH2];
     __shared__ float s_w3[kH3][kH2];

@@ -135,14 +135,14 @@ class _DetBase(nn.Module):
             bev = bev.float()
         ops.bev_pack(bev.contiguous(), ws.buf["a0"], self.precision)
 
-    def _run_heads(self, ws: engine.Workspace, stream, skip_first: bool = False):
+    def _run_heads(self, ws: engine.Workspace, stream):
         n, h, w = ws.n, ws.h, ws.w
         cls = torch.empty((n, h, w, ws.n_cls), dtype=torch.float32, device=ws.device)
         loc = torch.empty((n, h, w, ws.n_reg), dtype=torch.float32, device=ws.device)
-        if not skip_first:
-            ws.head_calls[0].launch(stream)
-        ws.head_calls[1].set_output((cls, loc), ws.n_cls)
-        ws.head_calls[1].launch(stream)
+        for c in ws.head_calls[:-1]:
+            c.launch(stream)
+        ws.head_calls[-1].set_output((cls, loc), ws.n_cls)   # fresh result tensors every call
+        ws.head_calls[-1].launch(stream)
         # NHWC is already the reference's permute(0,2,3,1) layout (DetModelBase.py:239-252)
         cls = cls.view(n, -1, self.category_num)
         loc = loc.view(-1, h, w, self.anchor_num_per_loc, self.out_seq_len, self.box_code_size)
@@ -283,7 +283,7 @@ class DiscoNet(_DetBase):
             ws.outage_dirty = False
 
         self._pack_input(bevs, ws)
-        body = ws.enc_calls + [ws.en_call, ws.fusion] + ws.dec_calls + ws.head_calls[:1]
+        body = ws.enc_calls + [ws.en_call, ws.fusion] + ws.dec_calls
 
         def run_body(sp):
             for c in body:
@@ -309,7 +309,7 @@ class DiscoNet(_DetBase):
         else:
             run_body(stream)
         ws.calls_done += 1
-        result = self._run_heads(ws, stream, skip_first=True)
+        result = self._run_heads(ws, stream)
         weights = st["weights"].clone() if self.kd_flag != 1 else None
         num_agent = st["na"].clone() if self.kd_flag != 1 else None
         if self.kd_flag == 1:

@@ -14,7 +14,7 @@ import torch
 
 from . import ops
 from ._lib import PREC_BF16X3, PREC_FP16, FusionDesc
-from .plan import ConvPlan, fold_bn, pack_conv
+from .plan import ConvPlan, fold_bn, pack_chain, pack_conv
 
 PRECISIONS = {"bf16x3": PREC_BF16X3, "fp16": PREC_FP16}
 
@@ -94,8 +94,10 @@ def build_head_plans(get: Getter, precision: int) -> Dict[str, ConvPlan]:
     wc, bc = _conv_bn(get, "classification.conv1", "classification.bn1")
     wr, br = _conv_bn(get, "regression.box_prediction.0", "regression.box_prediction.1")
     ch = wc.shape[0]
+    chained = precision == PREC_BF16X3
+    # (chained: 16-channel K stages -> more, smaller A stages next to the resident weights + A2/W2 buffers)
     h3 = pack_conv(torch.cat((wc, wr), 0), torch.cat((bc, br), 0), src_channels=[wc.shape[1]], relu=True,
-                   precision=precision, name="heads.3x3")
+                   precision=precision, name="heads.3x3", c_blk=16 if chained else None)
     w2c, b2c = get("classification.conv2.weight").detach().float(), get("classification.conv2.bias").detach().float()
     w2r = get("regression.box_prediction.3.weight").detach().float()
     b2r = get("regression.box_prediction.3.bias").detach().float()
@@ -103,8 +105,13 @@ def build_head_plans(get: Getter, precision: int) -> Dict[str, ConvPlan]:
     w = torch.zeros(nc + nr, 2 * ch, 1, 1, device=wc.device)
     w[:nc, :ch] = w2c
     w[nc:, ch:] = w2r
-    h1 = pack_conv(w, torch.cat((b2c, b2r), 0), src_channels=[2 * ch], relu=False, precision=precision,
-                   name="heads.1x1")
+    b2 = torch.cat((b2c, b2r), 0)
+    if chained and h3.stacked:
+        # the 1x1 runs as a chained MMA inside the 3x3 kernel: the 64-channel intermediate never touches HBM
+        h3.chain = pack_chain(w.view(nc + nr, 2 * ch), b2, 2 * ch, relu=False)
+        h3.name = "heads.3x3+1x1"
+        return {"h3": h3, "h1": None, "n_cls": nc, "n_reg": nr}
+    h1 = pack_conv(w, b2, src_channels=[2 * ch], relu=False, precision=precision, name="heads.1x1")
     return {"h3": h3, "h1": h1, "n_cls": nc, "n_reg": nr}
 
 
@@ -216,13 +223,17 @@ class Workspace:
         ]
         self.head_calls: List[ops.ConvCall] = []
         if heads is not None:
-            b["hh"] = A(h, w, heads["h3"].c_out)
             self.n_cls, self.n_reg = heads["n_cls"], heads["n_reg"]
-            dummy = (torch.empty(1, device=device), torch.empty(1, device=device))
-            self.head_calls = [
-                mk(heads["h3"], [b["x8"]], [0], b["hh"], h, w),
-                ops.ConvCall(heads["h1"], [b["hh"]], [0], dummy, n=n, h_in=h, w_in=w, out_split=self.n_cls),
-            ]
+            dummy = (torch.empty(4, device=device), torch.empty(4, device=device))
+            if heads["h1"] is None:   # fused 3x3 + chained 1x1
+                self.head_calls = [ops.ConvCall(heads["h3"], [b["x8"]], [0], dummy, n=n, h_in=h, w_in=w,
+                                                out_split=self.n_cls)]
+            else:
+                b["hh"] = A(h, w, heads["h3"].c_out)
+                self.head_calls = [
+                    mk(heads["h3"], [b["x8"]], [0], b["hh"], h, w),
+                    ops.ConvCall(heads["h1"], [b["hh"]], [0], dummy, n=n, h_in=h, w_in=w, out_split=self.n_cls),
+                ]
 
     def total_flops(self) -> int:
         calls = self.enc_calls + self.dec_calls + self.head_calls + ([self.en_call] if self.fusion else [])

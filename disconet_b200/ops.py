@@ -42,52 +42,8 @@ def conv_forward(plan: ConvPlan, srcs: Sequence[torch.Tensor], ups: Sequence[int
                  out_split: Optional[int] = None, reference: bool = False):
     """Run one conv layer.  srcs: activation buffers [parts,n,hs,ws,c]; out: activation buffer (OUT_ACT)
     or a tuple of fp32 NHWC tensors (OUT_F32)."""
-    lib = load()
-    d = ConvDesc()
-    _require_cuda(*srcs)
-    for i in range(2):
-        if i < len(srcs):
-            s = srcs[i]
-            d.src[i] = s.data_ptr()
-            d.src_lo_off[i] = _lo_off(s)
-            d.src_c[i] = s.shape[-1]
-            d.src_up[i] = int(ups[i])
-        else:
-            d.src[i] = None
-            d.src_lo_off[i] = 0
-            d.src_c[i] = 0
-            d.src_up[i] = 0
-    assert sum(s.shape[-1] for s in srcs) == plan.c_in, (plan.name, [s.shape for s in srcs], plan.c_in)
-    d.n, d.h_in, d.w_in = n, h_in, w_in
-    d.stride, d.taps, d.c_blk = plan.stride, plan.taps, plan.c_blk
-    d.h_out = (h_in - 1) // plan.stride + 1
-    d.w_out = (w_in - 1) // plan.stride + 1
-    d.c_out, d.block_n = plan.c_out, plan.block_n
-    d.wpack = plan.wpack.data_ptr()
-    d.wpack_stacked = int(plan.stacked)
-    d.wref = plan.wref.data_ptr() if plan.wref is not None else None
-    d.bias = plan.bias.data_ptr()
-    d.relu = int(plan.relu)
-    d.precision = plan.precision
-    if isinstance(out, torch.Tensor) and out.dtype in (torch.bfloat16, torch.float16):
-        _require_cuda(out)
-        assert out.shape[-1] == plan.c_out
-        d.out_mode = OUT_ACT
-        d.out[0] = out.data_ptr()
-        d.out[1] = None
-        d.out_lo_off = _lo_off(out)
-        d.out_split = plan.c_out
-    else:
-        outs = out if isinstance(out, (tuple, list)) else (out,)
-        _require_cuda(*outs)
-        d.out_mode = OUT_F32
-        d.out[0] = outs[0].data_ptr()
-        d.out[1] = outs[1].data_ptr() if len(outs) > 1 else None
-        d.out_lo_off = 0
-        d.out_split = plan.c_out if out_split is None else out_split
-    stream = _stream_ptr(srcs[0].device)
-    fn = lib.disco_conv_reference if reference else lib.disco_conv_forward
-    check(fn(C.byref(d), stream), f"conv[{plan.name}]")
+    call = ConvCall(plan, srcs, ups, out, n=n, h_in=h_in, w_in=w_in, out_split=out_split)
+    call.launch(_stream_ptr(srcs[0].device), reference=reference)
 
 
 def bev_pack(bev: torch.Tensor, out: torch.Tensor, precision: int):
@@ -139,8 +95,15 @@ class ConvCall:
         d.bias = plan.bias.data_ptr()
         d.relu = int(plan.relu)
         d.precision = plan.precision
+        fpp = plan.flops_per_pixel
+        if plan.chain is not None:
+            d.chain_wpack = plan.chain["wpack"].data_ptr()
+            d.chain_bias = plan.chain["bias"].data_ptr()
+            d.chain_c_out = plan.chain["c_out"]
+            d.chain_relu = int(plan.chain["relu"])
+            fpp += plan.chain["flops_per_pixel"]
         self.desc = d
-        self.flops = plan.flops_per_pixel * n * d.h_out * d.w_out
+        self.flops = fpp * n * d.h_out * d.w_out
         self.set_output(out, out_split)
         self._fn = load().disco_conv_forward
         self._ref = load().disco_conv_reference
@@ -163,7 +126,8 @@ class ConvCall:
             d.out[0] = outs[0].data_ptr()
             d.out[1] = outs[1].data_ptr() if len(outs) > 1 else None
             d.out_lo_off = 0
-            d.out_split = self.plan.c_out if out_split is None else out_split
+            oc = self.plan.chain["c_out"] if self.plan.chain is not None else self.plan.c_out
+            d.out_split = oc if out_split is None else out_split
 
     def launch(self, stream_ptr: int, reference: bool = False):
         check((self._ref if reference else self._fn)(C.byref(self.desc), stream_ptr), f"conv[{self.plan.name}]")

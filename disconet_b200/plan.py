@@ -62,13 +62,14 @@ class ConvPlan:
     bias: torch.Tensor        # fp32 [n_tiles*block_n]
     wref: Optional[torch.Tensor] = None   # fp32 [c_out, taps, c_in] (validator only)
     stacked: bool = False     # weight image layout [..][chunk][part][n][8] (see conv.h wpack_stacked)
+    chain: Optional[dict] = None   # chained 1x1: {wpack, bias, c_out, relu} (see conv.h chain_*)
     name: str = ""
     flops_per_pixel: int = field(default=0)
 
 
 def pack_conv(wf: torch.Tensor, bf: torch.Tensor, *, src_channels, stride: int = 1, relu: bool = True,
               precision: int = PREC_BF16X3, block_n: Optional[int] = None, keep_ref: bool = False,
-              name: str = "") -> ConvPlan:
+              name: str = "", c_blk: Optional[int] = None) -> ConvPlan:
     """wf [c_out, c_in_real, k, k] fp32 (BN folded), bf [c_out] -> ConvPlan.
 
     `src_channels` are the (padded) channel counts of the concatenated NHWC sources in order; real
@@ -79,7 +80,8 @@ def pack_conv(wf: torch.Tensor, bf: torch.Tensor, *, src_channels, stride: int =
     assert taps in (1, 9)
     c_in = int(sum(src_channels))
     assert c_in >= c_in_real
-    c_blk = choose_c_blk(src_channels, precision, stride)
+    if c_blk is None:
+        c_blk = choose_c_blk(src_channels, precision, stride)
     c_out_pad16 = (c_out + 15) // 16 * 16
     if block_n is None:
         # N=256 keeps the MMA's shared-memory operand reads (A 4 KB + B N*32 B per N/2 cycles) under the
@@ -108,3 +110,18 @@ def pack_conv(wf: torch.Tensor, bf: torch.Tensor, *, src_channels, stride: int =
     return ConvPlan(taps=taps, stride=stride, c_in=c_in, c_out=c_out, c_blk=c_blk, block_n=block_n, relu=relu,
                     precision=precision, wpack=wpack.reshape(-1), bias=bias, wref=wref, name=name, stacked=stacked,
                     flops_per_pixel=2 * taps * c_in_real * c_out)
+
+
+def pack_chain(w2: torch.Tensor, b2: torch.Tensor, k2: int, relu: bool = False) -> dict:
+    """1x1 conv chained onto a <=64-channel layer inside the same kernel: w2 [n2, k2] fp32 -> stacked bf16x3
+    image [k2/8][part][n2 padded to 16][8] (whole K resident, one bulk copy)."""
+    n2 = w2.shape[0]
+    bn = (n2 + 15) // 16 * 16
+    w = torch.zeros(bn, k2, dtype=torch.float32, device=w2.device)
+    w[:n2, :w2.shape[1]] = w2
+    w3 = w.view(bn, k2 // 8, 8).permute(1, 0, 2).contiguous()       # [chunk, n, 8]
+    hi, lo = split_bf16(w3)
+    img = torch.stack((hi, lo), dim=1).contiguous().view(torch.int16).reshape(-1)   # [chunk, part, n, 8]
+    bias = torch.zeros(bn, dtype=torch.float32, device=w2.device)
+    bias[:n2] = b2
+    return {"wpack": img, "bias": bias, "c_out": n2, "relu": bool(relu), "flops_per_pixel": 2 * k2 * n2}

@@ -62,6 +62,12 @@ typedef struct disco_conv_desc {
     void* out[2];            /* OUT_ACT: out[0]=hi; OUT_F32: out[0] gets channels < out_split, out[1] the rest */
     long long out_lo_off;
     int out_split;
+    /* optional chained 1x1 conv on the ReLU'd result inside the same kernel (heads): when chain_c_out > 0,
+     * out/out_split/out_mode describe the chain output (OUT_F32) and c_out (<= 64) the intermediate width */
+    const void* chain_wpack; /* [c_out/8][part][chain_block_n][8] bf16, K = c_out                         */
+    const float* chain_bias; /* [chain_block_n]                                                          */
+    int chain_c_out;         /* 0 = no chain                                                             */
+    int chain_relu;
 } disco_conv_desc;
 
 int disco_conv_forward(const disco_conv_desc* d /* host */, void* stream);

@@ -119,3 +119,31 @@ def test_conv_rejects_bad_descriptor(cuda_dev):
         conv_forward(plan, [a], [1], out, n=1, h_in=15, w_in=16)  # odd size with upsample flag
     with pytest.raises(ValueError):
         conv_forward(plan, [a.cpu()], [0], out, n=1, h_in=16, w_in=16)  # CPU tensor: no fallback
+
+
+def test_chained_1x1_matches_two_convs(cuda_dev):
+    """conv3x3(32->64)+ReLU with the 1x1 (64->48, split 12|36, fp32) chained inside the same kernel ==
+    the two-kernel composition in fp32 torch (heads: DetModelBase.py:283-351)."""
+    from disconet_b200.plan import pack_chain
+    dev = cuda_dev
+    g = torch.Generator().manual_seed(7)
+    n, h, w = 3, 40, 48
+    x = torch.randn(n, 32, h, w, generator=g).to(dev)
+    w1 = (torch.randn(64, 32, 3, 3, generator=g) / (32 * 9) ** 0.5).to(dev)
+    b1 = (torch.randn(64, generator=g) * 0.1).to(dev)
+    w2 = (torch.randn(48, 64, generator=g) / 8).to(dev)
+    b2 = (torch.randn(48, generator=g) * 0.1).to(dev)
+    a = to_act(x, PREC_BF16X3)
+    xv = act_value(a).permute(0, 3, 1, 2)
+    mid = F.relu(F.conv2d(xv, w1, b1, padding=1))
+    ref = F.conv2d(mid, w2.view(48, 64, 1, 1), b2).permute(0, 2, 3, 1)
+    plan = pack_conv(w1, b1, src_channels=[32], relu=True, precision=PREC_BF16X3, c_blk=16, name="chain_test")
+    assert plan.stacked
+    plan.chain = pack_chain(w2, b2, 64)
+    o0 = torch.full((n, h, w, 12), float("nan"), device=dev)
+    o1 = torch.full((n, h, w, 36), float("nan"), device=dev)
+    conv_forward(plan, [a], [0], (o0, o1), n=n, h_in=h, w_in=w, out_split=12)
+    torch.cuda.synchronize()
+    got = torch.cat((o0, o1), -1)
+    assert torch.isfinite(got).all()
+    assert rel_max(got, ref) < 1e-4
