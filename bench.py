@@ -266,7 +266,7 @@ def main():
     per = [[] for _ in calls]
     cls_t = torch.empty((AGENTS * B, H, W, ws.n_cls), device=dev)
     loc_t = torch.empty((AGENTS * B, H, W, ws.n_reg), device=dev)
-    ws.head_calls[1].set_output((cls_t, loc_t), ws.n_cls)
+    ws.head_calls[-1].set_output((cls_t, loc_t), ws.n_cls)
     for _ in range(reps):
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(calls) + 1)]
         evs[0].record()
