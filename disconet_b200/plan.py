@@ -41,6 +41,8 @@ def choose_c_blk(src_channels, precision: int, stride: int) -> int:
     cap = 64
     if precision == PREC_BF16X3 or stride == 2:
         cap = 32
+    if precision == PREC_BF16X3 and stride == 2:
+        cap = 16   # the 33x17 stride-2 patch is 4.4x a tile: 16-channel stages (38 KB) keep >= 3-4 of them in flight
     for cb in (64, 32, 16):
         if cb <= cap and all(c % cb == 0 for c in src_channels if c):
             return cb
