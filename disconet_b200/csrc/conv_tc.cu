@@ -746,7 +746,17 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     const int acc_cols = (d->wpack_stacked ? 2 : 1) * d->block_n;   // TMEM columns one accumulator writes
     g->msub = (wide && 4 * acc_cols <= 512) ? 2 : 1;
     g->stationary = (g->n_tiles == 1 && g->w_bytes + 3 * g->a_stage_bytes <= budget) ? 1 : 0;
-    if (g->stationary) g->msub = 1;  // nothing to amortise (measured: MSUB=2 is 5-15% slower on the stationary layers)
+    // Stationary layers: items of one sub-tile with issuers splitting ITEMS (private A rings) -- unless one item
+    // needs more channel blocks than a private ring can hold (conv8_1: 3 blocks, 2 slots per ring): then keep
+    // MSUB = 2 and let the issuers split the SUB-TILES of every item, which pipelines at channel-block granularity.
+    bool stationary_by_sub = false;
+    if (g->stationary && d->stride == 2 && (budget - g->w_bytes) / g->a_stage_bytes < 4 && wide && 4 * acc_cols <= 512)
+        g->stationary = 0;   // conv1_1: the big stride-2 patches need the room more than the weights do (measured)
+    if (g->stationary) {
+        const int sa_fit = (budget - g->w_bytes) / g->a_stage_bytes;
+        stationary_by_sub = (d->chain_c_out == 0 && g->msub == 2 && acc_cols <= 128 && sa_fit >= 4 && sa_fit / 2 < g->ncb);
+        if (!stationary_by_sub) g->msub = 1;
+    }
     g->nacc = (2 * g->msub * acc_cols <= 512) ? 2 : 1;
     g->nmma = 1;
     if (g->stationary && g->nacc == 2) {
@@ -809,9 +819,9 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     DISCO_REQUIRE(g->SA >= g->msub && g->SA >= 1, "conv: not enough A stages");
     g->by_sub = 0;
     g->nrings = 1;
-    if (g->nmma == 2 && g->SA / 2 >= g->msub) g->nrings = 2;   // stationary: issuers split items, private rings
+    if (g->nmma == 2 && g->SA / 2 >= g->msub && !stationary_by_sub) g->nrings = 2;   // issuers split items, private rings
     else g->nmma = 1;
-    if (!g->stationary && g->msub == 2 && acc_cols <= 128 && g->SA >= 4) {
+    if ((!g->stationary || stationary_by_sub) && g->msub == 2 && acc_cols <= 128 && g->SA >= 4) {
         // streamed N <= 64 layers are issue-bound too: two issuers, one per sub-tile, sharing every B stage
         g->by_sub = 1;
         g->nmma = 2;

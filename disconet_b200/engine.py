@@ -77,9 +77,9 @@ def build_decoder_plans(get: Getter, p: str, precision: int) -> Dict[str, ConvPl
     """Backbone.decode (Backbone.py:145-242); concat order = (upsampled, skip) (:176,195,214,233)."""
     P: Dict[str, ConvPlan] = {}
 
-    def add(name, conv, bn, srcs):
+    def add(name, conv, bn, srcs, c_blk=None):
         w, b = _conv_bn(get, p + conv, p + bn)
-        P[name] = pack_conv(w, b, src_channels=srcs, relu=True, precision=precision, name=p + conv)
+        P[name] = pack_conv(w, b, src_channels=srcs, relu=True, precision=precision, name=p + conv, c_blk=c_blk)
 
     add("c5_1", "conv5_1", "bn5_1", [512, 256]); add("c5_2", "conv5_2", "bn5_2", [256])
     add("c6_1", "conv6_1", "bn6_1", [256, 128]); add("c6_2", "conv6_2", "bn6_2", [128])
