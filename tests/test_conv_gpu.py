@@ -147,3 +147,31 @@ def test_chained_1x1_matches_two_convs(cuda_dev):
     got = torch.cat((o0, o1), -1)
     assert torch.isfinite(got).all()
     assert rel_max(got, ref) < 1e-4
+
+
+def test_conv_fuzz_against_validator(cuda_dev):
+    """Seeded random layer shapes (ragged sizes, both strides, 1 or 2 sources with/without upsample, 16..512
+    channels): the tcgen05 kernel must agree with the CUDA-core validator (same inputs, unpacked weights)."""
+    import random
+    rnd = random.Random(1234)
+    chans = [16, 32, 48, 64, 96, 128, 256]
+    for trial in range(28):
+        k = rnd.choice([3, 3, 3, 1])
+        stride = rnd.choice([1, 1, 2]) if k == 3 else 1
+        two = k == 3 and stride == 1 and rnd.random() < 0.4
+        n = rnd.randint(1, 3)
+        h, w = rnd.choice([8, 16, 24, 40, 56]), rnd.choice([8, 16, 20, 48, 72])
+        if two:
+            h, w = h + (h & 1), w + (w & 1)
+        c0 = rnd.choice(chans)
+        srcs = [(c0, c0, 1 if two else 0)] + ([(rnd.choice(chans[:5]), None, 0)] if two else [])
+        srcs = [(c, c, u) for c, _, u in srcs]
+        c_out = rnd.choice([16, 32, 64, 128, 256, 512] if k == 3 else [16, 48, 64, 256])
+        case = (f"fuzz{trial}", n, h, w, srcs, c_out, k, stride, "act")
+        prec = rnd.choice([PREC_BF16X3, PREC_BF16X3, PREC_FP16])
+        results, ref = _run_case(case, prec, cuda_dev, seed=100 + trial)
+        tol = {PREC_FP16: 1e-3, PREC_BF16X3: 5e-5}[prec]
+        for which, got in results.items():
+            assert torch.isfinite(got).all(), (case, which)
+            err = rel_max(got, ref)
+            assert err < tol, f"{case} {which}: {err:.3e}"
