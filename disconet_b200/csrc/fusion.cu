@@ -21,35 +21,46 @@ constexpr int kWarps = 8;
 constexpr int kCellsPerWarp = 4;
 constexpr int kHid = 128, kH2 = 32, kH3 = 8;
 
-template <int VEC>  // VEC uint4 (8 channels each) per lane: C = 256*VEC
+// CPL channels per lane (C = 32*CPL): 4 -> one 8-byte load, 8 / 16 -> one / two 16-byte loads per plane
+template <int CPL>
 __device__ __forceinline__ void load_feat(const uint16_t* p, long long lo_off, int precision, float wgt,
-                                          float (&acc)[8 * VEC]) {
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-        const uint4 hi = __ldg(reinterpret_cast<const uint4*>(p) + v);
-        const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w};
+                                          float (&acc)[CPL]) {
+    constexpr int NW = CPL / 2;   // 32-bit words (2 channels each)
+    uint32_t hw[NW], lw[NW];
+    if (CPL == 4) {
+        const uint2 h = __ldg(reinterpret_cast<const uint2*>(p));
+        hw[0] = h.x; hw[1] = h.y;
         if (precision == DISCO_PREC_BF16X3) {
-            const uint4 lo = __ldg(reinterpret_cast<const uint4*>(p + lo_off) + v);
-            const uint32_t lw[4] = {lo.x, lo.y, lo.z, lo.w};
+            const uint2 l = __ldg(reinterpret_cast<const uint2*>(p + lo_off));
+            lw[0] = l.x; lw[1] = l.y;
+        }
+    } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float a = __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16);
-                const float b = __uint_as_float(hw[q] & 0xffff0000u) + __uint_as_float(lw[q] & 0xffff0000u);
-                acc[8 * v + 2 * q] = fmaf(wgt, a, acc[8 * v + 2 * q]);
-                acc[8 * v + 2 * q + 1] = fmaf(wgt, b, acc[8 * v + 2 * q + 1]);
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[q]));
-                acc[8 * v + 2 * q] = fmaf(wgt, f.x, acc[8 * v + 2 * q]);
-                acc[8 * v + 2 * q + 1] = fmaf(wgt, f.y, acc[8 * v + 2 * q + 1]);
+        for (int v = 0; v < CPL / 8; ++v) {
+            const uint4 h = __ldg(reinterpret_cast<const uint4*>(p) + v);
+            hw[4 * v] = h.x; hw[4 * v + 1] = h.y; hw[4 * v + 2] = h.z; hw[4 * v + 3] = h.w;
+            if (precision == DISCO_PREC_BF16X3) {
+                const uint4 l = __ldg(reinterpret_cast<const uint4*>(p + lo_off) + v);
+                lw[4 * v] = l.x; lw[4 * v + 1] = l.y; lw[4 * v + 2] = l.z; lw[4 * v + 3] = l.w;
             }
         }
     }
+#pragma unroll
+    for (int q = 0; q < NW; ++q) {
+        float a, b;
+        if (precision == DISCO_PREC_BF16X3) {
+            a = __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16);
+            b = __uint_as_float(hw[q] & 0xffff0000u) + __uint_as_float(lw[q] & 0xffff0000u);
+        } else {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[q]));
+            a = f.x; b = f.y;
+        }
+        acc[2 * q] = fmaf(wgt, a, acc[2 * q]);
+        acc[2 * q + 1] = fmaf(wgt, b, acc[2 * q + 1]);
+    }
 }
 
-template <int VEC>
+template <int CPL>
 __global__ void __launch_bounds__(kWarps * 32, 3) fusion_kernel(const disco_fusion_desc d) {
     __shared__ float s_w2[kH2][kHid + 1];
     __shared__ float s_b2[kH2];
@@ -71,7 +82,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) fusion_kernel(const disco_fusi
     const uint16_t* feat = reinterpret_cast<const uint16_t*>(d.feat_hi);
     uint16_t* out = reinterpret_cast<uint16_t*>(d.out_hi);
     const long long cells = (long long)(d.row_end - d.row_begin) * h * w;
-    const int cpl = 8 * VEC;  // channels per lane
+    const int cpl = CPL;  // channels per lane
 
     for (int t = 0; t < kCellsPerWarp; ++t) {
         const long long cell = ((long long)blockIdx.x * kWarps + warp) * kCellsPerWarp + t;
@@ -84,14 +95,14 @@ __global__ void __launch_bounds__(kWarps * 32, 3) fusion_kernel(const disco_fusi
         const long long row_i = (((long long)n_i * h + y) * w + x);
         const long long row_o = (((long long)(n_i - d.row_begin) * h + y) * w + x);
 
-        float acc[8 * VEC];
+        float acc[CPL];
 #pragma unroll
-        for (int c = 0; c < 8 * VEC; ++c) acc[c] = 0.f;
+        for (int c = 0; c < CPL; ++c) acc[c] = 0.f;
         float esum = 0.f;
 
         const bool passthrough = (i >= n_ag) || (d.outage && d.outage[b * A + i]);
         if (passthrough) {  // absent agent / communication outage: features pass through unchanged
-            load_feat<VEC>(feat + row_i * C + lane * cpl, d.feat_lo_off, d.precision, 1.f, acc);
+            load_feat<CPL>(feat + row_i * C + lane * cpl, d.feat_lo_off, d.precision, 1.f, acc);
             esum = 1.f;
             if (d.weights && lane < A && i < n_ag)   // outage: the ego is its own (only) contributor
                 d.weights[((((long long)b * A + i) * A + lane) * h + y) * w + x] = (lane == i) ? 1.f : 0.f;
@@ -104,12 +115,12 @@ __global__ void __launch_bounds__(kWarps * 32, 3) fusion_kernel(const disco_fusi
                 // reference order: ego first, then neighbours j = 0..n-1 skipping i
                 const int j = (k == 0) ? i : ((k - 1 < i) ? k - 1 : k);
                 if (j != i && d.only_v2i && i != 0 && j != 0) continue;
-                float nb[8 * VEC];
+                float nb[CPL];
 #pragma unroll
-                for (int c = 0; c < 8 * VEC; ++c) nb[c] = 0.f;
+                for (int c = 0; c < CPL; ++c) nb[c] = 0.f;
                 float nn[4] = {0.f, 0.f, 0.f, 0.f};
                 if (j == i) {
-                    load_feat<VEC>(feat + row_i * C + lane * cpl, d.feat_lo_off, d.precision, 1.f, nb);
+                    load_feat<CPL>(feat + row_i * C + lane * cpl, d.feat_lo_off, d.precision, 1.f, nb);
                     const float4 n4 = __ldg(reinterpret_cast<const float4*>(d.en + row_i * (2 * kHid) + kHid) + lane);
                     nn[0] = n4.x; nn[1] = n4.y; nn[2] = n4.z; nn[3] = n4.w;
                 } else {
@@ -131,7 +142,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) fusion_kernel(const disco_fusi
                         const int xs = x0 + (tp & 1), ysf = y0 + (tp >> 1);
                         if (xs < 0 || xs >= w || ysf < 0 || ysf >= h) continue;  // zeros padding
                         const long long row_j = (((long long)(j * B + b) * h + (h - 1 - ysf)) * w + xs);
-                        load_feat<VEC>(feat + row_j * C + lane * cpl, d.feat_lo_off, d.precision, tw[tp], nb);
+                        load_feat<CPL>(feat + row_j * C + lane * cpl, d.feat_lo_off, d.precision, tw[tp], nb);
                         const float4 n4 =
                             __ldg(reinterpret_cast<const float4*>(d.en + row_j * (2 * kHid) + kHid) + lane);
                         nn[0] = fmaf(tw[tp], n4.x, nn[0]); nn[1] = fmaf(tw[tp], n4.y, nn[1]);
@@ -167,7 +178,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) fusion_kernel(const disco_fusi
                 const float ek = expf(wk);
                 esum += ek;
 #pragma unroll
-                for (int c = 0; c < 8 * VEC; ++c) acc[c] = fmaf(ek, nb[c], acc[c]);
+                for (int c = 0; c < CPL; ++c) acc[c] = fmaf(ek, nb[c], acc[c]);
                 if (d.weights && lane == 0)
                     d.weights[((((long long)b * A + i) * A + j) * h + y) * w + x] = ek;
             }
@@ -181,29 +192,34 @@ __global__ void __launch_bounds__(kWarps * 32, 3) fusion_kernel(const disco_fusi
             }
         }
         // ---- normalise and store -------------------------------------------------------------------
-        const float inv = 1.f / esum;
+        const float inv = passthrough ? 1.f : 1.f / esum;
         uint16_t* o = out + row_o * C + lane * cpl;
+        uint32_t hi[CPL / 2], lo[CPL / 2];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float a = passthrough ? acc[8 * v + 2 * q] : acc[8 * v + 2 * q] * inv;
-                const float c2 = passthrough ? acc[8 * v + 2 * q + 1] : acc[8 * v + 2 * q + 1] * inv;
-                if (d.precision == DISCO_PREC_BF16X3) {
-                    uint16_t h0, l0, h1_, l1;
-                    split_bf16(a, h0, l0);
-                    split_bf16(c2, h1_, l1);
-                    hi[q] = (uint32_t)h0 | ((uint32_t)h1_ << 16);
-                    lo[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-                } else {
-                    hi[q] = (uint32_t)f32_to_f16_bits(a) | ((uint32_t)f32_to_f16_bits(c2) << 16);
-                    lo[q] = 0;
-                }
+        for (int q = 0; q < CPL / 2; ++q) {
+            const float a = acc[2 * q] * inv, c2 = acc[2 * q + 1] * inv;
+            if (d.precision == DISCO_PREC_BF16X3) {
+                uint16_t h0, l0, h1_, l1;
+                split_bf16(a, h0, l0);
+                split_bf16(c2, h1_, l1);
+                hi[q] = (uint32_t)h0 | ((uint32_t)h1_ << 16);
+                lo[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+            } else {
+                hi[q] = (uint32_t)f32_to_f16_bits(a) | ((uint32_t)f32_to_f16_bits(c2) << 16);
+                lo[q] = 0;
             }
-            reinterpret_cast<uint4*>(o)[v] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            if (d.precision == DISCO_PREC_BF16X3)
-                reinterpret_cast<uint4*>(o + d.out_lo_off)[v] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        if (CPL == 4) {
+            *reinterpret_cast<uint2*>(o) = make_uint2(hi[0], hi[1]);
+            if (d.precision == DISCO_PREC_BF16X3) *reinterpret_cast<uint2*>(o + d.out_lo_off) = make_uint2(lo[0], lo[1]);
+        } else {
+#pragma unroll
+            for (int v = 0; v < CPL / 8; ++v) {
+                reinterpret_cast<uint4*>(o)[v] = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
+                if (d.precision == DISCO_PREC_BF16X3)
+                    reinterpret_cast<uint4*>(o + d.out_lo_off)[v] =
+                        make_uint4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+            }
         }
     }
 }
@@ -214,7 +230,7 @@ int disco_fusion_launch(const disco_fusion_desc* d, void* stream) {
     DISCO_REQUIRE(d->feat_hi && d->en && d->out_hi && d->trans && d->num_agent, "fusion: null tensor");
     DISCO_REQUIRE(d->w2 && d->b2 && d->w3 && d->b3 && d->w4 && d->b4, "fusion: null PWF weights");
     DISCO_REQUIRE(d->hid == kHid, "fusion: PWF hidden width must be %d (got %d)", kHid, d->hid);
-    DISCO_REQUIRE(d->C == 256 || d->C == 512, "fusion: C must be 256 or 512 (got %d)", d->C);
+    DISCO_REQUIRE(d->C == 128 || d->C == 256 || d->C == 512, "fusion: C must be 128, 256 or 512 (got %d)", d->C);
     DISCO_REQUIRE(d->A >= 1 && d->A <= 32 && d->B >= 1 && d->h > 0 && d->w > 0, "fusion: bad scene shape");
     DISCO_REQUIRE(d->row_begin >= 0 && d->row_begin < d->row_end && d->row_end <= d->A * d->B,
                   "fusion: bad ego row range [%d,%d)", d->row_begin, d->row_end);
@@ -222,8 +238,9 @@ int disco_fusion_launch(const disco_fusion_desc* d, void* stream) {
     const long long per_block = kWarps * kCellsPerWarp;
     const long long blocks = (cells + per_block - 1) / per_block;
     DISCO_REQUIRE(blocks < (1ll << 31), "fusion: too many cells");
-    if (d->C == 256) fusion_kernel<1><<<(unsigned)blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(*d);
-    else fusion_kernel<2><<<(unsigned)blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(*d);
+    if (d->C == 128) fusion_kernel<4><<<(unsigned)blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(*d);
+    else if (d->C == 256) fusion_kernel<8><<<(unsigned)blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(*d);
+    else fusion_kernel<16><<<(unsigned)blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(*d);
     DISCO_CHECK_CUDA(cudaGetLastError());
     return DISCO_OK;
 }

@@ -169,8 +169,8 @@ class DiscoNet(_DetBase):
             self.pixel_weighted_fusion = PixelWeightedFusionParams(128)
 
     def _build_plans(self, get):
-        if self.layer != 3:
-            raise NotImplementedError("disconet_b200 implements collaboration at --layer 3 (the CLI default)")
+        if self.layer not in (2, 3):
+            raise NotImplementedError("DiscoNet has a PixelWeightedFusion for --layer 2 or 3 only (DiscoNet.py:23-26)")
         p = self.precision
         return {
             "enc": engine.build_encoder_plans(get, "u_encoder.", p, compress=self.compress_level > 0),
@@ -185,7 +185,7 @@ class DiscoNet(_DetBase):
         if ws is None:
             P = self.plans()
             ws = engine.Workspace(n, h, w, self.precision, device, P["enc"], P["dec"], P["heads"], P["pwf"],
-                                  batch_size=batch_size, agents=self.agent_num)
+                                  batch_size=batch_size, agents=self.agent_num, fusion_level=self.layer)
             self._ws[key] = ws
         return ws
 
@@ -212,7 +212,7 @@ class DiscoNet(_DetBase):
         ws = self._ws.get(key)
         if ws is None:
             ws = engine.Workspace(n_loc, H, W, self.precision, dev, P["enc"], P["dec"], P["heads"], P["pwf"],
-                                  batch_size=B, agents=A, shard=(r0, A * B))
+                                  batch_size=B, agents=A, shard=(r0, A * B), fusion_level=self.layer)
             self._ws[key] = ws
         stream = torch.cuda.current_stream(dev).cuda_stream
         trans = trans_matrices.detach().to(device=dev, dtype=torch.float64, non_blocking=True).contiguous()
@@ -220,7 +220,7 @@ class DiscoNet(_DetBase):
         self._pack_input(bevs_local, ws)
         for c in ws.enc_calls:
             c.launch(stream)
-        parallel.all_gather_rows(ws.buf[ws.x3_key], ws.buf["x3g"], group)     # the path's one exchange step
+        parallel.all_gather_rows(ws.buf[ws.feat_key], ws.buf["x3g"], group)     # the path's one exchange step
         ws.en_call.launch(stream)
         f = ws.fusion
         f.trans, f.num_agent, f.only_v2i, f.weights = trans.data_ptr(), num_agent.data_ptr(), int(bool(self.only_v2i)), None
@@ -250,7 +250,7 @@ class DiscoNet(_DetBase):
         P = self.plans()
         ws = self._workspace(N, H, W, B, dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        h3, w3 = ws.h // 8, ws.w // 8
+        h3, w3 = ws.fuse_hw
         if getattr(ws, "static", None) is None:
             # static device-side arguments of the fusion kernel (so the launch sequence can be graph-captured)
             ws.static = {
@@ -314,7 +314,7 @@ class DiscoNet(_DetBase):
         num_agent = st["na"].clone() if self.kd_flag != 1 else None
         if self.kd_flag == 1:
             return (result, self._nchw(ws, "x8"), self._nchw(ws, "x7"), self._nchw(ws, "x6"), self._nchw(ws, "x5"),
-                    self._nchw(ws, "x3f"))
+                    self._nchw(ws, ws.fused_key))
         return result, AgentWeightList(weights, num_agent, bool(self.only_v2i), outage_host)
 
 

@@ -140,7 +140,7 @@ class Workspace:
 
     def __init__(self, n: int, h: int, w: int, precision: int, device, enc: Dict[str, ConvPlan],
                  dec: Dict[str, ConvPlan], heads=None, pwf=None, batch_size: int = 1, agents: int = 1,
-                 shard=None):
+                 shard=None, fusion_level: int = 3):
         """`n` = image rows held by this process.  `shard = (row_begin, n_global)` for the agent-sharded
         mode: encoder/decoder/heads run on the local rows, the fusion reads the gathered `x3g` of all
         `n_global` rows and produces only the local ego rows."""
@@ -187,14 +187,23 @@ class Workspace:
         self.fusion: Optional[FusionDesc] = None
         x3_dec = b[self.x3_key]
         self.shard = shard
+        x2_dec = b["x2"]
+        self.feat_key, self.fused_key = self.x3_key, "x3f"
         if pwf is not None:
+            # collaboration level: 3 -> x_3 (256 ch @ H/8), 2 -> x_2 (128 ch @ H/4)   (DiscoNet.py:23-26)
+            if fusion_level not in (2, 3):
+                raise NotImplementedError("DiscoNet builds its PixelWeightedFusion for layer 2 or 3 only")
             row_begin, n_glob = (0, n) if shard is None else shard
-            feat = b[self.x3_key]
+            hf, wf, cf = (h3, w3, 256) if fusion_level == 3 else (h2, w2, 128)
+            self.feat_key = self.x3_key if fusion_level == 3 else "x2"
+            self.fused_key = "x3f" if fusion_level == 3 else "x2f"
+            self.fuse_hw = (hf, wf)
+            feat = b[self.feat_key]
             if shard is not None:
-                feat = b["x3g"] = ops.alloc_act(n_glob, h3, w3, 256, precision, device)
-            b["en"] = torch.empty((n_glob, h3, w3, 256), dtype=torch.float32, device=device)
-            b["x3f"] = A(h3, w3, 256)
-            self.en_call = ops.ConvCall(pwf["en"], [feat], [0], (b["en"],), n=n_glob, h_in=h3, w_in=w3)
+                feat = b["x3g"] = ops.alloc_act(n_glob, hf, wf, cf, precision, device)
+            b["en"] = torch.empty((n_glob, hf, wf, 256), dtype=torch.float32, device=device)
+            b[self.fused_key] = A(hf, wf, cf)
+            self.en_call = ops.ConvCall(pwf["en"], [feat], [0], (b["en"],), n=n_glob, h_in=hf, w_in=wf)
             f = FusionDesc()
             f.feat_hi = feat.data_ptr()
             f.feat_lo_off = ops._lo_off(feat)
@@ -203,18 +212,21 @@ class Workspace:
             f.hid = 128
             t = pwf["tail"]
             f.w2, f.b2, f.w3, f.b3, f.w4, f.b4 = (x.data_ptr() for x in t)
-            f.B, f.A, f.h, f.w, f.C = batch_size, agents, h3, w3, 256
+            f.B, f.A, f.h, f.w, f.C = batch_size, agents, hf, wf, cf
             f.trans_scale = 4.0 / 128.0
-            f.out_hi = b["x3f"].data_ptr()
-            f.out_lo_off = ops._lo_off(b["x3f"])
+            f.out_hi = b[self.fused_key].data_ptr()
+            f.out_lo_off = ops._lo_off(b[self.fused_key])
             f.row_begin, f.row_end = row_begin, row_begin + n
             self.fusion = f
             self._pwf_keep = pwf
-            x3_dec = b["x3f"]
+            if fusion_level == 3:
+                x3_dec = b["x3f"]
+            else:
+                x2_dec = b["x2f"]
         self.dec_calls: List[ops.ConvCall] = [
             mk(dec["c5_1"], [b["x4"], x3_dec], [1, 0], b["t5"], h3, w3),
             mk(dec["c5_2"], [b["t5"]], [0], b["x5"], h3, w3),
-            mk(dec["c6_1"], [b["x5"], b["x2"]], [1, 0], b["t6"], h2, w2),
+            mk(dec["c6_1"], [b["x5"], x2_dec], [1, 0], b["t6"], h2, w2),
             mk(dec["c6_2"], [b["t6"]], [0], b["x6"], h2, w2),
             mk(dec["c7_1"], [b["x6"], b["x1"]], [1, 0], b["t7"], h1, w1),
             mk(dec["c7_2"], [b["t7"]], [0], b["x7"], h1, w1),

@@ -166,13 +166,15 @@ def heads(sd, x8, category_num=2, anchors=6, box_code=6):
 def disconet_forward(sd, bevs, trans_matrices, num_agent_tensor, batch_size, agent_num=5,
                      layer=3, only_v2i=False, return_all=False, outage=None):
     """Eval-mode DiscoNet.forward (DiscoNet.py:28-129).  bevs [A*B,1,H,W,13]."""
-    if layer != 3:
-        raise NotImplementedError("oracle restates the CLI default --layer 3")
+    if layer not in (2, 3):
+        raise NotImplementedError("the reference builds a PixelWeightedFusion for layer 2 or 3 only")
     bev = bevs.permute(0, 1, 4, 2, 3)
     bev = bev.reshape(-1, bev.shape[2], bev.shape[3], bev.shape[4])
     x, x1, x2, x3, x4 = encode(sd, "u_encoder.", bev)
-    fused, weights = fuse(sd, x3, trans_matrices, num_agent_tensor, batch_size, agent_num, only_v2i, outage)
-    x8, x7, x6, x5 = decode(sd, "decoder.", x, x1, x2, fused, x4)
+    enc = [x, x1, x2, x3, x4]
+    fused, weights = fuse(sd, enc[layer], trans_matrices, num_agent_tensor, batch_size, agent_num, only_v2i, outage)
+    enc[layer] = fused                         # DetModelBase.py:222 (get_decoded_layers)
+    x8, x7, x6, x5 = decode(sd, "decoder.", *enc)
     cls, loc = heads(sd, x8)
     out = {"cls": cls, "loc": loc}
     if return_all:

@@ -24,6 +24,7 @@ DISCO_CASES = {
     "disco_a2_b1": dict(A=2, B=1, num_agent=[2], kd_flag=1, only_v2i=False, compress_level=0, seed=11),
     "disco_a3_b2_absent": dict(A=3, B=2, num_agent=[3, 2], kd_flag=0, only_v2i=False, compress_level=0, seed=12),
     "disco_a3_b1_v2i_comp": dict(A=3, B=1, num_agent=[3], kd_flag=1, only_v2i=True, compress_level=2, seed=13),
+    "disco_a2_b1_layer2": dict(A=2, B=1, num_agent=[2], kd_flag=1, only_v2i=False, compress_level=0, seed=14, layer=2),
 }
 
 
@@ -50,7 +51,7 @@ def main():
     cfg = Config("train", binary=True, only_det=True)
     keys = {}
     for name, case in DISCO_CASES.items():
-        m = RDisco(cfg, layer=3, kd_flag=case["kd_flag"], num_agent=case["A"], compress_level=case["compress_level"],
+        m = RDisco(cfg, layer=case.get("layer", 3), kd_flag=case["kd_flag"], num_agent=case["A"], compress_level=case["compress_level"],
                    only_v2i=case["only_v2i"]).eval()
         keys[name] = [[k, list(v.shape)] for k, v in m.state_dict().items()]
         sd, bev, T, na = golden_case_inputs(case, m.state_dict())

@@ -24,7 +24,7 @@ TOL = {"bf16x3": 1e-3, "fp16": 1e-2}
 
 def _ours(case, sd, dev, precision, kd_flag=None):
     from disconet_b200 import DiscoNet
-    m = DiscoNet(_Cfg(), layer=3, kd_flag=case["kd_flag"] if kd_flag is None else kd_flag, num_agent=case["A"],
+    m = DiscoNet(_Cfg(), layer=case.get("layer", 3), kd_flag=case["kd_flag"] if kd_flag is None else kd_flag, num_agent=case["A"],
                  compress_level=case["compress_level"], only_v2i=case["only_v2i"], precision=precision)
     m.load_state_dict(sd)
     return m.to(dev).eval()
@@ -35,7 +35,8 @@ def _ours(case, sd, dev, precision, kd_flag=None):
 def test_disconet_matches_oracle_and_golden(name, precision, cuda_dev):
     case = DISCO_CASES[name]
     sd, bev, T, na = golden_case_inputs(case, _template(name))
-    ref = O.disconet_forward(sd, bev, T, na, case["B"], agent_num=case["A"], only_v2i=case["only_v2i"], return_all=True)
+    ref = O.disconet_forward(sd, bev, T, na, case["B"], agent_num=case["A"], only_v2i=case["only_v2i"], return_all=True,
+                             layer=case.get("layer", 3))
     m = _ours(case, sd, cuda_dev, precision)
     with torch.no_grad():
         out = m(bev.to(cuda_dev), T, na, batch_size=case["B"])   # trans on CPU like train_codet.py:333

@@ -55,7 +55,7 @@ def test_oracle_matches_reference_golden(name):
     rec = np.load(os.path.join(GOLD, name + ".npz"))
     sd, bev, T, na = golden_case_inputs(case, _template(name))
     out = O.disconet_forward(sd, bev, T, na, case["B"], agent_num=case["A"], only_v2i=case["only_v2i"],
-                             return_all=True)
+                             return_all=True, layer=case.get("layer", 3))
     _check_sub(name, out["cls"], rec, "cls")
     _check_sub(name, out["loc"], rec, "loc")
     if case["kd_flag"] == 1:
@@ -104,8 +104,8 @@ def test_state_dict_layout_matches_reference():
         keys = json.load(f)
     cfg = _Cfg()
     for name, case in DISCO_CASES.items():
-        m = DiscoNet(cfg, layer=3, kd_flag=case["kd_flag"], num_agent=case["A"], compress_level=case["compress_level"],
-                     only_v2i=case["only_v2i"])
+        m = DiscoNet(cfg, layer=case.get("layer", 3), kd_flag=case["kd_flag"], num_agent=case["A"],
+                     compress_level=case["compress_level"], only_v2i=case["only_v2i"])
         got = [[k, list(v.shape)] for k, v in m.state_dict().items()]
         assert got == keys[name], name
     assert [[k, list(v.shape)] for k, v in FaFNet(cfg, kd_flag=0, num_agent=2).state_dict().items()] == keys["fafnet_a2_128"]
