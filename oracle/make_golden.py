@@ -28,6 +28,24 @@ DISCO_CASES = {
 }
 
 
+# training-mode cases (a12): forward with batch-statistics BN + backward of `probe_loss` through the live reference
+TRAIN_CASES = {
+    "train_a2_b1": dict(A=2, B=1, num_agent=[2], kd_flag=1, only_v2i=False, compress_level=0, seed=31),
+    "train_a3_b1_absent": dict(A=3, B=1, num_agent=[2], kd_flag=1, only_v2i=False, compress_level=0, seed=32),
+}
+TRAIN_OUT_KEYS = ("cls", "loc", "x_8", "x_7", "x_6", "x_5", "fused")
+
+
+def grad_digest(named: dict, stride: int = 499):
+    """{name: tensor} -> flat strided subsample + per-tensor [l2 norm, max|.|] table (sorted by name)."""
+    subs, table = [], []
+    for k in sorted(named):
+        f = named[k].detach().reshape(-1).double()
+        subs.append(f[::stride].float().numpy())
+        table.append([f.norm().item(), f.abs().max().item() if f.numel() else 0.0])
+    return np.concatenate(subs), np.array(table)
+
+
 def golden_case_inputs(case: dict, template_sd: dict):
     A, B = case["A"], case["B"]
     sd = O.synth_state_dict(template_sd, seed=case["seed"])
@@ -71,6 +89,28 @@ def main():
             rec[k + "_shape"] = np.array(t.shape)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
         print(name, {k: v.shape for k, v in rec.items()})
+
+    for name, case in TRAIN_CASES.items():
+        m = RDisco(cfg, layer=3, kd_flag=1, num_agent=case["A"], compress_level=0, only_v2i=case["only_v2i"]).train()
+        keys[name] = [[k, list(v.shape)] for k, v in m.state_dict().items()]
+        sd, bev, T, na = golden_case_inputs(case, m.state_dict())
+        m.load_state_dict(sd)
+        out = m(bev, T, na, batch_size=case["B"])
+        tensors = dict(zip(TRAIN_OUT_KEYS, (out[0]["cls"], out[0]["loc"]) + tuple(out[1:])))
+        loss, _ = O.probe_loss(tensors, seed=case["seed"] + 300)
+        loss.backward()
+        rec = {"loss": np.array([loss.item()])}
+        for k, t in tensors.items():
+            rec[k + "_sub"], rec[k + "_stats"] = _sub(t, STRIDES[k])
+            rec[k + "_shape"] = np.array(t.shape)
+        grads = {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in m.named_parameters()}
+        rec["grad_sub"], rec["grad_table"] = grad_digest(grads)
+        rec["grad_names"] = np.array(sorted(grads))
+        rec["grad_none"] = np.array([k for k, p in m.named_parameters() if p.grad is None])
+        bufs = {k: v.float() for k, v in m.named_buffers()}
+        rec["buf_sub"], rec["buf_table"] = grad_digest(bufs, stride=7)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+        print(name, "loss", loss.item(), {k: v.shape for k, v in rec.items()})
 
     # FaFNet lower-bound plumbing config (BASELINE config 1): 2 agents, 128x128x13
     m = RFaF(cfg, kd_flag=0, num_agent=2).eval()

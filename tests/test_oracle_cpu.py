@@ -197,3 +197,54 @@ def test_c_abi_exports_every_declared_symbol():
             names.append(re.findall(r"(\w+)(?:\[\d+\])?$", first.strip())[0])
             names += [re.findall(r"(\w+)", r)[0] for r in rest]
         assert names == [f[0] for f in cls._fields_], (struct, names)
+
+
+# ---- training mode (a12): oracle restatement (batch-stat BN + torch.autograd) vs the live-reference golden ----
+def oracle_train_step(case, sd):
+    """Oracle forward in training mode + backward of probe_loss.  Returns (outputs, loss, grads, new buffers)."""
+    from oracle.make_golden import TRAIN_OUT_KEYS
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))
+              else v.clone()) for k, v in sd.items()}
+    _, bev, T, na = golden_case_inputs(case, sd)
+    with O.training(sd) as ctx:
+        out = O.disconet_forward_graph(sd, bev, T, na, case["B"], agent_num=case["A"], only_v2i=case["only_v2i"],
+                                       return_all=True)
+    tensors = {k: out[k] for k in TRAIN_OUT_KEYS}
+    loss, cot = O.probe_loss(tensors, seed=case["seed"] + 300)
+    loss.backward()
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in sd.items() if v.requires_grad}
+    return tensors, loss, grads, ctx.buffers, cot
+
+
+@pytest.mark.parametrize("name", ["train_a2_b1", "train_a3_b1_absent"])
+def test_oracle_training_matches_reference_golden(name):
+    from oracle.make_golden import TRAIN_CASES, grad_digest
+    case = TRAIN_CASES[name]
+    rec = np.load(os.path.join(GOLD, name + ".npz"))
+    sd, *_ = golden_case_inputs(case, _template(name))
+    tensors, loss, grads, bufs, _ = oracle_train_step(case, sd)
+    assert abs(loss.item() - rec["loss"][0]) <= 1e-3 * max(1.0, abs(rec["loss"][0]))   # sum of ~1e7 signed terms
+    for k, t in tensors.items():
+        _check_sub(name, t, rec, k, tol=2e-4)   # reference BN kernels: 3e-4 between 1 and 8 threads
+    assert sorted(grads) == rec["grad_names"].tolist()
+    sub, table = grad_digest(grads)
+    ref_table = rec["grad_table"]
+    # Gradient tolerance.  Train-mode gradients of this ReLU/BatchNorm stack are ill-conditioned in fp32: a forward
+    # perturbation of relative size f flips a fraction ~f of the ReLU gates and moves cancellation-dominated sums
+    # by ~sqrt(f).  Measured in this container: the reference against ITSELF at 1 vs 8 CPU threads moves its
+    # outputs by 3e-4 and its gradients by 2-8 % (rel-max per tensor); this fp32 oracle against its own float64
+    # run: outputs 1e-5, gradients up to 4e-2.  So the pin is: per-tensor l2 norms within 2 %, cosine similarity of
+    # the sampled gradient vector >= 0.9995.  (Conv biases in front of a BatchNorm have a mathematically zero
+    # gradient -- pure rounding noise on both sides -- and are skipped.)  Exact backward arithmetic is pinned
+    # per kernel in tests/test_train_gpu.py against torch.autograd on identical inputs.
+    names = sorted(grads)
+    for i, k in enumerate(names):
+        if k.endswith(".bias") and not (".bn" in k or "bn_" in k or "box_prediction.1" in k or "conv2." in k
+                                        or "box_prediction.3" in k or "conv1_4" in k):
+            assert table[i, 0] <= 1e-4 * ref_table[:, 0].max(), k     # BN-shadowed conv bias: zero up to noise
+            continue
+        assert abs(table[i, 0] - ref_table[i, 0]) <= 2e-2 * ref_table[i, 0], (k, table[i, 0], ref_table[i, 0])
+    cos = float(np.dot(sub, rec["grad_sub"]) / (np.linalg.norm(sub) * np.linalg.norm(rec["grad_sub"])))
+    assert cos >= 0.9995, cos
+    bsub, _ = grad_digest({k: v.float() for k, v in bufs.items()}, stride=7)
+    assert np.abs(bsub - rec["buf_sub"]).max() <= 2e-4 * np.abs(rec["buf_sub"]).max()
