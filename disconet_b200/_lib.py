@@ -53,6 +53,57 @@ class FusionDesc(C.Structure):
         ("weights", C.c_void_p),
         ("row_begin", C.c_int), ("row_end", C.c_int),
         ("outage", C.c_void_p),
+        ("wpre", C.c_void_p),
+    ]
+
+
+class GradSrc(C.Structure):
+    """struct disco_grad_src."""
+    _fields_ = [("ptr", C.c_void_p), ("c_total", C.c_int), ("c_off", C.c_int), ("pool", C.c_int)]
+
+
+class BnDesc(C.Structure):
+    """struct disco_bn_desc (training-mode BatchNorm forward/backward)."""
+    _fields_ = [
+        ("z", C.c_void_p), ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("c", C.c_int),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("num_batches_tracked", C.c_void_p),
+        ("momentum", C.c_float), ("eps", C.c_float),
+        ("sums", C.c_void_p), ("stats", C.c_void_p),
+        ("out_hi", C.c_void_p), ("out_lo_off", C.c_longlong), ("relu", C.c_int),
+        ("g", GradSrc * 3), ("n_g", C.c_int),
+        ("dz_hi", C.c_void_p), ("dz_lo_off", C.c_longlong),
+        ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+    ]
+
+
+class WgradDesc(C.Structure):
+    """struct disco_wgrad_desc."""
+    _fields_ = [
+        ("src", C.c_void_p * 2), ("src_lo_off", C.c_longlong * 2), ("src_c", C.c_int * 2), ("src_up", C.c_int * 2),
+        ("n", C.c_int), ("h_in", C.c_int), ("w_in", C.c_int), ("h_out", C.c_int), ("w_out", C.c_int),
+        ("stride", C.c_int), ("taps", C.c_int),
+        ("dz_hi", C.c_void_p), ("dz_lo_off", C.c_longlong), ("c_out", C.c_int),
+        ("partial", C.c_void_p), ("splits", C.c_int), ("dw", C.c_void_p), ("c_in_real", C.c_int), ("passes", C.c_int),
+    ]
+
+
+class PwfTrainDesc(C.Structure):
+    """struct disco_pwf_train_desc."""
+    _fields_ = [
+        ("feat_hi", C.c_void_p), ("feat_lo_off", C.c_longlong), ("en", C.c_void_p), ("hid", C.c_int),
+        ("g1", C.c_void_p), ("be1", C.c_void_p),
+        ("w2", C.c_void_p), ("b2", C.c_void_p), ("g2", C.c_void_p), ("be2", C.c_void_p),
+        ("w3", C.c_void_p), ("b3", C.c_void_p), ("g3", C.c_void_p), ("be3", C.c_void_p),
+        ("w4", C.c_void_p), ("b4", C.c_void_p),
+        ("eps", C.c_float), ("momentum", C.c_float),
+        ("rm1", C.c_void_p), ("rv1", C.c_void_p), ("rm2", C.c_void_p), ("rv2", C.c_void_p), ("rm3", C.c_void_p), ("rv3", C.c_void_p),
+        ("nbt1", C.c_void_p), ("nbt2", C.c_void_p), ("nbt3", C.c_void_p),
+        ("trans", C.c_void_p), ("num_agent", C.c_void_p), ("outage", C.c_void_p),
+        ("B", C.c_int), ("A", C.c_int), ("h", C.c_int), ("w", C.c_int), ("C", C.c_int),
+        ("only_v2i", C.c_int), ("trans_scale", C.c_float),
+        ("pstats", C.c_void_p), ("wlogit", C.c_void_p),
+        ("dfused", C.c_void_p), ("dwlogit", C.c_void_p), ("dfeat", C.c_void_p), ("den", C.c_void_p), ("dparams", C.c_void_p),
     ]
 
 
@@ -73,6 +124,19 @@ EXPORTS = {
     "disco_bev_scatter": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_int,
                                     C.c_int, C.c_void_p]),
     "disco_fusion_forward": (C.c_int, [C.POINTER(FusionDesc), C.c_void_p]),
+    # training mode
+    "disco_bn_train_forward": (C.c_int, [C.POINTER(BnDesc), C.c_void_p]),
+    "disco_bn_train_backward": (C.c_int, [C.POINTER(BnDesc), C.c_void_p]),
+    "disco_grad_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "disco_channel_sum": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "disco_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "disco_add_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "disco_conv_wgrad": (C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
+    "disco_conv_wgrad_reference": (C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
+    "disco_conv_wgrad_splits": (C.c_int, [C.POINTER(WgradDesc)]),
+    "disco_pwf_train_forward": (C.c_int, [C.POINTER(PwfTrainDesc), C.c_void_p]),
+    "disco_fusion_combine_backward": (C.c_int, [C.POINTER(PwfTrainDesc), C.c_void_p]),
+    "disco_pwf_train_backward": (C.c_int, [C.POINTER(PwfTrainDesc), C.c_void_p]),
 }
 
 _lib = None

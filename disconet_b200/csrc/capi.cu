@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "conv.h"
 #include "ops.h"
+#include "train.h"
 
 static thread_local char g_err[512] = "";
 
@@ -78,6 +79,53 @@ int disco_bev_scatter(const int* voxel_indices, int n_voxels, const int* dims, f
 int disco_fusion_forward(const disco_fusion_desc* d, void* stream) {
     if (!d) { disco_set_error("null descriptor"); return DISCO_EINVAL; }
     return disco_fusion_launch(d, stream);
+}
+
+// ---- training mode ----------------------------------------------------------------------
+int disco_bn_train_forward(const disco_bn_desc* d, void* stream) {
+    if (!d) { disco_set_error("null descriptor"); return DISCO_EINVAL; }
+    return disco_bn_train_forward_launch(d, stream);
+}
+int disco_bn_train_backward(const disco_bn_desc* d, void* stream) {
+    if (!d) { disco_set_error("null descriptor"); return DISCO_EINVAL; }
+    return disco_bn_train_backward_launch(d, stream);
+}
+int disco_grad_pack(const float* a, int ca, const float* b, int cb, long long n_pix, void* out_hi, long long out_lo_off,
+                    void* stream) {
+    return disco_grad_pack_launch(a, ca, b, cb, n_pix, out_hi, out_lo_off, stream);
+}
+int disco_channel_sum(const float* src, long long n_pix, int c, double* sums, float* out, void* stream) {
+    return disco_channel_sum_launch(src, n_pix, c, sums, out, stream);
+}
+int disco_nchw_to_nhwc(const float* src, int n, int c, int h, int w, float* dst, void* stream) {
+    return disco_nchw_to_nhwc_launch(src, n, c, h, w, dst, stream);
+}
+int disco_add_f32(float* dst, const float* a, const float* b, long long n, void* stream) {
+    return disco_add_f32_launch(dst, a, b, n, stream);
+}
+int disco_conv_wgrad(const disco_wgrad_desc* d, void* stream) {
+    if (!d) { disco_set_error("null descriptor"); return DISCO_EINVAL; }
+    return disco_wgrad_tc_launch(d, stream);
+}
+int disco_conv_wgrad_reference(const disco_wgrad_desc* d, void* stream) {
+    if (!d) { disco_set_error("null descriptor"); return DISCO_EINVAL; }
+    return disco_wgrad_ref_launch(d, stream);
+}
+int disco_conv_wgrad_splits(const disco_wgrad_desc* d) {
+    if (!d) { disco_set_error("null descriptor"); return DISCO_EINVAL; }
+    return disco_wgrad_splits(d);
+}
+int disco_pwf_train_forward(const disco_pwf_train_desc* d, void* stream) {
+    if (!d) { disco_set_error("null descriptor"); return DISCO_EINVAL; }
+    return disco_pwf_train_forward_launch(d, stream);
+}
+int disco_fusion_combine_backward(const disco_pwf_train_desc* d, void* stream) {
+    if (!d) { disco_set_error("null descriptor"); return DISCO_EINVAL; }
+    return disco_fusion_combine_backward_launch(d, stream);
+}
+int disco_pwf_train_backward(const disco_pwf_train_desc* d, void* stream) {
+    if (!d) { disco_set_error("null descriptor"); return DISCO_EINVAL; }
+    return disco_pwf_train_backward_launch(d, stream);
 }
 
 }  // extern "C"

@@ -18,7 +18,8 @@ struct disco_conv_desc {
     const void* src[2];      // hi tensors (16-bit elements)
     long long src_lo_off[2]; // elements from hi to lo tensor (BF16X3 only)
     int src_c[2];            // channels per source (multiple of 16; second may be 0)
-    int src_up[2];           // 1: source is (H_in/2 x W_in/2), nearest-upsampled x2 on the fly
+    int src_up[2];           // 1: source is (H_in/2 x W_in/2), nearest-upsampled x2 on the fly; 2: same size, ZERO-STUFFED
+                             // (value at even (h,w) only) -- the data gradient of a stride-2 conv as a stride-1 conv
     int n, h_in, w_in;       // logical (post-upsample) conv input size
     int h_out, w_out;
     int stride;              // 1 | 2

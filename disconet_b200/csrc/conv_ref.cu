@@ -32,7 +32,8 @@ __global__ void conv_ref_kernel(const disco_conv_desc d, long long total) {
             for (int s = 0; s < 2; ++s) {
                 const int Cs = d.src_c[s];
                 if (!Cs) continue;
-                const int up = d.src_up[s];
+                const int up = d.src_up[s] ? 1 : 0;
+                if (d.src_up[s] == 2 && ((hi | wi) & 1)) continue;   // zero-stuffed source: odd rows/cols are zero
                 const int Hs = d.h_in >> up, Ws = d.w_in >> up;
                 const uint16_t* p = reinterpret_cast<const uint16_t*>(d.src[s]) +
                                     (((long long)img * Hs + (hi >> up)) * Ws + (wi >> up)) * Cs;

@@ -405,7 +405,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                 const int cbl = sidx ? cb - g.ncb0 : cb;
                 const uint16_t* __restrict__ src = reinterpret_cast<const uint16_t*>(sidx ? d.src[1] : d.src[0]);
                 const int Cs = sidx ? d.src_c[1] : d.src_c[0];
-                const int up = sidx ? d.src_up[1] : d.src_up[0];
+                const int upm = sidx ? d.src_up[1] : d.src_up[0];
+                const int up = upm ? 1 : 0;          // 1: nearest x2 upsample, 2: zero-stuffed x2 (transposed stride-2 conv)
+                const bool stuff = upm == 2;
                 const int Hs = d.h_in >> up, Ws = d.w_in >> up;
                 const long long lo_off = sidx ? d.src_lo_off[1] : d.src_lo_off[0];
                 const uint32_t stage = a_base + sa * g.a_stage_bytes;
@@ -427,7 +429,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                         const int c = e >> g.chunk_shift, chunk = e & (g.chunks - 1);
                         const int wi = wi0 + c;
                         act[j] = e < per_row;
-                        vcol[j] = (wi >= 0) && (wi < d.w_in);
+                        vcol[j] = (wi >= 0) && (wi < d.w_in) && !(stuff && (wi & 1));
                         soff[j] = (uint32_t)chunk * g.plane +
                                   ((MODE == 0) ? (uint32_t)c * 16u
                                                : (uint32_t)(c & 1) * g.parplane + (uint32_t)(c >> 1) * 16u);
@@ -438,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
 #pragma unroll 2
                     for (int r = 0; r < PH; ++r) {
                         const int hi = hi0 + r;
-                        const bool rv = (hi >= 0) && (hi < d.h_in);
+                        const bool rv = (hi >= 0) && (hi < d.h_in) && !(stuff && (hi & 1));
                         const uint16_t* rowp = src + (img_base + (hi >> up)) * row_stride;
                         const uint32_t drow = stage + (uint32_t)r * ROWPITCH;
 #pragma unroll

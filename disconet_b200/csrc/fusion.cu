@@ -71,11 +71,13 @@ __global__ void __launch_bounds__(kWarps * 32, 3) fusion_kernel(const disco_fusi
     __shared__ __align__(16) float s_h1[kWarps][kHid];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int e = tid; e < kH2 * kHid; e += blockDim.x) s_w2[e / kHid][e % kHid] = d.w2[e];
-    for (int e = tid; e < kH3 * kH2; e += blockDim.x) s_w3[e / kH2][e % kH2] = d.w3[e];
-    if (tid < kH2) s_b2[tid] = d.b2[tid];
-    if (tid < kH3) { s_b3[tid] = d.b3[tid]; s_w4[tid] = d.w4[tid]; }
-    if (tid == 0) s_b4 = d.b4[0];
+    if (!d.wpre) {
+        for (int e = tid; e < kH2 * kHid; e += blockDim.x) s_w2[e / kHid][e % kHid] = d.w2[e];
+        for (int e = tid; e < kH3 * kH2; e += blockDim.x) s_w3[e / kH2][e % kH2] = d.w3[e];
+        if (tid < kH2) s_b2[tid] = d.b2[tid];
+        if (tid < kH3) { s_b3[tid] = d.b3[tid]; s_w4[tid] = d.w4[tid]; }
+        if (tid == 0) s_b4 = d.b4[0];
+    }
     __syncthreads();
 
     const int C = d.C, h = d.h, w = d.w, A = d.A, B = d.B;
@@ -107,7 +109,10 @@ __global__ void __launch_bounds__(kWarps * 32, 3) fusion_kernel(const disco_fusi
             if (d.weights && lane < A && i < n_ag)   // outage: the ego is its own (only) contributor
                 d.weights[((((long long)b * A + i) * A + lane) * h + y) * w + x] = (lane == i) ? 1.f : 0.f;
         } else {
-            const float4 e4 = __ldg(reinterpret_cast<const float4*>(d.en + row_i * (2 * kHid)) + lane);
+            // training mode: the PWF output maps were computed with per-pair batch statistics (fusion_train.cu)
+            const bool pre = d.wpre != nullptr;
+            const float4 e4 = pre ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                  : __ldg(reinterpret_cast<const float4*>(d.en + row_i * (2 * kHid)) + lane);
             const int yf = h - 1 - y;  // row in the H-flipped frame the reference warps in
             const float xb = (2.f * x + 1.f) / w - 1.f;
             const float yb = (2.f * yf + 1.f) / h - 1.f;
@@ -121,8 +126,10 @@ __global__ void __launch_bounds__(kWarps * 32, 3) fusion_kernel(const disco_fusi
                 float nn[4] = {0.f, 0.f, 0.f, 0.f};
                 if (j == i) {
                     load_feat<CPL>(feat + row_i * C + lane * cpl, d.feat_lo_off, d.precision, 1.f, nb);
-                    const float4 n4 = __ldg(reinterpret_cast<const float4*>(d.en + row_i * (2 * kHid) + kHid) + lane);
-                    nn[0] = n4.x; nn[1] = n4.y; nn[2] = n4.z; nn[3] = n4.w;
+                    if (!pre) {
+                        const float4 n4 = __ldg(reinterpret_cast<const float4*>(d.en + row_i * (2 * kHid) + kHid) + lane);
+                        nn[0] = n4.x; nn[1] = n4.y; nn[2] = n4.z; nn[3] = n4.w;
+                    }
                 } else {
                     const double* T = d.trans + (((long long)b * A + j) * A + i) * 16;
                     const float m00 = (float)T[0], m01 = (float)T[1], m02 = (-(float)T[3]) * d.trans_scale;
@@ -143,12 +150,17 @@ __global__ void __launch_bounds__(kWarps * 32, 3) fusion_kernel(const disco_fusi
                         if (xs < 0 || xs >= w || ysf < 0 || ysf >= h) continue;  // zeros padding
                         const long long row_j = (((long long)(j * B + b) * h + (h - 1 - ysf)) * w + xs);
                         load_feat<CPL>(feat + row_j * C + lane * cpl, d.feat_lo_off, d.precision, tw[tp], nb);
+                        if (pre) continue;
                         const float4 n4 =
                             __ldg(reinterpret_cast<const float4*>(d.en + row_j * (2 * kHid) + kHid) + lane);
                         nn[0] = fmaf(tw[tp], n4.x, nn[0]); nn[1] = fmaf(tw[tp], n4.y, nn[1]);
                         nn[2] = fmaf(tw[tp], n4.z, nn[2]); nn[3] = fmaf(tw[tp], n4.w, nn[3]);
                     }
                 }
+                float wk;
+                if (pre) {
+                    wk = __ldg(d.wpre + ((((long long)b * A + i) * A + j) * h + y) * w + x);
+                } else {
                 // ---- PWF tail: 128 -> 32 -> 8 -> 1 ------------------------------------------------
                 float4 h1;
                 h1.x = fmaxf(e4.x + nn[0], 0.f); h1.y = fmaxf(e4.y + nn[1], 0.f);
@@ -166,7 +178,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) fusion_kernel(const disco_fusi
                     h2 = fmaf(s_w2[lane][c + 3], hv.w, h2);
                 }
                 h2 = fmaxf(h2, 0.f);
-                float wk = s_b4;
+                wk = s_b4;
 #pragma unroll
                 for (int q = 0; q < kH3; ++q) {
                     float part = s_w3[q][lane] * h2;
@@ -175,6 +187,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) fusion_kernel(const disco_fusi
                     wk = fmaf(s_w4[q], fmaxf(part + s_b3[q], 0.f), wk);
                 }
                 wk = fmaxf(wk, 0.f);
+                }
                 const float ek = expf(wk);
                 esum += ek;
 #pragma unroll
@@ -227,8 +240,8 @@ __global__ void __launch_bounds__(kWarps * 32, 3) fusion_kernel(const disco_fusi
 }  // namespace
 
 int disco_fusion_launch(const disco_fusion_desc* d, void* stream) {
-    DISCO_REQUIRE(d->feat_hi && d->en && d->out_hi && d->trans && d->num_agent, "fusion: null tensor");
-    DISCO_REQUIRE(d->w2 && d->b2 && d->w3 && d->b3 && d->w4 && d->b4, "fusion: null PWF weights");
+    DISCO_REQUIRE(d->feat_hi && d->out_hi && d->trans && d->num_agent, "fusion: null tensor");
+    DISCO_REQUIRE(d->wpre || (d->en && d->w2 && d->b2 && d->w3 && d->b3 && d->w4 && d->b4), "fusion: null PWF weights");
     DISCO_REQUIRE(d->hid == kHid, "fusion: PWF hidden width must be %d (got %d)", kHid, d->hid);
     DISCO_REQUIRE(d->C == 128 || d->C == 256 || d->C == 512, "fusion: C must be 128, 256 or 512 (got %d)", d->C);
     DISCO_REQUIRE(d->A >= 1 && d->A <= 32 && d->B >= 1 && d->h > 0 && d->w > 0, "fusion: bad scene shape");

@@ -1,0 +1,632 @@
+// DiscoGraph fusion block in TRAINING mode: PixelWeightedFusionSoftmax with per-call batch statistics, and the
+// backward of the whole block.
+//
+// Reference semantics (DiscoNet.py:59-113,132-155 in train() mode): the PWF MLP is called once per (scene b, ego i,
+// k-th neighbour) on a [1, 2C, h, w] tensor, so each of its three BatchNorms normalises with the statistics of
+// THAT call's h*w pixels and updates its running statistics once per call, sequentially in (b, i, k) order.
+//
+//   pwf_train_fwd_kernel   one CTA per pair (b, i, j): four passes over the pair's pixels (each recomputing the
+//                          cheap chain from the tensor-core product `en`): stats of layer 1 -> 2 -> 3 -> output map
+//   pwf_running_kernel     sequential EMA of the per-pair statistics in the reference's call order
+//   (softmax over k + weighted sum: the eval fusion kernel reading the precomputed maps, fusion.cu `wpre`)
+//   fusion_combine_bwd     one warp per (ego, cell): softmax / weighted-sum backward, bilinear-warp transpose
+//                          (scatter-add into the feature gradient), gradient wrt the PWF output maps
+//   pwf_train_bwd_kernel   one CTA per pair: BatchNorm(train) backward needs per-pair sums of each layer's
+//                          gradient, hence four recompute passes (3 -> 2 -> 1 -> input); weight gradients of the
+//                          128->32->8->1 tail accumulate in registers / shared memory, then one atomic per CTA;
+//                          the gradient wrt `en` (ego half direct, neighbour half through the warp transpose) goes
+//                          back to the tensor cores (conv1_1 data + weight gradient).
+// As in the eval kernel the conv1_1 neighbour half commutes with the bilinear warp and the H flips are folded
+// into the row index.
+#include "common.cuh"
+#include "conv.h"
+#include "train.h"
+
+namespace {
+
+constexpr int kHid = 128, kH2 = 32, kH3 = 8;
+constexpr int kStatC = kHid + kH2 + kH3;   // 168 BatchNorm channels per pair
+// dparams layout
+constexpr int kDG1 = 0, kDBE1 = 128, kDW2 = 256, kDG2 = 4352, kDBE2 = 4384, kDW3 = 4416, kDG3 = 4672, kDBE3 = 4680,
+              kDW4 = 4688, kDB4 = 4696, kDParams = 4697;
+
+struct Taps {
+    int n;
+    long long row[4];
+    float w[4];
+};
+
+// Sampling taps of neighbour j's map for ego i at output cell (y, x) (unflipped frame); j == i: the cell itself.
+__device__ __forceinline__ Taps pair_taps(const disco_pwf_train_desc& d, int b, int i, int j, int y, int x) {
+    Taps t;
+    const int h = d.h, w = d.w, B = d.B, A = d.A;
+    if (j == i) {
+        t.n = 1;
+        t.row[0] = ((long long)(i * B + b) * h + y) * w + x;
+        t.w[0] = 1.f;
+        return t;
+    }
+    const int yf = h - 1 - y;
+    const float xb = (2.f * x + 1.f) / w - 1.f;
+    const float yb = (2.f * yf + 1.f) / h - 1.f;
+    const double* T = d.trans + (((long long)b * A + j) * A + i) * 16;
+    const float m00 = (float)T[0], m01 = (float)T[1], m02 = (-(float)T[3]) * d.trans_scale;
+    const float m10 = (float)T[4], m11 = (float)T[5], m12 = (-(float)T[7]) * d.trans_scale;
+    const float gx = m00 * xb + m01 * yb + m02;
+    const float gy = m10 * xb + m11 * yb + m12;
+    const float ix = ((gx + 1.f) * w - 1.f) * 0.5f;
+    const float iy = ((gy + 1.f) * h - 1.f) * 0.5f;
+    const float fx = floorf(ix), fy = floorf(iy);
+    const float ax = ix - fx, ay = iy - fy;
+    const bool finite = (fabsf(ix) < 1e6f) && (fabsf(iy) < 1e6f);
+    const int x0 = finite ? (int)fx : -10, y0 = finite ? (int)fy : -10;
+    const float tw[4] = {(1.f - ax) * (1.f - ay), ax * (1.f - ay), (1.f - ax) * ay, ax * ay};
+    t.n = 0;
+#pragma unroll
+    for (int tp = 0; tp < 4; ++tp) {
+        const int xs = x0 + (tp & 1), ysf = y0 + (tp >> 1);
+        if (xs < 0 || xs >= w || ysf < 0 || ysf >= h) continue;   // zeros padding
+        t.row[t.n] = ((long long)(j * B + b) * h + (h - 1 - ysf)) * w + xs;
+        t.w[t.n] = tw[tp];
+        ++t.n;
+    }
+    return t;
+}
+
+__device__ __forceinline__ bool pair_used(const disco_pwf_train_desc& d, int b, int i, int j) {
+    const int n_ag = d.num_agent[b];
+    if (i >= n_ag || j >= n_ag) return false;
+    if (d.outage && d.outage[b * d.A + i]) return false;
+    if (j != i && d.only_v2i && i != 0 && j != 0) return false;
+    return true;
+}
+
+// z1 (pre-BN output of conv1_1 on cat[ego, warped neighbour]) for this lane's 4 channels 4*lane..4*lane+3
+__device__ __forceinline__ float4 pair_z1(const disco_pwf_train_desc& d, long long row_i, const Taps& t, int lane) {
+    float4 z = __ldg(reinterpret_cast<const float4*>(d.en + row_i * (2 * kHid)) + lane);
+    for (int k = 0; k < t.n; ++k) {
+        const float4 n4 = __ldg(reinterpret_cast<const float4*>(d.en + t.row[k] * (2 * kHid) + kHid) + lane);
+        z.x = fmaf(t.w[k], n4.x, z.x); z.y = fmaf(t.w[k], n4.y, z.y);
+        z.z = fmaf(t.w[k], n4.z, z.z); z.w = fmaf(t.w[k], n4.w, z.w);
+    }
+    return z;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kFwdWarps = 16;
+
+struct FwdSmem {
+    float w2[kH2][kHid + 1];
+    float w3[kH3][kH2];
+    float b2[kH2], b3[kH3], w4[kH3], b4;
+    float gam[kStatC], bet[kStatC];       // BN gamma/beta of the three layers, concatenated 128 | 32 | 8
+    float mu[kStatC], rs[kStatC];         // per-pair batch mean / rstd
+    float h1[kFwdWarps][kHid];
+    float red[kFwdWarps][2 * kHid];       // cross-warp reduction scratch (sum | sum of squares)
+};
+
+// reduce per-warp partial sums of `nch` channels starting at stat channel `c_base`; writes mu/rs + pstats
+__device__ void fwd_finish_stats(FwdSmem& s, const disco_pwf_train_desc& d, float* pst, int c_base, int nch, int M) {
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t < nch) {
+        double a = 0.0, b = 0.0;
+        for (int wp = 0; wp < kFwdWarps; ++wp) {
+            a += (double)s.red[wp][t];
+            b += (double)s.red[wp][kHid + t];
+        }
+        const double mean = a / M;
+        double var = b / M - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)d.eps));
+        s.mu[c_base + t] = (float)mean;
+        s.rs[c_base + t] = rstd;
+        pst[c_base + t] = (float)mean;
+        pst[kStatC + c_base + t] = rstd;
+        pst[2 * kStatC + c_base + t] = (float)var;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kFwdWarps * 32) pwf_train_fwd_kernel(const disco_pwf_train_desc d) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    FwdSmem& s = *reinterpret_cast<FwdSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int A = d.A, h = d.h, w = d.w, HW = h * w;
+    const int pair = blockIdx.x;
+    const int j = pair % A, i = (pair / A) % A, b = pair / (A * A);
+    float* wl = d.wlogit + (long long)pair * HW;
+    if (!pair_used(d, b, i, j)) {
+        for (int p = tid; p < HW; p += blockDim.x) wl[p] = 0.f;
+        return;
+    }
+    for (int e = tid; e < kH2 * kHid; e += blockDim.x) s.w2[e / kHid][e % kHid] = d.w2[e];
+    for (int e = tid; e < kH3 * kH2; e += blockDim.x) s.w3[e / kH2][e % kH2] = d.w3[e];
+    if (tid < kH2) s.b2[tid] = d.b2[tid];
+    if (tid < kH3) { s.b3[tid] = d.b3[tid]; s.w4[tid] = d.w4[tid]; }
+    if (tid == 0) s.b4 = d.b4[0];
+    if (tid < kHid) { s.gam[tid] = d.g1[tid]; s.bet[tid] = d.be1[tid]; }
+    if (tid < kH2) { s.gam[kHid + tid] = d.g2[tid]; s.bet[kHid + tid] = d.be2[tid]; }
+    if (tid < kH3) { s.gam[kHid + kH2 + tid] = d.g3[tid]; s.bet[kHid + kH2 + tid] = d.be3[tid]; }
+    __syncthreads();
+    float* pst = d.pstats + (long long)pair * 3 * kStatC;
+    const int n_i = i * d.B + b;
+
+    for (int pass = 0; pass < 4; ++pass) {
+        float sa[8], sq[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { sa[q] = 0.f; sq[q] = 0.f; }
+        for (int p = warp; p < HW; p += kFwdWarps) {
+            const int y = p / w, x = p - y * w;
+            const long long row_i = ((long long)n_i * h + y) * w + x;
+            const Taps t = pair_taps(d, b, i, j, y, x);
+            const float4 z4 = pair_z1(d, row_i, t, lane);
+            const float z1[4] = {z4.x, z4.y, z4.z, z4.w};
+            if (pass == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { sa[q] += z1[q]; sq[q] = fmaf(z1[q], z1[q], sq[q]); }
+                continue;
+            }
+            float a1[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = 4 * lane + q;
+                a1[q] = fmaxf(fmaf((z1[q] - s.mu[c]) * s.rs[c], s.gam[c], s.bet[c]), 0.f);
+            }
+            __syncwarp();
+            reinterpret_cast<float4*>(s.h1[warp])[lane] = make_float4(a1[0], a1[1], a1[2], a1[3]);
+            __syncwarp();
+            float z2 = s.b2[lane];
+#pragma unroll 8
+            for (int c = 0; c < kHid; c += 4) {
+                const float4 hv = *reinterpret_cast<const float4*>(&s.h1[warp][c]);
+                z2 = fmaf(s.w2[lane][c], hv.x, z2);
+                z2 = fmaf(s.w2[lane][c + 1], hv.y, z2);
+                z2 = fmaf(s.w2[lane][c + 2], hv.z, z2);
+                z2 = fmaf(s.w2[lane][c + 3], hv.w, z2);
+            }
+            if (pass == 1) {
+                sa[0] += z2; sq[0] = fmaf(z2, z2, sq[0]);
+                continue;
+            }
+            const int c2 = kHid + lane;
+            const float a2 = fmaxf(fmaf((z2 - s.mu[c2]) * s.rs[c2], s.gam[c2], s.bet[c2]), 0.f);
+            float z3[kH3];
+#pragma unroll
+            for (int q = 0; q < kH3; ++q) z3[q] = warp_sum(s.w3[q][lane] * a2) + s.b3[q];
+            if (pass == 2) {
+#pragma unroll
+                for (int q = 0; q < kH3; ++q) { sa[q] += z3[q]; sq[q] = fmaf(z3[q], z3[q], sq[q]); }
+                continue;
+            }
+            float z4o = s.b4;
+#pragma unroll
+            for (int q = 0; q < kH3; ++q) {
+                const int c3 = kHid + kH2 + q;
+                z4o = fmaf(s.w4[q], fmaxf(fmaf((z3[q] - s.mu[c3]) * s.rs[c3], s.gam[c3], s.bet[c3]), 0.f), z4o);
+            }
+            if (lane == 0) wl[p] = fmaxf(z4o, 0.f);
+        }
+        if (pass == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { s.red[warp][4 * lane + q] = sa[q]; s.red[warp][kHid + 4 * lane + q] = sq[q]; }
+            fwd_finish_stats(s, d, pst, 0, kHid, HW);
+        } else if (pass == 1) {
+            s.red[warp][lane] = sa[0]; s.red[warp][kHid + lane] = sq[0];
+            fwd_finish_stats(s, d, pst, kHid, kH2, HW);
+        } else if (pass == 2) {
+            if (lane < kH3) {
+                float va = 0.f, vq = 0.f;
+#pragma unroll
+                for (int q = 0; q < kH3; ++q) if (lane == q) { va = sa[q]; vq = sq[q]; }
+                s.red[warp][lane] = va; s.red[warp][kHid + lane] = vq;
+            }
+            fwd_finish_stats(s, d, pst, kHid + kH2, kH3, HW);
+        }
+    }
+}
+
+// Sequential running-statistics update in the reference's call order (b, ego i, neighbour list [i, j != i ...])
+__global__ void pwf_running_kernel(const disco_pwf_train_desc d) {
+    const int c = threadIdx.x;
+    if (c >= kStatC) return;
+    float* rm; float* rv;
+    int cl;
+    if (c < kHid) { rm = d.rm1; rv = d.rv1; cl = c; }
+    else if (c < kHid + kH2) { rm = d.rm2; rv = d.rv2; cl = c - kHid; }
+    else { rm = d.rm3; rv = d.rv3; cl = c - kHid - kH2; }
+    const int A = d.A, HW = d.h * d.w;
+    const float unb = HW > 1 ? (float)HW / (float)(HW - 1) : 1.f;
+    float m = rm[cl], v = rv[cl];
+    long long calls = 0;
+    for (int b = 0; b < d.B; ++b)
+        for (int i = 0; i < A; ++i)
+            for (int k = 0; k < A; ++k) {
+                const int j = (k == 0) ? i : ((k - 1 < i) ? k - 1 : k);
+                if (!pair_used(d, b, i, j)) continue;
+                const float* pst = d.pstats + ((long long)(b * A + i) * A + j) * 3 * kStatC;
+                m = (1.f - d.momentum) * m + d.momentum * pst[c];
+                v = (1.f - d.momentum) * v + d.momentum * pst[2 * kStatC + c] * unb;
+                ++calls;
+            }
+    rm[cl] = m;
+    rv[cl] = v;
+    if (c == 0) { *d.nbt1 += calls; *d.nbt2 += calls; *d.nbt3 += calls; }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward of softmax-over-agents + weighted sum + warp (one warp per (ego row, cell))
+// ------------------------------------------------------------------------------------------------------------
+template <int CPL>
+__device__ __forceinline__ void load_feat_f32(const uint16_t* p, long long lo_off, float (&v)[CPL]) {
+#pragma unroll
+    for (int u = 0; u < CPL / 4; ++u) {
+        const uint2 hh = __ldg(reinterpret_cast<const uint2*>(p) + u);
+        const uint2 ll = __ldg(reinterpret_cast<const uint2*>(p + lo_off) + u);
+        v[4 * u] = __uint_as_float(hh.x << 16) + __uint_as_float(ll.x << 16);
+        v[4 * u + 1] = __uint_as_float(hh.x & 0xffff0000u) + __uint_as_float(ll.x & 0xffff0000u);
+        v[4 * u + 2] = __uint_as_float(hh.y << 16) + __uint_as_float(ll.y << 16);
+        v[4 * u + 3] = __uint_as_float(hh.y & 0xffff0000u) + __uint_as_float(ll.y & 0xffff0000u);
+    }
+}
+
+template <int CPL>
+__device__ __forceinline__ void atomic_axpy(float* dst, float a, const float (&g)[CPL]) {
+#pragma unroll
+    for (int u = 0; u < CPL / 4; ++u)
+        atomicAdd(reinterpret_cast<float4*>(dst) + u, make_float4(a * g[4 * u], a * g[4 * u + 1], a * g[4 * u + 2], a * g[4 * u + 3]));
+}
+
+constexpr int kCombWarps = 8;
+
+template <int CPL>
+__global__ void __launch_bounds__(kCombWarps * 32) fusion_combine_bwd_kernel(const disco_pwf_train_desc d) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int C = d.C, h = d.h, w = d.w, A = d.A, B = d.B, HW = h * w;
+    const long long cell = (long long)blockIdx.x * kCombWarps + warp;
+    if (cell >= (long long)A * B * HW) return;
+    const int x = (int)(cell % w), y = (int)((cell / w) % h);
+    const int n_i = (int)(cell / HW);
+    const int i = n_i / B, b = n_i - i * B;
+    const int n_ag = d.num_agent[b];
+    const long long row_i = ((long long)n_i * h + y) * w + x;
+    const uint16_t* feat = reinterpret_cast<const uint16_t*>(d.feat_hi);
+    float g[CPL];
+    {
+        const float4* gp = reinterpret_cast<const float4*>(d.dfused + row_i * C + lane * CPL);
+#pragma unroll
+        for (int u = 0; u < CPL / 4; ++u) {
+            const float4 v = __ldg(gp + u);
+            g[4 * u] = v.x; g[4 * u + 1] = v.y; g[4 * u + 2] = v.z; g[4 * u + 3] = v.w;
+        }
+    }
+    const bool passthrough = (i >= n_ag) || (d.outage && d.outage[b * A + i]);
+    if (passthrough) {
+        atomic_axpy<CPL>(d.dfeat + row_i * C + lane * CPL, 1.f, g);
+        if (lane < A) d.dwlogit[(((long long)b * A + i) * A + lane) * HW + y * w + x] = 0.f;
+        return;
+    }
+    // pass 1: e_k = exp(w_k), dot_k = <dfused, nb_k>; lane j keeps the values of neighbour id j
+    float my_e = 0.f, my_dot = 0.f, my_wl = 0.f;
+    float esum = 0.f;
+    for (int j = 0; j < A; ++j) {
+        if (!pair_used(d, b, i, j)) continue;
+        const Taps t = pair_taps(d, b, i, j, y, x);
+        float dot = 0.f;
+        for (int k = 0; k < t.n; ++k) {
+            float nb[CPL];
+            load_feat_f32<CPL>(feat + t.row[k] * C + lane * CPL, d.feat_lo_off, nb);
+            float part = 0.f;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) part = fmaf(nb[c], g[c], part);
+            dot = fmaf(t.w[k], part, dot);
+        }
+        dot = warp_sum(dot);
+        const float wl = d.wlogit[(((long long)b * A + i) * A + j) * HW + y * w + x];
+        const float e = expf(wl);
+        esum += e;
+        if (lane == j) { my_e = e; my_dot = dot; my_wl = wl; }
+    }
+    const float inv = 1.f / esum;
+    const float my_a = my_e * inv;                       // softmax weight of neighbour id `lane` (0 if unused)
+    const float S = warp_sum(my_a * my_dot);
+    if (lane < A) {
+        // d/dw_k of sum_m a_m nb_m = a_k (dot_k - S); the PWF output ReLU gate is applied here
+        const float dl = (my_wl > 0.f) ? my_a * (my_dot - S) : 0.f;
+        d.dwlogit[(((long long)b * A + i) * A + lane) * HW + y * w + x] = dl;
+    }
+    // pass 2: d nb_k = a_k * dfused, scattered through the transpose of the bilinear warp
+    for (int j = 0; j < A; ++j) {
+        const float a = __shfl_sync(0xffffffffu, my_a, j);
+        if (!pair_used(d, b, i, j)) continue;
+        const Taps t = pair_taps(d, b, i, j, y, x);
+        for (int k = 0; k < t.n; ++k) atomic_axpy<CPL>(d.dfeat + t.row[k] * C + lane * CPL, a * t.w[k], g);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// PWF backward (one CTA per pair, 8 warps)
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kBwdWarps = 8;
+
+struct BwdSmem {
+    float w2[kH2][kHid + 1];
+    float w3[kH3][kH2];
+    float b2[kH2], b3[kH3], w4[kH3], b4;
+    float gam[kStatC], bet[kStatC], mu[kStatC], rs[kStatC];
+    float mg[kStatC], mgx[kStatC];        // per-pair mean(g), mean(g * xhat) of each BN layer (filled pass by pass)
+    float h1[kBwdWarps][kHid];            // a1
+    float xh1[kBwdWarps][kHid];           // xhat1
+    float dz1[kBwdWarps][kHid];
+    float dz2[kBwdWarps][kH2];
+    float red[kBwdWarps][2 * kHid];       // cross-warp scratch: sum g | sum g*xhat
+    float dw2[kH2 * kHid];                // CTA accumulator of dW2
+    float dw3[kH3 * kH2];
+    float dw4[kH3 + 1];                   // dW4[8], db4
+};
+
+// cross-warp reduce of red[][0..nch) / red[][128..128+nch) -> mg/mgx (means) and global dgamma/dbeta accumulation
+__device__ void bwd_finish_sums(BwdSmem& s, const disco_pwf_train_desc& d, int c_base, int nch, int M, int off_g, int off_b) {
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t < nch) {
+        float a = 0.f, bx = 0.f;
+        for (int wp = 0; wp < kBwdWarps; ++wp) { a += s.red[wp][t]; bx += s.red[wp][kHid + t]; }
+        s.mg[c_base + t] = a / M;
+        s.mgx[c_base + t] = bx / M;
+        atomicAdd(d.dparams + off_b + t, a);     // dbeta = sum g
+        atomicAdd(d.dparams + off_g + t, bx);    // dgamma = sum g * xhat
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kBwdWarps * 32, 1) pwf_train_bwd_kernel(const disco_pwf_train_desc d) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    BwdSmem& s = *reinterpret_cast<BwdSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int A = d.A, h = d.h, w = d.w, HW = h * w;
+    const int pair = blockIdx.x;
+    const int j = pair % A, i = (pair / A) % A, b = pair / (A * A);
+    if (!pair_used(d, b, i, j)) return;
+    const float* pst = d.pstats + (long long)pair * 3 * kStatC;
+    for (int e = tid; e < kH2 * kHid; e += blockDim.x) { s.w2[e / kHid][e % kHid] = d.w2[e]; s.dw2[e] = 0.f; }
+    for (int e = tid; e < kH3 * kH2; e += blockDim.x) { s.w3[e / kH2][e % kH2] = d.w3[e]; s.dw3[e] = 0.f; }
+    if (tid < kH2) s.b2[tid] = d.b2[tid];
+    if (tid < kH3) { s.b3[tid] = d.b3[tid]; s.w4[tid] = d.w4[tid]; }
+    if (tid <= kH3) s.dw4[tid] = 0.f;
+    if (tid == 0) s.b4 = d.b4[0];
+    if (tid < kHid) { s.gam[tid] = d.g1[tid]; s.bet[tid] = d.be1[tid]; }
+    if (tid < kH2) { s.gam[kHid + tid] = d.g2[tid]; s.bet[kHid + tid] = d.be2[tid]; }
+    if (tid < kH3) { s.gam[kHid + kH2 + tid] = d.g3[tid]; s.bet[kHid + kH2 + tid] = d.be3[tid]; }
+    if (tid < kStatC) { s.mu[tid] = pst[tid]; s.rs[tid] = pst[kStatC + tid]; }
+    __syncthreads();
+    const int n_i = i * d.B + b;
+    const float* dwl = d.dwlogit + (long long)pair * HW;
+    const float invM = 1.f / HW;
+    (void)invM;
+
+    for (int pass = 0; pass < 4; ++pass) {
+        // per-lane accumulators of this pass
+        float s_g[8], s_gx[8];          // pass 0: layer 3 (8 ch, uniform); pass 1: [0] layer 2 (ch = lane); pass 2: [0..3] layer 1 (ch = lane + 32q)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { s_g[q] = 0.f; s_gx[q] = 0.f; }
+        float acc_w4[kH3 + 1];          // pass 0: dW4, db4
+#pragma unroll
+        for (int q = 0; q <= kH3; ++q) acc_w4[q] = 0.f;
+        float acc_w3[kH3];              // pass 1: dW3[q][lane]
+#pragma unroll
+        for (int q = 0; q < kH3; ++q) acc_w3[q] = 0.f;
+        float acc_w2[kH2][4];           // pass 2: dW2[o][lane + 32 q]
+        if (pass == 2) {
+#pragma unroll
+            for (int o = 0; o < kH2; ++o)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc_w2[o][q] = 0.f;
+        }
+
+        for (int p = warp; p < HW; p += kBwdWarps) {
+            const int y = p / w, x = p - y * w;
+            const long long row_i = ((long long)n_i * h + y) * w + x;
+            const Taps t = pair_taps(d, b, i, j, y, x);
+            // ---- forward recompute ----------------------------------------------------------------
+            const float4 z4v = pair_z1(d, row_i, t, lane);
+            const float z1[4] = {z4v.x, z4v.y, z4v.z, z4v.w};
+            float a1[4], xh1[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = 4 * lane + q;
+                xh1[q] = (z1[q] - s.mu[c]) * s.rs[c];
+                a1[q] = fmaxf(fmaf(xh1[q], s.gam[c], s.bet[c]), 0.f);
+            }
+            __syncwarp();
+            reinterpret_cast<float4*>(s.h1[warp])[lane] = make_float4(a1[0], a1[1], a1[2], a1[3]);
+            reinterpret_cast<float4*>(s.xh1[warp])[lane] = make_float4(xh1[0], xh1[1], xh1[2], xh1[3]);
+            __syncwarp();
+            float z2 = s.b2[lane];
+#pragma unroll 8
+            for (int c = 0; c < kHid; c += 4) {
+                const float4 hv = *reinterpret_cast<const float4*>(&s.h1[warp][c]);
+                z2 = fmaf(s.w2[lane][c], hv.x, z2);
+                z2 = fmaf(s.w2[lane][c + 1], hv.y, z2);
+                z2 = fmaf(s.w2[lane][c + 2], hv.z, z2);
+                z2 = fmaf(s.w2[lane][c + 3], hv.w, z2);
+            }
+            const int c2 = kHid + lane;
+            const float xh2 = (z2 - s.mu[c2]) * s.rs[c2];
+            const float y2 = fmaf(xh2, s.gam[c2], s.bet[c2]);
+            const float a2 = fmaxf(y2, 0.f);
+            float xh3[kH3], a3[kH3];
+            bool on3[kH3];
+            float z4o = s.b4;
+#pragma unroll
+            for (int q = 0; q < kH3; ++q) {
+                const int c3 = kHid + kH2 + q;
+                const float z3 = warp_sum(s.w3[q][lane] * a2) + s.b3[q];
+                xh3[q] = (z3 - s.mu[c3]) * s.rs[c3];
+                const float y3 = fmaf(xh3[q], s.gam[c3], s.bet[c3]);
+                on3[q] = y3 > 0.f;
+                a3[q] = fmaxf(y3, 0.f);
+                z4o = fmaf(s.w4[q], a3[q], z4o);
+            }
+            // ---- backward chain -------------------------------------------------------------------
+            const float dz4 = (z4o > 0.f) ? __ldg(dwl + p) : 0.f;
+            float g3[kH3];
+#pragma unroll
+            for (int q = 0; q < kH3; ++q) g3[q] = on3[q] ? s.w4[q] * dz4 : 0.f;
+            if (pass == 0) {
+#pragma unroll
+                for (int q = 0; q < kH3; ++q) {
+                    acc_w4[q] = fmaf(dz4, a3[q], acc_w4[q]);
+                    s_g[q] += g3[q];
+                    s_gx[q] = fmaf(g3[q], xh3[q], s_gx[q]);
+                }
+                acc_w4[kH3] += dz4;
+                continue;
+            }
+            float da2 = 0.f;
+#pragma unroll
+            for (int q = 0; q < kH3; ++q) {
+                const int c3 = kHid + kH2 + q;
+                const float dz3 = s.gam[c3] * s.rs[c3] * (g3[q] - s.mg[c3] - xh3[q] * s.mgx[c3]);
+                if (pass == 1) acc_w3[q] = fmaf(dz3, a2, acc_w3[q]);
+                da2 = fmaf(s.w3[q][lane], dz3, da2);
+            }
+            const float g2 = (y2 > 0.f) ? da2 : 0.f;
+            if (pass == 1) {
+                s_g[0] += g2;
+                s_gx[0] = fmaf(g2, xh2, s_gx[0]);
+                continue;
+            }
+            const float dz2 = s.gam[c2] * s.rs[c2] * (g2 - s.mg[c2] - xh2 * s.mgx[c2]);
+            __syncwarp();
+            s.dz2[warp][lane] = dz2;
+            __syncwarp();
+            // channels of layer 1 owned in this part: c = lane + 32 q  (conflict-free reads of w2 rows / h1 / xh1)
+            float a1c[4], xh1c[4], da1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { a1c[q] = s.h1[warp][lane + 32 * q]; xh1c[q] = s.xh1[warp][lane + 32 * q]; }
+#pragma unroll
+            for (int o = 0; o < kH2; ++o) {
+                const float dzo = s.dz2[warp][o];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (pass == 2) acc_w2[o][q] = fmaf(dzo, a1c[q], acc_w2[o][q]);
+                    da1[q] = fmaf(s.w2[o][lane + 32 * q], dzo, da1[q]);
+                }
+            }
+            float g1[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) g1[q] = (a1c[q] > 0.f) ? da1[q] : 0.f;
+            if (pass == 2) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { s_g[q] += g1[q]; s_gx[q] = fmaf(g1[q], xh1c[q], s_gx[q]); }
+                continue;
+            }
+            // pass 3: dz1 -> gradient wrt en (ego half direct, neighbour half through the warp transpose)
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = lane + 32 * q;
+                s.dz1[warp][c] = s.gam[c] * s.rs[c] * (g1[q] - s.mg[c] - xh1c[q] * s.mgx[c]);
+            }
+            __syncwarp();
+            const float4 dz = reinterpret_cast<const float4*>(s.dz1[warp])[lane];
+            atomicAdd(reinterpret_cast<float4*>(d.den + row_i * (2 * kHid)) + lane, dz);
+            for (int k = 0; k < t.n; ++k)
+                atomicAdd(reinterpret_cast<float4*>(d.den + t.row[k] * (2 * kHid) + kHid) + lane,
+                          make_float4(t.w[k] * dz.x, t.w[k] * dz.y, t.w[k] * dz.z, t.w[k] * dz.w));
+        }
+        // ---- end of pass: cross-warp reductions ---------------------------------------------------
+        if (pass == 0) {
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < kH3; ++q) { s.red[warp][q] = s_g[q]; s.red[warp][kHid + q] = s_gx[q]; }
+#pragma unroll
+                for (int q = 0; q <= kH3; ++q) atomicAdd(&s.dw4[q], acc_w4[q]);
+            }
+            bwd_finish_sums(s, d, kHid + kH2, kH3, HW, kDG3, kDBE3);
+            if (tid <= kH3) atomicAdd(d.dparams + kDW4 + tid, s.dw4[tid]);   // dW4[0..7], db4
+        } else if (pass == 1) {
+            s.red[warp][lane] = s_g[0]; s.red[warp][kHid + lane] = s_gx[0];
+#pragma unroll
+            for (int q = 0; q < kH3; ++q) atomicAdd(&s.dw3[q * kH2 + lane], acc_w3[q]);
+            bwd_finish_sums(s, d, kHid, kH2, HW, kDG2, kDBE2);
+            for (int e = tid; e < kH3 * kH2; e += blockDim.x) atomicAdd(d.dparams + kDW3 + e, s.dw3[e]);
+        } else if (pass == 2) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { s.red[warp][lane + 32 * q] = s_g[q]; s.red[warp][kHid + lane + 32 * q] = s_gx[q]; }
+#pragma unroll
+            for (int o = 0; o < kH2; ++o)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) atomicAdd(&s.dw2[o * kHid + lane + 32 * q], acc_w2[o][q]);
+            bwd_finish_sums(s, d, 0, kHid, HW, kDG1, kDBE1);
+            for (int e = tid; e < kH2 * kHid; e += blockDim.x) atomicAdd(d.dparams + kDW2 + e, s.dw2[e]);
+        }
+    }
+}
+
+int check_desc(const disco_pwf_train_desc* d) {
+    DISCO_REQUIRE(d && d->en && d->trans && d->num_agent && d->pstats && d->wlogit, "pwf_train: null tensor");
+    DISCO_REQUIRE(d->g1 && d->be1 && d->w2 && d->b2 && d->g2 && d->be2 && d->w3 && d->b3 && d->g3 && d->be3 && d->w4 && d->b4,
+                  "pwf_train: null parameter");
+    DISCO_REQUIRE(d->hid == kHid, "pwf_train: hidden width must be %d", kHid);
+    DISCO_REQUIRE(d->A >= 1 && d->A <= 32 && d->B >= 1 && d->h > 0 && d->w > 0, "pwf_train: bad scene shape");
+    return DISCO_OK;
+}
+
+}  // namespace
+
+int disco_pwf_train_forward_launch(const disco_pwf_train_desc* d, void* stream) {
+    int rc = check_desc(d);
+    if (rc < 0) return rc;
+    DISCO_REQUIRE(d->rm1 && d->rv1 && d->rm2 && d->rv2 && d->rm3 && d->rv3 && d->nbt1 && d->nbt2 && d->nbt3,
+                  "pwf_train forward: null running statistics");
+    cudaStream_t s = (cudaStream_t)stream;
+    static bool attr = false;
+    if (!attr) {
+        DISCO_CHECK_CUDA(cudaFuncSetAttribute(pwf_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem)));
+        attr = true;
+    }
+    pwf_train_fwd_kernel<<<d->B * d->A * d->A, kFwdWarps * 32, sizeof(FwdSmem), s>>>(*d);
+    pwf_running_kernel<<<1, 192, 0, s>>>(*d);
+    DISCO_CHECK_CUDA(cudaGetLastError());
+    return DISCO_OK;
+}
+
+int disco_fusion_combine_backward_launch(const disco_pwf_train_desc* d, void* stream) {
+    int rc = check_desc(d);
+    if (rc < 0) return rc;
+    DISCO_REQUIRE(d->feat_hi && d->dfused && d->dwlogit && d->dfeat, "fusion backward: null tensor");
+    DISCO_REQUIRE(d->C == 128 || d->C == 256 || d->C == 512, "fusion backward: C must be 128, 256 or 512");
+    const long long cells = (long long)d->A * d->B * d->h * d->w;
+    const unsigned blocks = (unsigned)((cells + kCombWarps - 1) / kCombWarps);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (d->C == 128) fusion_combine_bwd_kernel<4><<<blocks, kCombWarps * 32, 0, s>>>(*d);
+    else if (d->C == 256) fusion_combine_bwd_kernel<8><<<blocks, kCombWarps * 32, 0, s>>>(*d);
+    else fusion_combine_bwd_kernel<16><<<blocks, kCombWarps * 32, 0, s>>>(*d);
+    DISCO_CHECK_CUDA(cudaGetLastError());
+    return DISCO_OK;
+}
+
+int disco_pwf_train_backward_launch(const disco_pwf_train_desc* d, void* stream) {
+    int rc = check_desc(d);
+    if (rc < 0) return rc;
+    DISCO_REQUIRE(d->dwlogit && d->den && d->dparams, "pwf_train backward: null tensor");
+    cudaStream_t s = (cudaStream_t)stream;
+    static bool attr = false;
+    if (!attr) {
+        DISCO_CHECK_CUDA(cudaFuncSetAttribute(pwf_train_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+        attr = true;
+    }
+    pwf_train_bwd_kernel<<<d->B * d->A * d->A, kBwdWarps * 32, sizeof(BwdSmem), s>>>(*d);
+    DISCO_CHECK_CUDA(cudaGetLastError());
+    return DISCO_OK;
+}

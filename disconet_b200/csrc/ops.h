@@ -32,6 +32,8 @@ struct disco_fusion_desc {
     int row_begin, row_end;
     const int* outage;         // optional [B, A] int32: 1 = communication outage for that ego (DetModelBase.py:129-137,
                                // DiscoNet.py:68-69): the ego keeps its own features
+    const float* wpre;         // optional [B, A(ego), A(neighbour id), h, w]: precomputed PWF output maps (training mode,
+                               // per-pair batch statistics -- fusion_train.cu); when set, en / w2..b4 are unused
 };
 
 int disco_fusion_launch(const disco_fusion_desc* d, void* stream);

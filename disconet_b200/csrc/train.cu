@@ -1,0 +1,345 @@
+// Training-mode BatchNorm (batch statistics) forward/backward and gradient re-packing kernels.
+//
+// Replaces, for the DiscoNet hot path in train() mode, the F.batch_norm + F.relu calls of Backbone.encode /
+// decode (Backbone.py:102-136,173-237), the heads (DetModelBase.py:283-351) and their autograd backward
+// (CoDetModule.py:289-291).  All kernels are HBM-bound streaming passes over fp32 NHWC conv outputs:
+//   forward  : stats (read z) + apply (read z, write hi/lo bf16)          = 12 B/element
+//   backward : reduce (read z, g) + apply (read z, g, write hi/lo bf16)   = 20 B/element
+// Per-channel sums are accumulated in fp32 per thread over <= ~150 pixels, then in double precision across
+// threads/blocks, so the batch variance E[z^2] - mean^2 does not lose bits to cancellation.
+#include "common.cuh"
+#include "train.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxC = 512;
+
+__device__ __forceinline__ float grad_src_load(const disco_grad_src& s, long long pix, int h, int w, int c) {
+    if (!s.pool) return __ldg(s.ptr + pix * s.c_total + s.c_off + c);
+    const int x = (int)(pix % w);
+    const int y = (int)((pix / w) % h);
+    const long long n = pix / ((long long)w * h);
+    const long long base = ((n * (2 * h) + 2 * y) * (2 * w) + 2 * x) * s.c_total + s.c_off + c;
+    const long long row = (long long)(2 * w) * s.c_total;
+    return __ldg(s.ptr + base) + __ldg(s.ptr + base + s.c_total) + __ldg(s.ptr + base + row) +
+           __ldg(s.ptr + base + row + s.c_total);
+}
+
+// Generic per-channel reduction skeleton: thread t owns channel(s) c = t % Cb (+ 256*k for C > 256) and pixel lane
+// t / Cb; consecutive threads read consecutive channels (coalesced).  MODE 0: sum z, z^2.  MODE 1: sum g, g*xhat.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const disco_bn_desc d, long long M) {
+    __shared__ float s_a[kThreads * 2], s_b[kThreads * 2];
+    const int C = d.c;
+    const int Cb = C < kThreads ? C : kThreads;
+    const int lanes = kThreads / Cb;              // pixel lanes per block
+    const int cpt = (C + kThreads - 1) / kThreads;  // channels per thread (1, or 2 for C = 512)
+    const int t = threadIdx.x;
+    const int lane = t / Cb, c0 = t - lane * Cb;
+    const bool active = lane < lanes;
+    float a[2] = {0.f, 0.f}, b[2] = {0.f, 0.f};
+    if (active) {
+        for (long long p = (long long)blockIdx.x * lanes + lane; p < M; p += (long long)gridDim.x * lanes) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (k >= cpt) break;
+                const int c = c0 + k * kThreads;
+                const float z = __ldg(d.z + p * C + c);
+                if (MODE == 0) {
+                    a[k] += z;
+                    b[k] = fmaf(z, z, b[k]);
+                } else {
+                    const float mean = d.stats[c], rstd = d.stats[C + c];
+                    const float xh = (z - mean) * rstd;
+                    float g = 0.f;
+                    for (int s = 0; s < d.n_g; ++s) g += grad_src_load(d.g[s], p, d.h, d.w, c);
+                    if (d.relu && fmaf(xh, d.gamma[c], d.beta[c]) <= 0.f) g = 0.f;
+                    a[k] += g;
+                    b[k] = fmaf(g, xh, b[k]);
+                }
+            }
+        }
+    }
+    for (int k = 0; k < cpt; ++k) {
+        s_a[k * kThreads + t] = a[k];
+        s_b[k * kThreads + t] = b[k];
+    }
+    __syncthreads();
+    if (t < Cb) {
+        for (int k = 0; k < cpt; ++k) {
+            double sa = 0.0, sb = 0.0;
+            for (int l = 0; l < lanes; ++l) {
+                sa += (double)s_a[k * kThreads + l * Cb + t];
+                sb += (double)s_b[k * kThreads + l * Cb + t];
+            }
+            atomicAdd(d.sums + t + k * kThreads, sa);
+            atomicAdd(d.sums + C + t + k * kThreads, sb);
+        }
+    }
+}
+
+__global__ void bn_finalize_kernel(const disco_bn_desc d, long long M) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < d.c) {
+        const double mean = d.sums[c] / (double)M;
+        double var = d.sums[d.c + c] / (double)M - mean * mean;
+        if (var < 0.0) var = 0.0;
+        d.stats[c] = (float)mean;
+        d.stats[d.c + c] = (float)(1.0 / sqrt(var + (double)d.eps));
+        if (d.running_mean) {
+            const double unb = M > 1 ? var * ((double)M / (double)(M - 1)) : var;
+            d.running_mean[c] = (float)((1.0 - d.momentum) * (double)d.running_mean[c] + d.momentum * mean);
+            d.running_var[c] = (float)((1.0 - d.momentum) * (double)d.running_var[c] + d.momentum * unb);
+        }
+    }
+    if (c == 0 && d.num_batches_tracked) *d.num_batches_tracked += 1;
+}
+
+__device__ __forceinline__ void store_act8(uint16_t* o, long long lo_off, const float* v) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint16_t h0, l0, h1, l1;
+        split_bf16(v[2 * q], h0, l0);
+        split_bf16(v[2 * q + 1], h1, l1);
+        hw[q] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+        lw[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+    }
+    *reinterpret_cast<uint4*>(o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(o + lo_off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+
+// y = relu(z * scale + shift), 8 channels per thread
+__global__ void __launch_bounds__(kThreads) bn_apply_kernel(const disco_bn_desc d, long long M) {
+    __shared__ float s_scale[kMaxC], s_shift[kMaxC];
+    const int C = d.c;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float sc = d.gamma[c] * d.stats[C + c];
+        s_scale[c] = sc;
+        s_shift[c] = d.beta[c] - d.stats[c] * sc;
+    }
+    __syncthreads();
+    const int groups = C >> 3;
+    const long long total = M * groups;
+    uint16_t* out = reinterpret_cast<uint16_t*>(d.out_hi);
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long p = e / groups;
+        const int c = (int)(e - p * groups) * 8;
+        const float4 z0 = __ldg(reinterpret_cast<const float4*>(d.z + p * C + c));
+        const float4 z1 = __ldg(reinterpret_cast<const float4*>(d.z + p * C + c + 4));
+        const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float y = fmaf(zz[i], s_scale[c + i], s_shift[c + i]);
+            v[i] = d.relu ? fmaxf(y, 0.f) : y;
+        }
+        store_act8(out + p * C + c, d.out_lo_off, v);
+    }
+}
+
+// dz = gamma*rstd * (g - mean(g) - xhat*mean(g*xhat)), 8 channels per thread; block 0 also writes dgamma/dbeta
+__global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const disco_bn_desc d, long long M) {
+    __shared__ float s_mean[kMaxC], s_rstd[kMaxC], s_gam[kMaxC], s_bet[kMaxC], s_mg[kMaxC], s_mgx[kMaxC];
+    const int C = d.c;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        s_mean[c] = d.stats[c];
+        s_rstd[c] = d.stats[C + c];
+        s_gam[c] = d.gamma[c];
+        s_bet[c] = d.beta[c];
+        s_mg[c] = (float)(d.sums[c] / (double)M);
+        s_mgx[c] = (float)(d.sums[C + c] / (double)M);
+        if (blockIdx.x == 0) {
+            if (d.dbeta) d.dbeta[c] = (float)d.sums[c];
+            if (d.dgamma) d.dgamma[c] = (float)d.sums[C + c];
+        }
+    }
+    __syncthreads();
+    const int groups = C >> 3;
+    const long long total = M * groups;
+    uint16_t* out = reinterpret_cast<uint16_t*>(d.dz_hi);
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long p = e / groups;
+        const int c = (int)(e - p * groups) * 8;
+        const float4 z0 = __ldg(reinterpret_cast<const float4*>(d.z + p * C + c));
+        const float4 z1 = __ldg(reinterpret_cast<const float4*>(d.z + p * C + c + 4));
+        const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+        float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int s = 0; s < d.n_g; ++s) {
+            const disco_grad_src& gs = d.g[s];
+            if (!gs.pool) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(gs.ptr + p * gs.c_total + gs.c_off + c));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(gs.ptr + p * gs.c_total + gs.c_off + c + 4));
+                g[0] += a.x; g[1] += a.y; g[2] += a.z; g[3] += a.w;
+                g[4] += b.x; g[5] += b.y; g[6] += b.z; g[7] += b.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g[i] += grad_src_load(gs, p, d.h, d.w, c + i);
+            }
+        }
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float xh = (zz[i] - s_mean[c + i]) * s_rstd[c + i];
+            float gi = g[i];
+            if (d.relu && fmaf(xh, s_gam[c + i], s_bet[c + i]) <= 0.f) gi = 0.f;
+            v[i] = s_gam[c + i] * s_rstd[c + i] * (gi - s_mg[c + i] - xh * s_mgx[c + i]);
+        }
+        store_act8(out + p * C + c, d.dz_lo_off, v);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) grad_pack_kernel(const float* a, int ca, const float* b, int cb, long long M,
+                                                             uint16_t* out, long long lo_off) {
+    const int C = ca + cb;
+    const int groups = C >> 2;   // 4 channels per thread (ca, cb multiples of 4)
+    const long long total = M * groups;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long p = e / groups;
+        const int c = (int)(e - p * groups) * 4;
+        const float4 v = (c < ca) ? __ldg(reinterpret_cast<const float4*>(a + p * ca + c))
+                                  : __ldg(reinterpret_cast<const float4*>(b + p * cb + (c - ca)));
+        uint16_t h[4], l[4];
+        split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]);
+        split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+        uint16_t* o = out + p * C + c;
+        *reinterpret_cast<uint2*>(o) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+        *reinterpret_cast<uint2*>(o + lo_off) = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) channel_sum_kernel(const float* src, long long M, int C, double* sums) {
+    __shared__ float s_a[kThreads];
+    const int lanes = kThreads / C;   // C <= 256
+    const int t = threadIdx.x;
+    const int lane = t / C, c = t - lane * C;
+    float a = 0.f;
+    if (lane < lanes)
+        for (long long p = (long long)blockIdx.x * lanes + lane; p < M; p += (long long)gridDim.x * lanes)
+            a += __ldg(src + p * C + c);
+    s_a[t] = a;
+    __syncthreads();
+    if (t < C) {
+        double sa = 0.0;
+        for (int l = 0; l < lanes; ++l) sa += (double)s_a[l * C + t];
+        atomicAdd(sums + t, sa);
+    }
+}
+
+__global__ void sums_to_f32_kernel(const double* sums, int n, float* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)sums[i];
+}
+
+// fp32 NCHW -> NHWC through a 32x32 shared-memory tile per (n, channel block, pixel block)
+__global__ void nchw_to_nhwc_kernel(const float* src, int C, long long HW, float* dst) {
+    __shared__ float tile[32][33];
+    const long long n = blockIdx.z;
+    const int c0 = blockIdx.y * 32;
+    const long long p0 = (long long)blockIdx.x * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j;
+        const long long p = p0 + tx;
+        tile[j][tx] = (c < C && p < HW) ? __ldg(src + (n * C + c) * HW + p) : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const long long p = p0 + j;
+        const int c = c0 + tx;
+        if (c < C && p < HW) dst[(n * HW + p) * C + c] = tile[tx][j];
+    }
+}
+
+__global__ void add_f32_kernel(float* dst, const float* a, const float* b, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = a[i] + b[i];
+}
+
+int grid_for(long long work_items, int per_block) {
+    long long b = (work_items + per_block - 1) / per_block;
+    const long long cap = 148 * 8;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+int check_bn(const disco_bn_desc* d) {
+    DISCO_REQUIRE(d && d->z && d->gamma && d->beta && d->sums && d->stats, "bn: null tensor");
+    DISCO_REQUIRE(d->c >= 8 && d->c % 8 == 0 && d->c <= kMaxC, "bn: channels %d unsupported", d->c);
+    DISCO_REQUIRE((d->c <= kThreads && kThreads % d->c == 0) || d->c == 2 * kThreads,
+                  "bn: channels %d must divide %d (or be %d)", d->c, kThreads, 2 * kThreads);
+    DISCO_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0, "bn: empty input");
+    return DISCO_OK;
+}
+
+}  // namespace
+
+int disco_bn_train_forward_launch(const disco_bn_desc* d, void* stream) {
+    int rc = check_bn(d);
+    if (rc < 0) return rc;
+    DISCO_REQUIRE(d->out_hi, "bn forward: null output");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long M = (long long)d->n * d->h * d->w;
+    DISCO_CHECK_CUDA(cudaMemsetAsync(d->sums, 0, sizeof(double) * 2 * d->c, s));
+    const int lanes = d->c < kThreads ? kThreads / d->c : 1;
+    bn_reduce_kernel<0><<<grid_for(M, lanes * 64), kThreads, 0, s>>>(*d, M);
+    bn_finalize_kernel<<<(d->c + 127) / 128, 128, 0, s>>>(*d, M);
+    bn_apply_kernel<<<grid_for(M * (d->c / 8), kThreads * 4), kThreads, 0, s>>>(*d, M);
+    DISCO_CHECK_CUDA(cudaGetLastError());
+    return DISCO_OK;
+}
+
+int disco_bn_train_backward_launch(const disco_bn_desc* d, void* stream) {
+    int rc = check_bn(d);
+    if (rc < 0) return rc;
+    DISCO_REQUIRE(d->dz_hi && d->n_g >= 1 && d->n_g <= 3, "bn backward: null output / bad source count");
+    for (int i = 0; i < d->n_g; ++i) {
+        DISCO_REQUIRE(d->g[i].ptr && d->g[i].c_total % 4 == 0 && d->g[i].c_off % 4 == 0, "bn backward: bad gradient source %d", i);
+        DISCO_REQUIRE(d->g[i].c_off + d->c <= d->g[i].c_total, "bn backward: gradient source %d too narrow", i);
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long M = (long long)d->n * d->h * d->w;
+    DISCO_CHECK_CUDA(cudaMemsetAsync(d->sums, 0, sizeof(double) * 2 * d->c, s));
+    const int lanes = d->c < kThreads ? kThreads / d->c : 1;
+    bn_reduce_kernel<1><<<grid_for(M, lanes * 64), kThreads, 0, s>>>(*d, M);
+    bn_bwd_apply_kernel<<<grid_for(M * (d->c / 8), kThreads * 4), kThreads, 0, s>>>(*d, M);
+    DISCO_CHECK_CUDA(cudaGetLastError());
+    return DISCO_OK;
+}
+
+int disco_grad_pack_launch(const float* a, int ca, const float* b, int cb, long long n_pix, void* out_hi,
+                           long long out_lo_off, void* stream) {
+    DISCO_REQUIRE(a && out_hi && ca > 0 && ca % 4 == 0 && cb % 4 == 0 && (cb == 0 || b) && n_pix > 0, "grad_pack: bad arguments");
+    grad_pack_kernel<<<grid_for(n_pix * ((ca + cb) / 4), kThreads * 4), kThreads, 0, (cudaStream_t)stream>>>(
+        a, ca, b, cb, n_pix, reinterpret_cast<uint16_t*>(out_hi), out_lo_off);
+    DISCO_CHECK_CUDA(cudaGetLastError());
+    return DISCO_OK;
+}
+
+int disco_channel_sum_launch(const float* src, long long n_pix, int c, double* sums, float* out, void* stream) {
+    DISCO_REQUIRE(src && sums && out && c > 0 && c <= kThreads && n_pix > 0, "channel_sum: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    DISCO_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * c, s));
+    channel_sum_kernel<<<grid_for(n_pix, (kThreads / c) * 64), kThreads, 0, s>>>(src, n_pix, c, sums);
+    sums_to_f32_kernel<<<(c + 127) / 128, 128, 0, s>>>(sums, c, out);
+    DISCO_CHECK_CUDA(cudaGetLastError());
+    return DISCO_OK;
+}
+
+int disco_nchw_to_nhwc_launch(const float* src, int n, int c, int h, int w, float* dst, void* stream) {
+    DISCO_REQUIRE(src && dst && n > 0 && c > 0 && h > 0 && w > 0, "nchw_to_nhwc: bad arguments");
+    const long long HW = (long long)h * w;
+    dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n);
+    nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, c, HW, dst);
+    DISCO_CHECK_CUDA(cudaGetLastError());
+    return DISCO_OK;
+}
+
+int disco_add_f32_launch(float* dst, const float* a, const float* b, long long n, void* stream) {
+    DISCO_REQUIRE(dst && a && b && n > 0, "add_f32: bad arguments");
+    add_f32_kernel<<<grid_for(n, kThreads * 4), kThreads, 0, (cudaStream_t)stream>>>(dst, a, b, n);
+    DISCO_CHECK_CUDA(cudaGetLastError());
+    return DISCO_OK;
+}

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import engine, ops
+from . import engine, ops, train as train_mod
 from ._lib import DiscoError, load
 from .modules import (BackboneParams, ClassificationHeadParams, PixelWeightedFusionParams, RegressionHeadParams)
 
@@ -54,6 +54,35 @@ class AgentWeightList(collections.abc.Sequence):
         return self._build()[k]
 
 
+class _TrainFn(torch.autograd.Function):
+    """One training step of the hot path as a single autograd node: forward = TrainRunner.forward (batch-statistics
+    BatchNorm, running-stat updates), backward = TrainRunner.backward (all parameter gradients).  Replaces the
+    autograd graph torch builds over the reference model (CoDetModule.py:249-256,289-291)."""
+
+    @staticmethod
+    def forward(ctx, runner, bevs, trans, num_agent, outage_host, kd_keys, names, *params):
+        out = runner.forward(bevs, trans, num_agent, outage_host)
+        ctx.runner, ctx.kd_keys, ctx.names = runner, kd_keys, names
+        tensors = []
+        if "cls" in out:
+            tensors += [out["cls"], out["loc"]]
+        ctx.has_heads = "cls" in out
+        tensors += [runner.kd_map(k) for k in kd_keys]
+        return tuple(tensors)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        grads = {}
+        gs = list(gs)
+        if ctx.has_heads:
+            grads["cls"], grads["loc"] = gs[0], gs[1]
+            gs = gs[2:]
+        for k, g in zip(ctx.kd_keys, gs):
+            grads[k] = g
+        res = ctx.runner.backward(grads)
+        return (None,) * 7 + tuple(res.get(n) for n in ctx.names)
+
+
 class _DetBase(nn.Module):
     """Shared plumbing: config fields, heads, plan/workspace caches (DetModelBase.py:27-51)."""
 
@@ -88,6 +117,7 @@ class _DetBase(nn.Module):
         self._plans = None
         self._plans_key = None
         self._ws: Dict[tuple, engine.Workspace] = {}
+        self._runners: Dict[tuple, train_mod.TrainRunner] = {}
 
     # ---- caches ---------------------------------------------------------------------------------------
     @property
@@ -117,10 +147,10 @@ class _DetBase(nn.Module):
 
     def _check_inputs(self, bevs):
         load()  # raises if libdisco_b200.so is missing
-        if self.training:
-            raise NotImplementedError(
-                "disconet_b200 round 1 implements the eval-mode forward (BN folded); call model.eval(). "
-                "The training forward/backward kernels are the next row of DESIGN.md §scope.")
+        if self.training and self.precision_name != "bf16x3":
+            raise NotImplementedError("training mode runs in the default bf16x3 precision only")
+        if self.training and getattr(self, "compress_level", 0) > 0:
+            raise NotImplementedError("training mode with compress_level > 0 is not implemented")
         if not bevs.is_cuda:
             raise ValueError("disconet_b200 runs on CUDA tensors only (no CPU fallback); got a CPU `bevs`")
         if bevs.dim() != 5 or bevs.shape[1] != 1 or bevs.shape[4] != self.in_channels:
@@ -150,6 +180,24 @@ class _DetBase(nn.Module):
 
     def _nchw(self, ws, key):
         return ops.act_to_nchw_f32(ws.buf[key], self.precision)
+
+    # ---- training mode (a12) ------------------------------------------------------------------------------
+    def _train_step(self, runner, bevs, trans, num_agent, outage_host, kd_keys):
+        """Run the training forward through one autograd node; returns (result dict | None, [kd maps])."""
+        live = runner_param_names(runner)
+        named = dict(self.named_parameters())
+        names = tuple(k for k in named if k in live)
+        outs = _TrainFn.apply(runner, bevs, trans, num_agent, outage_host, tuple(kd_keys), names,
+                              *[named[k] for k in names])
+        outs = list(outs)
+        result = None
+        if runner.head_layers:
+            cls, loc = outs[0], outs[1]
+            outs = outs[2:]
+            n, h, w = runner.n, runner.h, runner.w
+            result = {"loc": loc.view(-1, h, w, self.anchor_num_per_loc, self.out_seq_len, self.box_code_size),
+                      "cls": cls.view(n, -1, self.category_num)}
+        return result, outs
 
 
 class DiscoNet(_DetBase):
@@ -247,6 +295,8 @@ class DiscoNet(_DetBase):
             raise ValueError(f"bevs has {N} rows but agent_num*batch_size = {A}*{B}")
         if tuple(trans_matrices.shape) != (B, A, A, 4, 4):
             raise ValueError(f"trans_matrices must be [{B},{A},{A},4,4] (got {tuple(trans_matrices.shape)})")
+        if self.training:
+            return self._forward_train(bevs, trans_matrices, num_agent_tensor, B)
         P = self.plans()
         ws = self._workspace(N, H, W, B, dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -317,6 +367,47 @@ class DiscoNet(_DetBase):
                     self._nchw(ws, ws.fused_key))
         return result, AgentWeightList(weights, num_agent, bool(self.only_v2i), outage_host)
 
+    def _forward_train(self, bevs, trans_matrices, num_agent_tensor, B):
+        """model.train() forward (batch-statistics BatchNorm incl. the per-pair PWF statistics) with autograd."""
+        dev = bevs.device
+        N, _, H, W, _ = bevs.shape
+        A = self.agent_num
+        key = (N, H, W, B, str(dev), bool(self.only_v2i), self.layer)
+        runner = self._runners.get(key)
+        if runner is None:
+            runner = train_mod.TrainRunner(self._getter(), N, H, W, dev, "u_encoder.", "decoder.", heads=True,
+                                           pwf_prefix="pixel_weighted_fusion.", batch_size=B, agents=A,
+                                           fusion_level=self.layer, only_v2i=bool(self.only_v2i))
+            self._runners[key] = runner
+        runner.get = self._getter()
+        outage_host = None
+        if self.p_com_outage != 0.0:
+            na_host = num_agent_tensor.detach()[:, 0].tolist()
+            outage_host = torch.zeros((B, A), dtype=torch.int32)
+            for b in range(B):
+                for i in range(int(na_host[b])):
+                    outage_host[b, i] = int(self.outage())
+        kd_keys = ["x8", "x7", "x6", "x5", runner.fused_key] if self.kd_flag == 1 else []
+        result, maps = self._train_step(runner, bevs, trans_matrices, num_agent_tensor, outage_host, kd_keys)
+        if self.kd_flag == 1:
+            return (result, *maps)
+        return result, AgentWeightList(runner.weights.clone(), runner.na.clone(), bool(self.only_v2i), outage_host)
+
+
+def runner_param_names(runner) -> set:
+    """Names of the parameters a TrainRunner differentiates (the reference's live parameters)."""
+    names = set()
+    for L in runner.enc + runner.dec:
+        names |= {L.conv + ".weight", L.conv + ".bias", L.bn + ".weight", L.bn + ".bias"}
+    if runner.head_layers:
+        for m in ("classification.conv1", "classification.conv2", "classification.bn1", "regression.box_prediction.0",
+                  "regression.box_prediction.1", "regression.box_prediction.3"):
+            names |= {m + ".weight", m + ".bias"}
+    if runner.pwf_prefix:
+        for m in ("conv1_1", "bn1_1", "conv1_2", "bn1_2", "conv1_3", "bn1_3", "conv1_4"):
+            names |= {runner.pwf_prefix + m + ".weight", runner.pwf_prefix + m + ".bias"}
+    return names
+
 
 class _StpnModel(_DetBase):
     """NonIntermediateModelBase.py:12-24: one STPN_KD backbone named `stpn`, no fusion."""
@@ -342,6 +433,16 @@ class _StpnModel(_DetBase):
             self._ws[key] = ws
         return ws
 
+    def _train_runner(self, bevs, heads: bool):
+        N, _, H, W, _ = bevs.shape
+        key = (N, H, W, str(bevs.device), heads)
+        runner = self._runners.get(key)
+        if runner is None:
+            runner = train_mod.TrainRunner(self._getter(), N, H, W, bevs.device, "stpn.", "stpn.", heads=heads)
+            self._runners[key] = runner
+        runner.get = self._getter()
+        return runner
+
     def _backbone(self, bevs):
         self._check_inputs(bevs)
         N, _, H, W, _ = bevs.shape
@@ -357,6 +458,12 @@ class FaFNet(_StpnModel):
     """Early-fusion / no-fusion baseline (reference FaFNet.py:4-39); BASELINE config 1."""
 
     def forward(self, bevs, maps=None, vis=None, batch_size=None):
+        if self.training:
+            self._check_inputs(bevs)
+            runner = self._train_runner(bevs, heads=True)
+            kd_keys = ["x8", "x7", "x6", "x5", "x3"] if self.kd_flag == 1 else []
+            result, maps_ = self._train_step(runner, bevs, None, None, None, kd_keys)
+            return (result, *maps_) if self.kd_flag == 1 else result
         ws, stream = self._backbone(bevs)
         result = self._run_heads(ws, stream)
         if self.kd_flag == 1:
@@ -372,6 +479,11 @@ class TeacherNet(_StpnModel):
         super().__init__(config, compress_level=0, precision=precision)
 
     def forward(self, bevs, maps=None, vis=None):
+        if self.training:
+            self._check_inputs(bevs)
+            runner = self._train_runner(bevs, heads=False)
+            _, maps_ = self._train_step(runner, bevs, None, None, None, ["x8", "x7", "x6", "x5", "x3", "x4"])
+            return tuple(maps_)
         ws, _ = self._backbone(bevs)
         return (self._nchw(ws, "x8"), self._nchw(ws, "x7"), self._nchw(ws, "x6"), self._nchw(ws, "x5"),
                 self._nchw(ws, ws.x3_key), self._nchw(ws, "x4"))

@@ -44,7 +44,8 @@ typedef struct disco_conv_desc {
     const void* src[2];      /* NHWC 16-bit sources, concatenated along channels (src[1] may be NULL) */
     long long src_lo_off[2]; /* BF16X3: elements from hi to lo                                         */
     int src_c[2];            /* channels per source, multiples of 16                                   */
-    int src_up[2];           /* 1: source is (h_in/2, w_in/2) and is nearest-upsampled x2 on the fly   */
+    int src_up[2];           /* 1: source is (h_in/2, w_in/2) and is nearest-upsampled x2 on the fly;
+                              * 2: zero-stuffed x2 instead (transposed stride-2 conv = data gradient)   */
     int n, h_in, w_in;       /* logical conv input size                                                */
     int h_out, w_out;        /* (h_in-1)/stride+1, (w_in-1)/stride+1                                   */
     int stride;              /* 1 | 2                                                                  */
@@ -122,9 +123,121 @@ typedef struct disco_fusion_desc {
     float* weights;        /* optional [B, A(ego), A(neighbour id), h, w] softmax weights (unflipped) */
     int row_begin, row_end; /* ego rows n = a*B+b computed by this call; output row = n - row_begin      */
     const int* outage;     /* optional [B, A] int32 (device): 1 = outage, ego keeps its own features    */
+    const float* wpre;     /* optional [B, A, A, h, w]: precomputed PWF output maps (training mode); en/w2..b4 unused */
 } disco_fusion_desc;
 
 int disco_fusion_forward(const disco_fusion_desc* d /* host */, void* stream);
+
+/* ======================================================================================================
+ * Training mode: replaces, for model.train(), the batch-statistics F.batch_norm calls of
+ * Backbone.encode/decode + heads + PixelWeightedFusionSoftmax and torch.autograd's backward of the whole path
+ * (utils/CoDetModule.py:289-291 `loss.backward()`).  Forward convs run through disco_conv_forward with the raw
+ * (unfolded) weights and fp32 output; data gradients are disco_conv_forward calls with transposed/flipped
+ * weights (stride-2 layers: src_up = 2, zero-stuffed source).
+ * ====================================================================================================== */
+
+/* A channel slice of an fp32 NHWC gradient tensor; pool = 1: tensor is (2h x 2w) and each 2x2 block is summed
+ * (backward of the nearest x2 upsample feeding conv5_1..conv8_1, Backbone.py:176,195,214,233). */
+typedef struct disco_grad_src {
+    const float* ptr;
+    int c_total;
+    int c_off;
+    int pool;
+} disco_grad_src;
+
+/* conv -> BatchNorm2d/3d(train) -> ReLU around the conv kernel (nn.BatchNorm semantics: biased batch variance to
+ * normalise, momentum update of running_mean / unbiased running_var, num_batches_tracked += 1). */
+typedef struct disco_bn_desc {
+    const float* z;            /* [n*h*w, c] conv output incl. bias, fp32 NHWC                         */
+    int n, h, w, c;            /* c in {8,16,32,64,128,256,512}                                       */
+    const float* gamma;
+    const float* beta;
+    float* running_mean;       /* updated in place; may be NULL                                       */
+    float* running_var;
+    long long* num_batches_tracked;
+    float momentum, eps;
+    double* sums;              /* workspace [2*c]                                                     */
+    float* stats;              /* [2*c] mean | rstd: written by forward, read by backward             */
+    void* out_hi;              /* forward: y = relu(bn(z)) activation buffer                          */
+    long long out_lo_off;
+    int relu;
+    disco_grad_src g[3];       /* backward: gradient sources wrt y (summed)                           */
+    int n_g;
+    void* dz_hi;               /* backward: gradient wrt z, activation buffer                         */
+    long long dz_lo_off;
+    float* dgamma;             /* [c] assigned                                                        */
+    float* dbeta;              /* [c] assigned                                                        */
+} disco_bn_desc;
+
+int disco_bn_train_forward(const disco_bn_desc* d /* host */, void* stream);
+int disco_bn_train_backward(const disco_bn_desc* d /* host */, void* stream);
+
+/* fp32 NHWC gradient tensors a [n_pix, ca] | b [n_pix, cb] (channel-concatenated; b may be NULL with cb = 0)
+ * -> activation buffer [n_pix, ca + cb]. */
+int disco_grad_pack(const float* a, int ca, const float* b, int cb, long long n_pix, void* out_hi, long long out_lo_off,
+                    void* stream);
+/* out[c] = sum over pixels of src[pix, c] (bias gradient of a conv without BatchNorm); sums: workspace [c] double */
+int disco_channel_sum(const float* src, long long n_pix, int c, double* sums, float* out, void* stream);
+/* fp32 NCHW -> NHWC (gradients of the returned KD feature maps arrive NCHW) */
+int disco_nchw_to_nhwc(const float* src, int n, int c, int h, int w, float* dst, void* stream);
+int disco_add_f32(float* dst, const float* a, const float* b, long long n, void* stream);
+
+/* Weight gradient dW[co][ci][kh][kw] = sum_pixels dz[p][co] * x[p (+) tap][ci] of a conv layer on the tensor cores
+ * (MN-major tcgen05 operands, split-K over pixel tiles). */
+typedef struct disco_wgrad_desc {
+    const void* src[2];        /* forward input of the conv: as in disco_conv_desc                    */
+    long long src_lo_off[2];
+    int src_c[2];
+    int src_up[2];
+    int n, h_in, w_in, h_out, w_out;
+    int stride, taps;
+    const void* dz_hi;         /* gradient wrt the conv output, activation buffer [n,h_out,w_out,c_out] */
+    long long dz_lo_off;
+    int c_out;                 /* multiple of 16; <= 128 or a multiple of 128                          */
+    float* partial;            /* workspace [splits][c_out][taps][c_in] fp32                           */
+    int splits;                /* what `partial` was sized for (>= disco_conv_wgrad_splits)            */
+    float* dw;                 /* [c_out][c_in_real][taps] fp32 (OIHW), assigned                       */
+    int c_in_real;
+    int passes;                /* 3 (bf16x3) | 1                                                       */
+} disco_wgrad_desc;
+
+int disco_conv_wgrad(const disco_wgrad_desc* d /* host */, void* stream);
+int disco_conv_wgrad_reference(const disco_wgrad_desc* d /* host */, void* stream); /* CUDA-core validator */
+int disco_conv_wgrad_splits(const disco_wgrad_desc* d /* host */);
+
+/* PixelWeightedFusionSoftmax in train() mode (DiscoNet.py:86-95,148-155: one call per (scene, ego, neighbour) with
+ * that call's batch statistics and a sequential running-statistics update) and the backward of the DiscoGraph
+ * fusion block (DiscoNet.py:83-111 softmax / weighted sum, DetModelBase.py:139-169 affine warp). */
+typedef struct disco_pwf_train_desc {
+    const void* feat_hi;
+    long long feat_lo_off;
+    const float* en;           /* [A*B,h,w,2*hid] fp32: conv1_1 ego half (+bias) | neighbour half, raw weights */
+    int hid;
+    const float* g1; const float* be1;
+    const float* w2; const float* b2; const float* g2; const float* be2;
+    const float* w3; const float* b3; const float* g3; const float* be3;
+    const float* w4; const float* b4;
+    float eps, momentum;
+    float* rm1; float* rv1; float* rm2; float* rv2; float* rm3; float* rv3;
+    long long* nbt1; long long* nbt2; long long* nbt3;
+    const double* trans;
+    const int* num_agent;
+    const int* outage;
+    int B, A, h, w, C;
+    int only_v2i;
+    float trans_scale;
+    float* pstats;             /* [B*A*A][3][168] per-pair mean | rstd | biased variance               */
+    float* wlogit;             /* [B,A,A,h,w] PWF output maps (post-ReLU), 0 for unused pairs          */
+    const float* dfused;       /* backward: [A*B,h,w,C] fp32 gradient wrt the fused map                */
+    float* dwlogit;            /* [B,A,A,h,w]                                                         */
+    float* dfeat;              /* [A*B,h,w,C] fp32, accumulated (caller zeroes)                        */
+    float* den;                /* [A*B,h,w,2*hid] fp32, accumulated (caller zeroes)                    */
+    float* dparams;            /* [4697] accumulated: dg1 dbe1 dw2 dg2 dbe2 dw3 dg3 dbe3 dw4 db4       */
+} disco_pwf_train_desc;
+
+int disco_pwf_train_forward(const disco_pwf_train_desc* d /* host */, void* stream);
+int disco_fusion_combine_backward(const disco_pwf_train_desc* d /* host */, void* stream);
+int disco_pwf_train_backward(const disco_pwf_train_desc* d /* host */, void* stream);
 
 #ifdef __cplusplus
 }
