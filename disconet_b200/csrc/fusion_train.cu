@@ -28,7 +28,7 @@ constexpr int kHid = 128, kH2 = 32, kH3 = 8;
 constexpr int kStatC = kHid + kH2 + kH3;   // 168 BatchNorm channels per pair
 // dparams layout
 constexpr int kDG1 = 0, kDBE1 = 128, kDW2 = 256, kDG2 = 4352, kDBE2 = 4384, kDW3 = 4416, kDG3 = 4672, kDBE3 = 4680,
-              kDW4 = 4688, kDB4 = 4696, kDParams = 4697;
+              kDW4 = 4688;   // dW4[8] followed by db4 (4696); 4697 floats in total
 
 struct Taps {
     int n;
@@ -109,7 +109,7 @@ struct FwdSmem {
     float b2[kH2], b3[kH3], w4[kH3], b4;
     float gam[kStatC], bet[kStatC];       // BN gamma/beta of the three layers, concatenated 128 | 32 | 8
     float mu[kStatC], rs[kStatC];         // per-pair batch mean / rstd
-    float h1[kFwdWarps][kHid];
+    alignas(16) float h1[kFwdWarps][kHid];
     float red[kFwdWarps][2 * kHid];       // cross-warp reduction scratch (sum | sum of squares)
 };
 
@@ -363,9 +363,9 @@ struct BwdSmem {
     float b2[kH2], b3[kH3], w4[kH3], b4;
     float gam[kStatC], bet[kStatC], mu[kStatC], rs[kStatC];
     float mg[kStatC], mgx[kStatC];        // per-pair mean(g), mean(g * xhat) of each BN layer (filled pass by pass)
-    float h1[kBwdWarps][kHid];            // a1
-    float xh1[kBwdWarps][kHid];           // xhat1
-    float dz1[kBwdWarps][kHid];
+    alignas(16) float h1[kBwdWarps][kHid];    // a1
+    alignas(16) float xh1[kBwdWarps][kHid];   // xhat1
+    alignas(16) float dz1[kBwdWarps][kHid];
     float dz2[kBwdWarps][kH2];
     float red[kBwdWarps][2 * kHid];       // cross-warp scratch: sum g | sum g*xhat
     float dw2[kH2 * kHid];                // CTA accumulator of dW2
