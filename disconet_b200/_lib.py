@@ -77,6 +77,16 @@ class BnDesc(C.Structure):
     ]
 
 
+class PackDesc(C.Structure):
+    """struct disco_pack_desc."""
+    _fields_ = [
+        ("w", C.c_void_p), ("co_src", C.c_int), ("ci_src", C.c_int), ("taps", C.c_int),
+        ("transpose", C.c_int), ("c0", C.c_int), ("n_real", C.c_int), ("k_pad", C.c_int),
+        ("block_n", C.c_int), ("c_blk", C.c_int), ("n_tiles", C.c_int), ("stacked", C.c_int),
+        ("wpack", C.c_void_p), ("bias_src", C.c_void_p), ("bias", C.c_void_p),
+    ]
+
+
 class WgradDesc(C.Structure):
     """struct disco_wgrad_desc."""
     _fields_ = [
@@ -102,8 +112,8 @@ class PwfTrainDesc(C.Structure):
         ("trans", C.c_void_p), ("num_agent", C.c_void_p), ("outage", C.c_void_p),
         ("B", C.c_int), ("A", C.c_int), ("h", C.c_int), ("w", C.c_int), ("C", C.c_int),
         ("only_v2i", C.c_int), ("trans_scale", C.c_float),
-        ("pstats", C.c_void_p), ("wlogit", C.c_void_p),
-        ("dfused", C.c_void_p), ("dwlogit", C.c_void_p), ("dfeat", C.c_void_p), ("den", C.c_void_p), ("dparams", C.c_void_p),
+        ("psum", C.c_void_p), ("wlogit", C.c_void_p),
+        ("dfused", C.c_void_p), ("dwlogit", C.c_void_p), ("dfeat", C.c_void_p), ("den", C.c_void_p), ("gsum", C.c_void_p), ("dparams", C.c_void_p),
     ]
 
 
@@ -127,6 +137,7 @@ EXPORTS = {
     # training mode
     "disco_bn_train_forward": (C.c_int, [C.POINTER(BnDesc), C.c_void_p]),
     "disco_bn_train_backward": (C.c_int, [C.POINTER(BnDesc), C.c_void_p]),
+    "disco_pack_weights": (C.c_int, [C.POINTER(PackDesc), C.c_void_p]),
     "disco_grad_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p]),
     "disco_channel_sum": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "disco_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

@@ -90,6 +90,10 @@ int disco_bn_train_backward(const disco_bn_desc* d, void* stream) {
     if (!d) { disco_set_error("null descriptor"); return DISCO_EINVAL; }
     return disco_bn_train_backward_launch(d, stream);
 }
+int disco_pack_weights(const disco_pack_desc* d, void* stream) {
+    if (!d) { disco_set_error("null descriptor"); return DISCO_EINVAL; }
+    return disco_pack_weights_launch(d, stream);
+}
 int disco_grad_pack(const float* a, int ca, const float* b, int cb, long long n_pix, void* out_hi, long long out_lo_off,
                     void* stream) {
     return disco_grad_pack_launch(a, ca, b, cb, n_pix, out_hi, out_lo_off, stream);

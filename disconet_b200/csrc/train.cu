@@ -40,23 +40,41 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const disco_bn_desc
     const bool active = lane < lanes;
     float a[2] = {0.f, 0.f}, b[2] = {0.f, 0.f};
     if (active) {
-        for (long long p = (long long)blockIdx.x * lanes + lane; p < M; p += (long long)gridDim.x * lanes) {
+        // kUnroll independent rows per iteration: the loop is latency-bound otherwise (one 4-byte load in flight
+        // per thread); out-of-range rows are predicated off
+        constexpr int kUnroll = 8;
+        const long long stride = (long long)gridDim.x * lanes;
+        for (long long p0 = (long long)blockIdx.x * lanes + lane; p0 < M; p0 += stride * kUnroll) {
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 if (k >= cpt) break;
                 const int c = c0 + k * kThreads;
-                const float z = __ldg(d.z + p * C + c);
+                float zv[kUnroll], gv[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    const long long p = p0 + u * stride;
+                    const bool ok = p < M;
+                    zv[u] = ok ? __ldg(d.z + p * C + c) : 0.f;
+                    gv[u] = 0.f;
+                    if (MODE == 1 && ok)
+                        for (int s = 0; s < d.n_g; ++s) gv[u] += grad_src_load(d.g[s], p, d.h, d.w, c);
+                }
                 if (MODE == 0) {
-                    a[k] += z;
-                    b[k] = fmaf(z, z, b[k]);
+#pragma unroll
+                    for (int u = 0; u < kUnroll; ++u) {
+                        a[k] += zv[u];
+                        b[k] = fmaf(zv[u], zv[u], b[k]);
+                    }
                 } else {
-                    const float mean = d.stats[c], rstd = d.stats[C + c];
-                    const float xh = (z - mean) * rstd;
-                    float g = 0.f;
-                    for (int s = 0; s < d.n_g; ++s) g += grad_src_load(d.g[s], p, d.h, d.w, c);
-                    if (d.relu && fmaf(xh, d.gamma[c], d.beta[c]) <= 0.f) g = 0.f;
-                    a[k] += g;
-                    b[k] = fmaf(g, xh, b[k]);
+                    const float mean = d.stats[c], rstd = d.stats[C + c], gam = d.gamma[c], bet = d.beta[c];
+#pragma unroll
+                    for (int u = 0; u < kUnroll; ++u) {
+                        const float xh = (zv[u] - mean) * rstd;
+                        float g = gv[u];
+                        if (d.relu && fmaf(xh, gam, bet) <= 0.f) g = 0.f;
+                        a[k] += g;
+                        b[k] = fmaf(g, xh, b[k]);
+                    }
                 }
             }
         }
@@ -215,9 +233,16 @@ __global__ void __launch_bounds__(kThreads) channel_sum_kernel(const float* src,
     const int t = threadIdx.x;
     const int lane = t / C, c = t - lane * C;
     float a = 0.f;
-    if (lane < lanes)
-        for (long long p = (long long)blockIdx.x * lanes + lane; p < M; p += (long long)gridDim.x * lanes)
-            a += __ldg(src + p * C + c);
+    if (lane < lanes) {
+        const long long stride = (long long)gridDim.x * lanes;
+        for (long long p0 = (long long)blockIdx.x * lanes + lane; p0 < M; p0 += stride * 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (p0 + u * stride < M) ? __ldg(src + (p0 + u * stride) * C + c) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a += v[u];
+        }
+    }
     s_a[t] = a;
     __syncthreads();
     if (t < C) {
@@ -257,9 +282,60 @@ __global__ void add_f32_kernel(float* dst, const float* a, const float* b, long 
         dst[i] = a[i] + b[i];
 }
 
-int grid_for(long long work_items, int per_block) {
+// one thread per (n_tile, k block, tap, 8-channel chunk, n): 8 K-consecutive values, hi and lo planes
+__global__ void __launch_bounds__(kThreads) pack_weights_kernel(const disco_pack_desc d, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int chunks = d.c_blk >> 3, ncb = d.k_pad / d.c_blk;
+    if (idx < (long long)d.n_tiles * d.block_n && d.bias) {
+        const int nn = (int)idx;
+        d.bias[nn] = (d.bias_src && nn < d.n_real) ? d.bias_src[nn] : 0.f;
+    }
+    if (idx >= total) return;
+    long long r = idx;
+    const int n = (int)(r % d.block_n); r /= d.block_n;
+    const int chunk = (int)(r % chunks); r /= chunks;
+    const int tap = (int)(r % d.taps); r /= d.taps;
+    const int cb = (int)(r % ncb);
+    const int n_tile = (int)(r / ncb);
+    const int nn = n_tile * d.block_n + n;
+    const int k_real = d.transpose ? d.co_src : d.ci_src;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int kc = cb * d.c_blk + chunk * 8 + e;
+        float x = 0.f;
+        if (nn < d.n_real && kc < k_real)
+            x = d.transpose ? d.w[((long long)kc * d.ci_src + d.c0 + nn) * d.taps + (d.taps - 1 - tap)]
+                            : d.w[((long long)nn * d.ci_src + kc) * d.taps + tap];
+        v[e] = x;
+    }
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint16_t h0, l0, h1, l1;
+        split_bf16(v[2 * q], h0, l0);
+        split_bf16(v[2 * q + 1], h1, l1);
+        hw[q] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+        lw[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+    }
+    // element offsets (in 8-element rows): [n_tile][cb][tap] block of 2*chunks*block_n rows
+    const long long blk = (((long long)n_tile * ncb + cb) * d.taps + tap) * (2LL * chunks * d.block_n);
+    long long row_hi, row_lo;
+    if (d.stacked) {
+        row_hi = blk + ((long long)chunk * 2 + 0) * d.block_n + n;
+        row_lo = blk + ((long long)chunk * 2 + 1) * d.block_n + n;
+    } else {
+        row_hi = blk + (long long)chunk * d.block_n + n;
+        row_lo = blk + ((long long)chunks + chunk) * d.block_n + n;
+    }
+    uint4* out = reinterpret_cast<uint4*>(d.wpack);
+    out[row_hi] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    out[row_lo] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+
+int grid_for(long long work_items, int per_block, int cap_blocks = 148 * 8) {
     long long b = (work_items + per_block - 1) / per_block;
-    const long long cap = 148 * 8;
+    const long long cap = cap_blocks;
     if (b > cap) b = cap;
     if (b < 1) b = 1;
     return (int)b;
@@ -284,7 +360,7 @@ int disco_bn_train_forward_launch(const disco_bn_desc* d, void* stream) {
     const long long M = (long long)d->n * d->h * d->w;
     DISCO_CHECK_CUDA(cudaMemsetAsync(d->sums, 0, sizeof(double) * 2 * d->c, s));
     const int lanes = d->c < kThreads ? kThreads / d->c : 1;
-    bn_reduce_kernel<0><<<grid_for(M, lanes * 64), kThreads, 0, s>>>(*d, M);
+    bn_reduce_kernel<0><<<grid_for(M, lanes * 16, 148 * 4), kThreads, 0, s>>>(*d, M);
     bn_finalize_kernel<<<(d->c + 127) / 128, 128, 0, s>>>(*d, M);
     bn_apply_kernel<<<grid_for(M * (d->c / 8), kThreads * 4), kThreads, 0, s>>>(*d, M);
     DISCO_CHECK_CUDA(cudaGetLastError());
@@ -303,8 +379,23 @@ int disco_bn_train_backward_launch(const disco_bn_desc* d, void* stream) {
     const long long M = (long long)d->n * d->h * d->w;
     DISCO_CHECK_CUDA(cudaMemsetAsync(d->sums, 0, sizeof(double) * 2 * d->c, s));
     const int lanes = d->c < kThreads ? kThreads / d->c : 1;
-    bn_reduce_kernel<1><<<grid_for(M, lanes * 64), kThreads, 0, s>>>(*d, M);
+    bn_reduce_kernel<1><<<grid_for(M, lanes * 16, 148 * 4), kThreads, 0, s>>>(*d, M);
     bn_bwd_apply_kernel<<<grid_for(M * (d->c / 8), kThreads * 4), kThreads, 0, s>>>(*d, M);
+    DISCO_CHECK_CUDA(cudaGetLastError());
+    return DISCO_OK;
+}
+
+int disco_pack_weights_launch(const disco_pack_desc* d, void* stream) {
+    DISCO_REQUIRE(d && d->w && d->wpack, "pack_weights: null tensor");
+    DISCO_REQUIRE(d->c_blk == 16 || d->c_blk == 32 || d->c_blk == 64, "pack_weights: c_blk must be 16/32/64");
+    DISCO_REQUIRE(d->k_pad > 0 && d->k_pad % d->c_blk == 0 && d->block_n % 16 == 0 && d->n_tiles >= 1 && d->taps >= 1,
+                  "pack_weights: bad geometry");
+    DISCO_REQUIRE(d->n_real <= d->n_tiles * d->block_n, "pack_weights: n_real exceeds the padded rows");
+    DISCO_REQUIRE(!d->transpose || d->c0 + d->n_real <= d->ci_src, "pack_weights: slice out of range");
+    const long long total = (long long)d->n_tiles * (d->k_pad / d->c_blk) * d->taps * (d->c_blk / 8) * d->block_n;
+    const long long blocks = (total + kThreads - 1) / kThreads;
+    DISCO_REQUIRE(blocks < (1ll << 31), "pack_weights: too large");
+    pack_weights_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(*d, total);
     DISCO_CHECK_CUDA(cudaGetLastError());
     return DISCO_OK;
 }
@@ -322,7 +413,7 @@ int disco_channel_sum_launch(const float* src, long long n_pix, int c, double* s
     DISCO_REQUIRE(src && sums && out && c > 0 && c <= kThreads && n_pix > 0, "channel_sum: bad arguments");
     cudaStream_t s = (cudaStream_t)stream;
     DISCO_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * c, s));
-    channel_sum_kernel<<<grid_for(n_pix, (kThreads / c) * 64), kThreads, 0, s>>>(src, n_pix, c, sums);
+    channel_sum_kernel<<<grid_for(n_pix, (kThreads / c) * 16, 148 * 4), kThreads, 0, s>>>(src, n_pix, c, sums);
     sums_to_f32_kernel<<<(c + 127) / 128, 128, 0, s>>>(sums, c, out);
     DISCO_CHECK_CUDA(cudaGetLastError());
     return DISCO_OK;

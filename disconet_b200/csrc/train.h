@@ -56,6 +56,25 @@ int disco_nchw_to_nhwc_launch(const float* src, int n, int c, int h, int w, floa
 // dst[i] += src[i]  /  dst[i] = a[i] + b[i]
 int disco_add_f32_launch(float* dst, const float* a, const float* b, long long n, void* stream);
 
+// Raw conv weights (fp32 OIHW) -> the bf16x3 UMMA operand image disco_conv_forward consumes (same layout as
+// disconet_b200/plan.py::pack_conv).  The weights change with every optimizer step, so a training step re-packs
+// every layer: one launch per layer instead of a dozen host-side tensor ops.
+//   transpose = 0: forward weights        B[n = co][k = ci][tap]
+//   transpose = 1: data-gradient weights  B[n = ci - c0][k = co][tap'] = W[co][ci][taps-1-tap']  (flipped taps)
+struct disco_pack_desc {
+    const float* w;          // [co_src][ci_src][taps]
+    int co_src, ci_src, taps;
+    int transpose;
+    int c0;                  // transpose: first input channel of the slice
+    int n_real;              // rows of B that are real (forward: co_src; transpose: slice width)
+    int k_pad;               // padded K channels (multiple of c_blk)
+    int block_n, c_blk, n_tiles, stacked;
+    void* wpack;             // [n_tile][k_pad/c_blk][tap][part][c_blk/8][block_n][8] (stacked: [..][c_blk/8][part][..])
+    const float* bias_src;   // optional [n_real]
+    float* bias;             // optional [n_tiles*block_n]: bias_src zero-padded (zeros when bias_src is null)
+};
+int disco_pack_weights_launch(const disco_pack_desc* d, void* stream);
+
 // Weight gradient of a 3x3 / 1x1 conv:  dW[co][tap][ci] = sum_pixels dz[p][co] * x[p (+) tap][ci]
 // on the tensor cores (MN-major operands: both dz and x are pixel-major NHWC, the contraction runs over pixels).
 struct disco_wgrad_desc {
@@ -106,13 +125,15 @@ struct disco_pwf_train_desc {
     int only_v2i;
     float trans_scale;
     // forward products
-    float* pstats;              // [B*A*A][3][168]: per pair (b, ego i, neighbour id j) mean | rstd | biased var
+    double* psum;               // [B*A*A][2][168]: per pair (b, ego i, neighbour id j) sum | sum of squares of the three
+                                // pre-BatchNorm activations (written by the forward, read by the backward)
     float* wlogit;              // [B, A, A, h, w] post-ReLU PWF output w_k (unflipped frame), 0 for unused pairs
     // backward
     const float* dfused;        // [A*B, h, w, C] fp32 gradient wrt the fused map
     float* dwlogit;             // [B, A, A, h, w] gradient wrt wlogit (written by the combine backward)
     float* dfeat;               // [A*B, h, w, C] fp32 gradient wrt the features (accumulated with atomics; zeroed by caller)
     float* den;                 // [A*B, h, w, 2*hid] fp32 gradient wrt `en` (accumulated; zeroed by caller)
+    float* gsum;                // [B*A*A][2][168] backward workspace: per pair sum g | sum g*xhat
     float* dparams;             // [4697] accumulated: dg1[128] dbe1[128] dw2[4096] dg2[32] dbe2[32] dw3[256] dg3[8] dbe3[8] dw4[8] db4[1]
 };
 

@@ -379,7 +379,7 @@ int build_wgeom(const disco_wgrad_desc* d, WGeom* g) {
     const int items = g->mblks * g->nblks;
     int splits = (2 * g_sms + items - 1) / items;
     if (splits > g->n_tiles / 2) splits = g->n_tiles / 2;
-    if (splits > 64) splits = 64;
+    if (splits > 2 * g_sms) splits = 2 * g_sms;
     if (splits < 1) splits = 1;
     g->splits = splits;
     const char* sw = getenv("DISCO_WGRAD_SWAP");

@@ -25,7 +25,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import ops
-from ._lib import (PREC_BF16X3, BnDesc, FusionDesc, PwfTrainDesc, WgradDesc, check, load)
+from ._lib import (PREC_BF16X3, BnDesc, FusionDesc, PackDesc, PwfTrainDesc, WgradDesc, check, load)
 from .plan import ConvPlan, pack_conv
 
 BN_EPS, BN_MOMENTUM = 1e-5, 0.1
@@ -252,27 +252,50 @@ class TrainRunner:
         W'[ci, co, kh, kw] = W[co, c0+ci, k-1-kh, k-1-kw]."""
         return w[:, c0:c0 + cs].flip(2, 3).permute(1, 0, 2, 3).contiguous()
 
-    def _repack(self):
-        """Refresh the packed operand images from the current parameter values (same pointers)."""
+    def _pack(self, plan: ConvPlan, w: torch.Tensor, bias: Optional[torch.Tensor], stream, transpose=False, c0=0,
+              n_real=None):
+        """Device-side re-pack of `w` [co, ci, k, k] (fp32, contiguous) into plan.wpack (+ plan.bias)."""
+        d = PackDesc()
+        d.w = w.data_ptr()
+        d.co_src, d.ci_src, d.taps = w.shape[0], w.shape[1], plan.taps
+        d.transpose, d.c0 = int(transpose), c0
+        d.n_real = plan.c_out if n_real is None else n_real
+        d.k_pad, d.block_n, d.c_blk = plan.c_in, plan.block_n, plan.c_blk
+        d.n_tiles = (plan.c_out + plan.block_n - 1) // plan.block_n
+        d.stacked = int(plan.stacked)
+        d.wpack = plan.wpack.data_ptr()
+        d.bias_src = bias.data_ptr() if bias is not None else None
+        d.bias = plan.bias.data_ptr() if bias is not None else None
+        check(self.lib.disco_pack_weights(C.byref(d), stream), f"pack_weights[{plan.name}]")
+
+    def _raw_params(self, L: Layer):
+        """(weight [co, ci_real, k, k] contiguous fp32, bias) WITHOUT channel padding (the pack kernel pads)."""
+        if L.name in ("h3", "h1"):
+            return self._conv_params(L)
+        g = self.get
+        return _w4(_f32(g(L.conv + ".weight"))), _f32(g(L.conv + ".bias"))
+
+    def _repack(self, stream=None):
+        """Refresh the packed operand images from the current parameter values (same pointers): one pack_weights
+        launch per forward / data-gradient weight image."""
+        if stream is None:
+            stream = torch.cuda.current_stream(self.dev).cuda_stream
+        keep = self._pack_keep = []
         for L in self.layers:
             S = self.st[L.name]
-            w, b = self._conv_params(L)
-            p = pack_conv(w, b, src_channels=L.c_in, stride=L.stride, relu=False, precision=self.prec, name=L.conv)
-            S.plan.wpack.copy_(p.wpack); S.plan.bias.copy_(p.bias)
+            w, b = self._raw_params(L)
+            keep += [w, b]
+            self._pack(S.plan, w, b, stream)
             c0 = 0
             if L.need_dgrad:
                 for si, cs in enumerate(L.c_in):
-                    dp = pack_conv(self._dgrad_weight(w, c0, cs), torch.zeros(cs, device=w.device), src_channels=[L.c_out],
-                                   stride=1, relu=False, precision=self.prec)
-                    S.dplans[si].wpack.copy_(dp.wpack)
+                    self._pack(S.dplans[si], w, None, stream, transpose=True, c0=c0, n_real=cs)
                     c0 += cs
         if self.fused_key:
             w, b = self._pwf_en_params()
-            p = pack_conv(w, b, src_channels=[self.fuse_c], relu=False, precision=self.prec)
-            self.en_plan.wpack.copy_(p.wpack); self.en_plan.bias.copy_(p.bias)
-            dp = pack_conv(self._dgrad_weight(w, 0, self.fuse_c), torch.zeros(self.fuse_c, device=w.device),
-                           src_channels=[256], relu=False, precision=self.prec)
-            self.en_dplan.wpack.copy_(dp.wpack)
+            keep += [w, b]
+            self._pack(self.en_plan, w, b, stream)
+            self._pack(self.en_dplan, w, None, stream, transpose=True, c0=0, n_real=self.fuse_c)
 
     # ------------------------------------------------------------------------------------------------
     # fusion block
@@ -309,7 +332,8 @@ class TrainRunner:
         self.trans = torch.zeros((B, A, A, 4, 4), dtype=torch.float64, device=dev)
         self.na = torch.zeros((B,), dtype=torch.int32, device=dev)
         self.outage = torch.zeros((B, A), dtype=torch.int32, device=dev)
-        self.pstats = torch.zeros((B * A * A, 3, 168), dtype=torch.float32, device=dev)
+        self.psum = torch.zeros((B * A * A, 2, 168), dtype=torch.float64, device=dev)
+        self.gsum = torch.zeros((B * A * A, 2, 168), dtype=torch.float32, device=dev)
         self.wlogit = torch.zeros((B, A, A, hf, wf), dtype=torch.float32, device=dev)
         self.dwlogit = torch.zeros((B, A, A, hf, wf), dtype=torch.float32, device=dev)
         self.weights = torch.zeros((B, A, A, hf, wf), dtype=torch.float32, device=dev)
@@ -335,7 +359,7 @@ class TrainRunner:
         p.trans, p.num_agent, p.outage = self.trans.data_ptr(), self.na.data_ptr(), self.outage.data_ptr()
         p.B, p.A, p.h, p.w, p.C = B, A, hf, wf, cf
         p.only_v2i, p.trans_scale = int(bool(self.only_v2i)), 4.0 / 128.0
-        p.pstats, p.wlogit = self.pstats.data_ptr(), self.wlogit.data_ptr()
+        p.psum, p.wlogit, p.gsum = self.psum.data_ptr(), self.wlogit.data_ptr(), self.gsum.data_ptr()
         p.dfused, p.dwlogit = self.dfused.data_ptr(), self.dwlogit.data_ptr()
         p.dfeat, p.den, p.dparams = self.dfeat.data_ptr(), self.den.data_ptr(), self.dparams.data_ptr()
         self.pwf = p

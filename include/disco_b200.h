@@ -172,6 +172,24 @@ typedef struct disco_bn_desc {
 int disco_bn_train_forward(const disco_bn_desc* d /* host */, void* stream);
 int disco_bn_train_backward(const disco_bn_desc* d /* host */, void* stream);
 
+/* Raw conv weights (fp32 OIHW) -> the bf16x3 operand image of disco_conv_forward (`wpack`), on the device.
+ * transpose = 0: forward weights; 1: data-gradient weights of input channels [c0, c0 + n_real) -- B[n = ci][k = co]
+ * with the taps flipped.  Replaces the host-side packing when the weights change every step (training). */
+typedef struct disco_pack_desc {
+    const float* w;          /* [co_src][ci_src][taps]                                                  */
+    int co_src, ci_src, taps;
+    int transpose;
+    int c0;
+    int n_real;              /* real rows of B (forward: co_src; transpose: slice width)                */
+    int k_pad;               /* padded K channels, multiple of c_blk                                    */
+    int block_n, c_blk, n_tiles, stacked;
+    void* wpack;
+    const float* bias_src;   /* optional [n_real]                                                        */
+    float* bias;             /* optional [n_tiles*block_n] zero-padded copy                              */
+} disco_pack_desc;
+
+int disco_pack_weights(const disco_pack_desc* d /* host */, void* stream);
+
 /* fp32 NHWC gradient tensors a [n_pix, ca] | b [n_pix, cb] (channel-concatenated; b may be NULL with cb = 0)
  * -> activation buffer [n_pix, ca + cb]. */
 int disco_grad_pack(const float* a, int ca, const float* b, int cb, long long n_pix, void* out_hi, long long out_lo_off,
@@ -226,12 +244,13 @@ typedef struct disco_pwf_train_desc {
     int B, A, h, w, C;
     int only_v2i;
     float trans_scale;
-    float* pstats;             /* [B*A*A][3][168] per-pair mean | rstd | biased variance               */
+    double* psum;              /* [B*A*A][2][168] per-pair sum | sum of squares of the pre-BN activations */
     float* wlogit;             /* [B,A,A,h,w] PWF output maps (post-ReLU), 0 for unused pairs          */
     const float* dfused;       /* backward: [A*B,h,w,C] fp32 gradient wrt the fused map                */
     float* dwlogit;            /* [B,A,A,h,w]                                                         */
     float* dfeat;              /* [A*B,h,w,C] fp32, accumulated (caller zeroes)                        */
     float* den;                /* [A*B,h,w,2*hid] fp32, accumulated (caller zeroes)                    */
+    float* gsum;               /* [B*A*A][2][168] backward workspace (sum g | sum g*xhat per pair)      */
     float* dparams;            /* [4697] accumulated: dg1 dbe1 dw2 dg2 dbe2 dw3 dg3 dbe3 dw4 db4       */
 } disco_pwf_train_desc;
 

@@ -187,7 +187,7 @@ def test_c_abi_exports_every_declared_symbol():
         hdr = f.read()
     for struct, cls in (("disco_conv_desc", _lib.ConvDesc), ("disco_fusion_desc", _lib.FusionDesc),
                         ("disco_grad_src", _lib.GradSrc), ("disco_bn_desc", _lib.BnDesc),
-                        ("disco_wgrad_desc", _lib.WgradDesc), ("disco_pwf_train_desc", _lib.PwfTrainDesc)):
+                        ("disco_wgrad_desc", _lib.WgradDesc), ("disco_pack_desc", _lib.PackDesc), ("disco_pwf_train_desc", _lib.PwfTrainDesc)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), hdr, flags=re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = []

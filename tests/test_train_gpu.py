@@ -93,6 +93,37 @@ def test_bn_train_forward_backward_matches_torch(cuda_dev):
         assert rel_max(dgam.cpu(), gd.grad) < 1e-4 and rel_max(dbet.cpu(), bd.grad) < 1e-4
 
 
+def test_device_weight_pack_is_bit_identical_to_host_pack(cuda_dev):
+    """disco_pack_weights (device) == plan.pack_conv (host tensor ops) for forward and data-gradient images."""
+    from disconet_b200 import _lib as L
+    from disconet_b200.plan import pack_conv
+    from disconet_b200.train import TrainRunner
+    dev = cuda_dev
+    lib = L.load()
+    rng = np.random.default_rng(3)
+    for (co, ci, k, srcs, stride) in [(32, 13, 3, [16], 1), (64, 32, 3, [32], 2), (256, 768, 3, [512, 256], 1), (48, 64, 1, [64], 1),
+                                      (512, 512, 3, [512], 1), (64, 64, 1, [64], 1)]:
+        w = torch.from_numpy(rng.standard_normal((co, ci, k, k)).astype(np.float32)).to(dev)
+        b = torch.from_numpy(rng.standard_normal(co).astype(np.float32)).to(dev)
+        wp = torch.zeros(co, sum(srcs), k, k, device=dev)
+        wp[:, :ci] = w
+        ref = pack_conv(wp, b, src_channels=srcs, stride=stride, relu=False, precision=P)
+        got = pack_conv(torch.zeros_like(wp), torch.zeros_like(b), src_channels=srcs, stride=stride, relu=False, precision=P)
+        TrainRunner._pack(type("R", (), {"lib": lib})(), got, w, b, _stream(dev))
+        torch.cuda.synchronize()
+        assert torch.equal(got.wpack, ref.wpack) and torch.equal(got.bias, ref.bias), (co, ci, k)
+        if ci == sum(srcs):   # data-gradient image of each source slice
+            c0 = 0
+            for cs in srcs:
+                wt = TrainRunner._dgrad_weight(w, c0, cs)
+                ref = pack_conv(wt, torch.zeros(cs, device=dev), src_channels=[co], relu=False, precision=P)
+                got = pack_conv(torch.zeros_like(wt), torch.zeros(cs, device=dev), src_channels=[co], relu=False, precision=P)
+                TrainRunner._pack(type("R", (), {"lib": lib})(), got, w, None, _stream(dev), transpose=True, c0=c0, n_real=cs)
+                torch.cuda.synchronize()
+                assert torch.equal(got.wpack, ref.wpack), ("dgrad", co, ci, k, c0)
+                c0 += cs
+
+
 # ------------------------------------------------------------------------------------------------------------
 WGRAD_CASES = [
     # (n, h_in, w_in, src channels, ups, c_out, stride, taps, c_in_real)
