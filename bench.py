@@ -137,6 +137,85 @@ def cpu_oracle_rate(seconds_budget: float, threads: int, scenes_per_call: int = 
     return n / dt, n, dt, threads
 
 
+def cpu_oracle_train_ms(threads: int):
+    """One training step (forward + backward, A=5, B=1) of the oracle port on the host cores, in ms."""
+    from oracle import disconet_oracle as O
+    from disconet_b200 import DiscoNet
+    torch.set_num_threads(threads)
+    sd = O.synth_state_dict(DiscoNet(Cfg(), kd_flag=1, num_agent=AGENTS).state_dict(), seed=0)
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+    bev, T, na = synth_inputs(1, seed=100)
+    t0 = time.perf_counter()
+    with O.training(sd):
+        out = O.disconet_forward_graph(sd, bev, T, na, 1, agent_num=AGENTS, return_all=True)
+    loss = out["cls"].square().mean() + out["loc"].square().mean() + out["x_7"].mean() + out["x_6"].mean() + out["x_5"].mean() + out["fused"].mean()
+    loss.backward()
+    return (time.perf_counter() - t0) * 1e3
+
+
+def train_leg(dev, dist, world, steps: int, warmup: int, scenes: int = 4):
+    """Training step of the same model (BASELINE configs[2] per-GPU batch: 4 scenes x 5 agents): DiscoNet(kd_flag=1)
+    in train() mode -- batch-statistics BatchNorm forward, backward of a synthetic loss over cls/loc/x_7/x_6/x_5/fused
+    (the tensors FaFModule.step differentiates, CoDetModule.py:249-291,340-382), Adam step -- plus, timed separately,
+    the KD teacher's eval forward.  With several ranks the model is wrapped in DistributedDataParallel (scene-sharded,
+    NCCL all-reduce of the gradients)."""
+    from disconet_b200 import DiscoNet, TeacherNet
+    from disconet_b200 import synth as O
+    rank = int(os.environ.get("RANK", "0"))
+    m = DiscoNet(Cfg(), kd_flag=1, num_agent=AGENTS)
+    m.load_state_dict(O.synth_state_dict(m.state_dict(), seed=0))
+    m = m.to(dev).train()
+    net = m
+    if dist:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        net = DDP(m, device_ids=[dev.index], find_unused_parameters=True)   # the reference model owns dead parameters
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+    teacher = TeacherNet(Cfg())
+    teacher.load_state_dict(O.synth_state_dict(teacher.state_dict(), seed=1))
+    teacher = teacher.to(dev).eval()
+    bev, T, na = synth_inputs(scenes, seed=300 + rank)
+    bev, na = bev.to(dev), na.to(dev)
+
+    def step():
+        res, x8, x7, x6, x5, fused = net(bev, T, na, batch_size=scenes)
+        loss = res["cls"].square().mean() + res["loc"].square().mean() + x7.mean() + x6.mean() + x5.mean() + fused.mean()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    if dist:
+        import torch.distributed as td
+        td.barrier()
+    torch.cuda.synchronize()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    with torch.no_grad():
+        for _ in range(steps):
+            teacher(bev)
+    e2.record()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3
+    ms = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2)], device=dev)
+    if dist:
+        td.all_reduce(ms, op=td.ReduceOp.MAX)
+    ms_step, ms_teacher = ms[0].item() / steps, ms[1].item() / steps
+    return {
+        "metric": "scenes/sec, training step", "value": world * scenes / (ms_step / 1e3), "unit": "scenes/s",
+        "ms_per_step": ms_step, "teacher_forward_ms": ms_teacher, "scenes_per_step_per_gpu": scenes, "steps": steps,
+        "algorithmic_tflops": 3 * ALGO_GFLOP_PER_SCENE * scenes / ms_step,
+        "config": "DiscoNet kd_flag=1 train(): forward (batch-stat BN) + backward + Adam on a synthetic loss over "
+                  "cls/loc/x_7/x_6/x_5/fused; 5 agents, 256x256x13" + ("; DistributedDataParallel over scenes" if dist else ""),
+        "loss": float(loss.detach()), "wall_ms_per_step_incl_teacher": wall / steps,
+    }
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; the Python
     reference cannot travel to the GPU box), all host threads, one scene per step."""
@@ -180,6 +259,7 @@ def main():
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "fp16"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
     ap.add_argument("--layer-table", default=None, help="write the per-launch timing table (csv) here")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -289,6 +369,17 @@ def main():
                 f.write(f"{c.plan.name},{c.flops / 1e9:.3f},{m:.4f},{c.flops / 1e9 / m:.1f},{passes * c.flops / 1e9 / m:.1f}\n")
             f.write(f"TOTAL,{conv_flops / 1e9:.3f},{conv_ms:.4f},{conv_flops / 1e9 / conv_ms:.1f},{passes * conv_flops / 1e9 / conv_ms:.1f}\n")
 
+    # ---------------- training step (a12) -------------------------------------------------------------
+    train = None
+    if not args.no_train and args.precision == "bf16x3":
+        del pipe, bev_pin
+        model._ws.clear()
+        torch.cuda.empty_cache()
+        try:
+            train = train_leg(dev, dist, world, steps=max(3, min(args.steps, 10)), warmup=3)
+        except Exception as e:   # the headline (eval) numbers above stay valid
+            train = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     if rank != 0:
         if dist:
             td.destroy_process_group()
@@ -306,6 +397,8 @@ def main():
         v, n, dt, threads = cpu_oracle_rate(12.0, 0)
         cpu = {"value": v, "unit": "scenes/s", "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
                "sample": f"{n} scenes in {dt:.1f}s (A=5, 256x256x13, fp32 eval, oracle port of the reference torch CPU path)"}
+        if train is not None and "error" not in train:
+            train["cpu_port_ms_per_scene"] = cpu_oracle_train_ms(threads)
     line = {
         "metric": "scenes/sec", "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -327,6 +420,7 @@ def main():
                      "note": "algorithmic FLOPs (159.38 GF/scene); bf16x3 executes 3 MMA passes per product",
                      "conv_ms_per_step": conv_ms},
         "cpu_baseline": cpu,
+        "train": train,
     }
     print(json.dumps(line), flush=True)
     if dist:
