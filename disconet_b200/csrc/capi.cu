@@ -81,6 +81,19 @@ int disco_fusion_forward(const disco_fusion_desc* d, void* stream) {
     return disco_fusion_launch(d, stream);
 }
 
+// ---- BEV segmentation U-Net ---------------------------------------------------------------
+int disco_maxpool2(const void* src_hi, long long src_lo_off, void* dst_hi, long long dst_lo_off, int precision, int n, int h,
+                   int w, int c, void* stream) {
+    return disco_maxpool2_launch(src_hi, src_lo_off, dst_hi, dst_lo_off, precision, n, h, w, c, stream);
+}
+int disco_upsample_bilinear2x(const void* src_hi, long long src_lo_off, void* dst_hi, long long dst_lo_off, int precision, int n,
+                              int h, int w, int c, void* stream) {
+    return disco_upsample_bilinear2x_launch(src_hi, src_lo_off, dst_hi, dst_lo_off, precision, n, h, w, c, stream);
+}
+int disco_nhwc_to_nchw(const float* src, int n, int h, int w, int c_src, int c, float* dst, void* stream) {
+    return disco_nhwc_to_nchw_launch(src, n, h, w, c_src, c, dst, stream);
+}
+
 // ---- training mode ----------------------------------------------------------------------
 int disco_bn_train_forward(const disco_bn_desc* d, void* stream) {
     if (!d) { disco_set_error("null descriptor"); return DISCO_EINVAL; }

@@ -46,3 +46,10 @@ int disco_voxelize_launch(const float* points, int n_points, int point_stride, c
                           int* n_voxels, float* dense, void* stream);
 int disco_bev_scatter_launch(const int* voxel_indices, int n_voxels, const int* dims, float* bev_f32, void* act_hi,
                              int act_c, int precision, void* stream);
+
+// BEV-segmentation U-Net data movement (seg.cu)
+int disco_maxpool2_launch(const void* src_hi, long long src_lo_off, void* dst_hi, long long dst_lo_off, int precision, int n,
+                          int h, int w, int c, void* stream);
+int disco_upsample_bilinear2x_launch(const void* src_hi, long long src_lo_off, void* dst_hi, long long dst_lo_off, int precision,
+                                     int n, int h, int w, int c, void* stream);
+int disco_nhwc_to_nchw_launch(const float* src, int n, int h, int w, int c_src, int c, float* dst, void* stream);

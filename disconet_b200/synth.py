@@ -22,8 +22,7 @@ def synth_state_dict(template: dict, seed: int = 0) -> dict:
             v = rng.normal(0, 0.1, shape).astype(np.float32)
         elif k.endswith("running_var"):
             v = rng.uniform(0.5, 1.5, shape).astype(np.float32)
-        elif len(shape) == 1 and (".bn" in k or "bn_" in k or k.endswith("box_prediction.1.weight")
-                                  or k.endswith("box_prediction.1.bias")):
+        elif len(shape) == 1 and (k.rsplit(".", 1)[0] + ".running_mean") in template:   # BatchNorm affine
             v = (rng.uniform(0.5, 1.5, shape) if k.endswith("weight") else rng.normal(0, 0.1, shape)).astype(np.float32)
         else:
             if len(shape) > 1:

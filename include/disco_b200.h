@@ -128,6 +128,17 @@ typedef struct disco_fusion_desc {
 
 int disco_fusion_forward(const disco_fusion_desc* d /* host */, void* stream);
 
+/* ---- BEV segmentation U-Net (models/seg/SegModelBase.py) around disco_conv_forward ------------------------
+ * nn.MaxPool2d(2) of the Down blocks (:113-123): activation buffer [n,h,w,c] -> [n,h/2,w/2,c]. */
+int disco_maxpool2(const void* src_hi, long long src_lo_off, void* dst_hi, long long dst_lo_off, int precision, int n, int h,
+                   int w, int c, void* stream);
+/* nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True) of the Up blocks (:126-142): [n,h,w,c] -> [n,2h,2w,c];
+ * the torch.cat([skip, up]) that follows is the two-source gather of disco_conv_forward. */
+int disco_upsample_bilinear2x(const void* src_hi, long long src_lo_off, void* dst_hi, long long dst_lo_off, int precision, int n,
+                              int h, int w, int c, void* stream);
+/* fp32 NHWC [n,h,w,c_src] -> fp32 NCHW [n,c,h,w] (first c channels): layout of the logits OutConv returns (:145-151). */
+int disco_nhwc_to_nchw(const float* src, int n, int h, int w, int c_src, int c, float* dst, void* stream);
+
 /* ======================================================================================================
  * Training mode: replaces, for model.train(), the batch-statistics F.batch_norm calls of
  * Backbone.encode/decode + heads + PixelWeightedFusionSoftmax and torch.autograd's backward of the whole path

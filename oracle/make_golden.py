@@ -36,6 +36,27 @@ TRAIN_CASES = {
 TRAIN_OUT_KEYS = ("cls", "loc", "x_8", "x_7", "x_6", "x_5", "fused")
 
 
+# BEV segmentation DiscoNet (f1 / BASELINE config 5), eval forward through the live reference
+SEG_CASES = {
+    "seg_a2_b1": dict(A=2, B=1, num_agent=[2], only_v2i=False, seed=51),
+    "seg_a4_b1_absent_v2i": dict(A=4, B=1, num_agent=[3], only_v2i=True, seed=52),
+}
+SEG_KEYS = ("logits", "x9", "x8", "x7", "x6", "x5", "feat")
+SEG_STRIDES = {"logits": 499, "x9": 1999, "x8": 1999, "x7": 997, "x6": 499, "x5": 251, "feat": 251}
+
+
+def seg_case_inputs(case: dict, template_sd: dict):
+    A, B = case["A"], case["B"]
+    sd = O.synth_state_dict(template_sd, seed=case["seed"])
+    bev = O.synth_bev(A * B, seed=case["seed"] + 100)[:, 0].permute(0, 3, 1, 2).contiguous()   # [N, 13, H, W]
+    na = torch.tensor([[n] * A for n in case["num_agent"]])
+    for b, n in enumerate(case["num_agent"]):
+        for a in range(n, A):
+            bev[a * B + b] = 0
+    T = O.synth_poses(B, A, num_agent=case["num_agent"], seed=case["seed"] + 200)
+    return sd, bev, T, na
+
+
 def grad_digest(named: dict, stride: int = 499):
     """{name: tensor} -> flat strided subsample + per-tensor [l2 norm, max|.|] table (sorted by name)."""
     subs, table = [], []
@@ -111,6 +132,21 @@ def main():
         rec["buf_sub"], rec["buf_table"] = grad_digest(bufs, stride=7)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
         print(name, "loss", loss.item(), {k: v.shape for k, v in rec.items()})
+
+    from coperception.models.seg.DiscoNet import DiscoNet as RSeg
+    for name, case in SEG_CASES.items():
+        m = RSeg(13, 8, num_agent=case["A"], kd_flag=True, only_v2i=case["only_v2i"]).eval()
+        keys[name] = [[k, list(v.shape)] for k, v in m.state_dict().items()]
+        sd, bev, T, na = seg_case_inputs(case, m.state_dict())
+        m.load_state_dict(sd)
+        with torch.no_grad():
+            out = m(bev, T, na)
+        rec = {}
+        for k, t in zip(SEG_KEYS, out):
+            rec[k + "_sub"], rec[k + "_stats"] = _sub(t, SEG_STRIDES[k])
+            rec[k + "_shape"] = np.array(t.shape)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+        print(name, {k: v.shape for k, v in rec.items() if k.endswith("_shape")})
 
     # FaFNet lower-bound plumbing config (BASELINE config 1): 2 agents, 128x128x13
     m = RFaF(cfg, kd_flag=0, num_agent=2).eval()

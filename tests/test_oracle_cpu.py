@@ -250,3 +250,26 @@ def test_oracle_training_matches_reference_golden(name):
     assert cos >= 0.9995, cos
     bsub, _ = grad_digest({k: v.float() for k, v in bufs.items()}, stride=7)
     assert np.abs(bsub - rec["buf_sub"]).max() <= 2e-4 * np.abs(rec["buf_sub"]).max()
+
+
+# ---- BEV segmentation DiscoNet (f1 / BASELINE config 5): oracle vs the live-reference golden ----
+@pytest.mark.parametrize("name", ["seg_a2_b1", "seg_a4_b1_absent_v2i"])
+def test_seg_oracle_matches_reference_golden(name):
+    from oracle import seg_oracle as S
+    from oracle.make_golden import SEG_CASES, SEG_KEYS, SEG_STRIDES, seg_case_inputs
+    case = SEG_CASES[name]
+    rec = np.load(os.path.join(GOLD, name + ".npz"))
+    sd, bev, T, na = seg_case_inputs(case, _template(name))
+    out = S.seg_disconet_forward(sd, bev, T, na, agent_num=case["A"], only_v2i=case["only_v2i"], return_all=True)
+    for k in SEG_KEYS:
+        _check_sub(name, out[k], rec, k, stride=SEG_STRIDES[k])
+
+
+def test_seg_state_dict_layout_matches_reference():
+    from disconet_b200.seg import SegDiscoNet
+    with open(os.path.join(GOLD, "state_dict_keys.json")) as f:
+        keys = json.load(f)["seg_a2_b1"]
+    m = SegDiscoNet(13, 8, num_agent=2)
+    assert [[k, list(v.shape)] for k, v in m.state_dict().items()] == keys
+    with pytest.raises(ValueError, match="CUDA"):
+        m.eval()(torch.zeros(2, 13, 32, 32), torch.zeros(1, 2, 2, 4, 4), torch.ones(1, 2, dtype=torch.int64))
