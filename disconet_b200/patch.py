@@ -22,6 +22,16 @@ def patch_coperception(classes=("DiscoNet", "FaFNet", "TeacherNet")) -> None:
         sub = sys.modules.get(f"coperception.models.det.{name}")
         if sub is not None:
             setattr(sub, name, getattr(ours, name))
+    # BEV segmentation (tools/seg/*.py do `from coperception.models.seg import *`)
+    try:
+        seg_pkg = importlib.import_module("coperception.models.seg")
+    except Exception:   # the seg package pulls optional dependencies; the detection tools do not need it
+        return
+    from .seg import SegDiscoNet
+    setattr(seg_pkg, "DiscoNet", SegDiscoNet)
+    sub = sys.modules.get("coperception.models.seg.DiscoNet")
+    if sub is not None:
+        setattr(sub, "DiscoNet", SegDiscoNet)
 
 
 if __name__ == "__main__":
