@@ -310,7 +310,8 @@ def main():
     dev = torch.device("cuda", local)
     if dist:
         import torch.distributed as td
-        td.init_process_group("nccl", device_id=dev)
+        import datetime
+        td.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=4))
 
     from disconet_b200 import DiscoNet, _lib
     from disconet_b200 import synth as O
