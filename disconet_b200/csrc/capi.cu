@@ -103,6 +103,10 @@ int disco_bn_train_backward(const disco_bn_desc* d, void* stream) {
     if (!d) { disco_set_error("null descriptor"); return DISCO_EINVAL; }
     return disco_bn_train_backward_launch(d, stream);
 }
+int disco_kd_kl(const float* student, const float* teacher, int n, int c, long long hw, double* loss_sum, float* grad,
+                float grad_scale, void* stream) {
+    return disco_kd_kl_launch(student, teacher, n, c, hw, loss_sum, grad, grad_scale, stream);
+}
 int disco_pack_weights(const disco_pack_desc* d, void* stream) {
     if (!d) { disco_set_error("null descriptor"); return DISCO_EINVAL; }
     return disco_pack_weights_launch(d, stream);

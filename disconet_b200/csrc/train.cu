@@ -434,3 +434,62 @@ int disco_add_f32_launch(float* dst, const float* a, const float* b, long long n
     DISCO_CHECK_CUDA(cudaGetLastError());
     return DISCO_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// KD loss term: nn.KLDivLoss(mean over elements)(log_softmax(student, C), softmax(teacher, C)) of
+// two NCHW fp32 maps, forward value and gradient wrt the student in ONE pass pair (FaFModule.get_kd_loss,
+// CoDetModule.py:334-382, does permute + reshape + log_softmax + softmax + kl_div per map and autograd walks them
+// back: ~15 full passes over the maps; this is 4 reads + 1 write per element).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(kThreads) kd_kl_kernel(const float* __restrict__ s, const float* __restrict__ t, int C, long long hw,
+                                                         long long total, double* loss_sum, float* __restrict__ grad, float gscale) {
+    __shared__ double s_part[kThreads / 32];
+    double local = 0.0;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long img = e / hw, p = e - img * hw;
+        const float* sp = s + img * C * hw + p;
+        const float* tp = t + img * C * hw + p;
+        // pass 1: online max / sum of exponentials of both logit vectors (coalesced: consecutive threads = consecutive pixels)
+        float ms = -INFINITY, mt = -INFINITY, zs = 0.f, zt = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float a = __ldg(sp + (long long)c * hw), b = __ldg(tp + (long long)c * hw);
+            if (a > ms) { zs *= expf(ms - a); ms = a; }
+            zs += expf(a - ms);
+            if (b > mt) { zt *= expf(mt - b); mt = b; }
+            zt += expf(b - mt);
+        }
+        const float lzs = logf(zs), lzt = logf(zt), izs = 1.f / zs, izt = 1.f / zt;
+        // pass 2: KL terms and the gradient (softmax(s) - softmax(t)) * gscale
+        float acc = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float a = __ldg(sp + (long long)c * hw) - ms, b = __ldg(tp + (long long)c * hw) - mt;
+            const float pt = expf(b) * izt;
+            if (pt > 0.f) acc = fmaf(pt, (b - lzt) - (a - lzs), acc);
+            if (grad) grad[img * C * hw + (long long)c * hw + p] = (expf(a) * izs - pt) * gscale;
+        }
+        local += (double)acc;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0;
+        for (int i = 0; i < kThreads / 32; ++i) a += s_part[i];
+        atomicAdd(loss_sum, a);
+    }
+}
+
+}  // namespace
+
+int disco_kd_kl_launch(const float* student, const float* teacher, int n, int c, long long hw, double* loss_sum, float* grad,
+                       float grad_scale, void* stream) {
+    DISCO_REQUIRE(student && teacher && loss_sum && n > 0 && c > 0 && hw > 0, "kd_kl: bad arguments");
+    const long long total = (long long)n * hw;
+    kd_kl_kernel<<<grid_for(total, kThreads, 148 * 8), kThreads, 0, (cudaStream_t)stream>>>(student, teacher, c, hw, total, loss_sum,
+                                                                                           grad, grad_scale);
+    DISCO_CHECK_CUDA(cudaGetLastError());
+    return DISCO_OK;
+}

@@ -75,6 +75,11 @@ struct disco_pack_desc {
 };
 int disco_pack_weights_launch(const disco_pack_desc* d, void* stream);
 
+// KD loss term: sum over elements of softmax(t) * (log softmax(t) - log_softmax(s)) over the channel axis of two
+// NCHW fp32 maps is ADDED to *loss_sum; grad (optional, NCHW) = (softmax(s) - softmax(t)) * grad_scale.
+int disco_kd_kl_launch(const float* student, const float* teacher, int n, int c, long long hw, double* loss_sum, float* grad,
+                       float grad_scale, void* stream);
+
 // Weight gradient of a 3x3 / 1x1 conv:  dW[co][tap][ci] = sum_pixels dz[p][co] * x[p (+) tap][ci]
 // on the tensor cores (MN-major operands: both dz and x are pixel-major NHWC, the contraction runs over pixels).
 struct disco_wgrad_desc {

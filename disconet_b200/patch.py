@@ -22,6 +22,13 @@ def patch_coperception(classes=("DiscoNet", "FaFNet", "TeacherNet")) -> None:
         sub = sys.modules.get(f"coperception.models.det.{name}")
         if sub is not None:
             setattr(sub, name, getattr(ours, name))
+    # KD loss of the training step (FaFModule.get_kd_loss) on the fused kernel
+    try:
+        mod = importlib.import_module("coperception.utils.CoDetModule")
+        from . import kd
+        mod.FaFModule.get_kd_loss = kd.get_kd_loss
+    except Exception:
+        pass
     # BEV segmentation (tools/seg/*.py do `from coperception.models.seg import *`)
     try:
         seg_pkg = importlib.import_module("coperception.models.seg")

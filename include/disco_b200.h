@@ -211,6 +211,13 @@ int disco_channel_sum(const float* src, long long n_pix, int c, double* sums, fl
 int disco_nchw_to_nhwc(const float* src, int n, int c, int h, int w, float* dst, void* stream);
 int disco_add_f32(float* dst, const float* a, const float* b, long long n, void* stream);
 
+/* One KD term of FaFModule.get_kd_loss (utils/CoDetModule.py:334-382): nn.KLDivLoss(mean over elements) between
+ * log_softmax(student) and softmax(teacher) over the channel axis of two NCHW fp32 maps [n, c, hw].  The SUM over elements
+ * is added to *loss_sum (device double, caller zeroes it and divides by n*c*hw); grad (optional, NCHW) receives
+ * (softmax(student) - softmax(teacher)) * grad_scale, i.e. d(mean KL)/d student for grad_scale = 1/(n*c*hw). */
+int disco_kd_kl(const float* student, const float* teacher, int n, int c, long long hw, double* loss_sum, float* grad,
+                float grad_scale, void* stream);
+
 /* Weight gradient dW[co][ci][kh][kw] = sum_pixels dz[p][co] * x[p (+) tap][ci] of a conv layer on the tensor cores
  * (MN-major tcgen05 operands, split-K over pixel tiles). */
 typedef struct disco_wgrad_desc {

@@ -426,3 +426,23 @@ def test_fafnet_training_step_matches_oracle(cuda_dev):
     cos = (a @ b / (a.norm() * b.norm())).item()
     print("fafnet train grads cos", cos)
     assert cos >= 0.999
+
+
+def test_kd_loss_kernel_matches_reference_formula(cuda_dev):
+    """f2: one fused launch == the reference's permute/log_softmax/softmax/KLDivLoss(mean) chain (CoDetModule.py:334-382)."""
+    from disconet_b200.kd import kd_kl_mean
+    dev = cuda_dev
+    rng = np.random.default_rng(9)
+    for (n, c, h, w) in [(2, 64, 32, 32), (1, 256, 16, 24), (3, 128, 8, 8)]:
+        s = torch.from_numpy((rng.standard_normal((n, c, h, w)) * 2).astype(np.float32))
+        t = torch.from_numpy((rng.standard_normal((n, c, h, w)) * 3).astype(np.float32))
+        sd = s.double().requires_grad_(True)
+        ref = torch.nn.KLDivLoss(reduction="mean")(F.log_softmax(sd.permute(0, 2, 3, 1).reshape(-1, c), dim=1),
+                                                   F.softmax(t.double().permute(0, 2, 3, 1).reshape(-1, c), dim=1))
+        (ref * 7.0).backward()
+        sg = s.to(dev).requires_grad_(True)
+        got = kd_kl_mean(sg, t.to(dev))
+        (got * 7.0).backward()
+        torch.cuda.synchronize()
+        assert abs(got.item() - ref.item()) <= 1e-5 * abs(ref.item()), (got.item(), ref.item())
+        assert rel_max(sg.grad.cpu(), sd.grad) < 1e-5
