@@ -168,14 +168,18 @@ __global__ void __launch_bounds__(kWarps * 32, 3) fusion_kernel(const disco_fusi
                 __syncwarp();
                 reinterpret_cast<float4*>(s_h1[warp])[lane] = h1;
                 __syncwarp();
-                float h2 = s_b2[lane];
+                float h2;
+                {   // four independent accumulators: the 128-long FMA chain is otherwise pure latency
+                    float q0 = s_b2[lane], q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll 8
-                for (int c = 0; c < kHid; c += 4) {
-                    const float4 hv = *reinterpret_cast<const float4*>(&s_h1[warp][c]);
-                    h2 = fmaf(s_w2[lane][c], hv.x, h2);
-                    h2 = fmaf(s_w2[lane][c + 1], hv.y, h2);
-                    h2 = fmaf(s_w2[lane][c + 2], hv.z, h2);
-                    h2 = fmaf(s_w2[lane][c + 3], hv.w, h2);
+                    for (int c = 0; c < kHid; c += 4) {
+                        const float4 hv = *reinterpret_cast<const float4*>(&s_h1[warp][c]);
+                        q0 = fmaf(s_w2[lane][c], hv.x, q0);
+                        q1 = fmaf(s_w2[lane][c + 1], hv.y, q1);
+                        q2 = fmaf(s_w2[lane][c + 2], hv.z, q2);
+                        q3 = fmaf(s_w2[lane][c + 3], hv.w, q3);
+                    }
+                    h2 = (q0 + q1) + (q2 + q3);
                 }
                 h2 = fmaxf(h2, 0.f);
                 wk = s_b4;

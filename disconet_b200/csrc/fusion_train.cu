@@ -196,14 +196,18 @@ __global__ void __launch_bounds__(kPW * 32) pwf_fwd_pass_kernel(const disco_pwf_
         __syncwarp();
         reinterpret_cast<float4*>(s.h1[warp])[lane] = make_float4(a1[0], a1[1], a1[2], a1[3]);
         __syncwarp();
-        float z2 = s.b2[lane];
+        float z2;
+        {   // four independent accumulators: the 128-long FMA chain is otherwise pure latency
+            float q0 = s.b2[lane], q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll 8
-        for (int c = 0; c < kHid; c += 4) {
-            const float4 hv = *reinterpret_cast<const float4*>(&s.h1[warp][c]);
-            z2 = fmaf(s.w2[lane][c], hv.x, z2);
-            z2 = fmaf(s.w2[lane][c + 1], hv.y, z2);
-            z2 = fmaf(s.w2[lane][c + 2], hv.z, z2);
-            z2 = fmaf(s.w2[lane][c + 3], hv.w, z2);
+            for (int c = 0; c < kHid; c += 4) {
+                const float4 hv = *reinterpret_cast<const float4*>(&s.h1[warp][c]);
+                q0 = fmaf(s.w2[lane][c], hv.x, q0);
+                q1 = fmaf(s.w2[lane][c + 1], hv.y, q1);
+                q2 = fmaf(s.w2[lane][c + 2], hv.z, q2);
+                q3 = fmaf(s.w2[lane][c + 3], hv.w, q3);
+            }
+            z2 = (q0 + q1) + (q2 + q3);
         }
         if (PASS == 1) {
             sa[0] += z2; sq[0] = fmaf(z2, z2, sq[0]);
@@ -337,14 +341,18 @@ __global__ void __launch_bounds__(kPW * 32, 1) pwf_bwd_pass_kernel(const disco_p
         reinterpret_cast<float4*>(s.h1[warp])[lane] = make_float4(a1[0], a1[1], a1[2], a1[3]);
         reinterpret_cast<float4*>(s.xh1[warp])[lane] = make_float4(xh1[0], xh1[1], xh1[2], xh1[3]);
         __syncwarp();
-        float z2 = s.b2[lane];
+        float z2;
+        {   // four independent accumulators: the 128-long FMA chain is otherwise pure latency
+            float q0 = s.b2[lane], q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll 8
-        for (int c = 0; c < kHid; c += 4) {
-            const float4 hv = *reinterpret_cast<const float4*>(&s.h1[warp][c]);
-            z2 = fmaf(s.w2[lane][c], hv.x, z2);
-            z2 = fmaf(s.w2[lane][c + 1], hv.y, z2);
-            z2 = fmaf(s.w2[lane][c + 2], hv.z, z2);
-            z2 = fmaf(s.w2[lane][c + 3], hv.w, z2);
+            for (int c = 0; c < kHid; c += 4) {
+                const float4 hv = *reinterpret_cast<const float4*>(&s.h1[warp][c]);
+                q0 = fmaf(s.w2[lane][c], hv.x, q0);
+                q1 = fmaf(s.w2[lane][c + 1], hv.y, q1);
+                q2 = fmaf(s.w2[lane][c + 2], hv.z, q2);
+                q3 = fmaf(s.w2[lane][c + 3], hv.w, q3);
+            }
+            z2 = (q0 + q1) + (q2 + q3);
         }
         const int c2 = kHid + lane;
         const float xh2 = (z2 - s.mu[c2]) * s.rs[c2];

@@ -26,74 +26,94 @@ __device__ __forceinline__ float grad_src_load(const disco_grad_src& s, long lon
            __ldg(s.ptr + base + row + s.c_total);
 }
 
-// Generic per-channel reduction skeleton: thread t owns channel(s) c = t % Cb (+ 256*k for C > 256) and pixel lane
-// t / Cb; consecutive threads read consecutive channels (coalesced).  MODE 0: sum z, z^2.  MODE 1: sum g, g*xhat.
+// 8 consecutive channels [c, c+8) of one gradient source at pixel `pix` (2x2 block sum for pooled sources)
+__device__ __forceinline__ void grad_src_add8(const disco_grad_src& s, long long pix, int h, int w, int c, float* g) {
+    if (!s.pool) {
+        const float4* p = reinterpret_cast<const float4*>(s.ptr + pix * s.c_total + s.c_off + c);
+        const float4 a = __ldg(p), b = __ldg(p + 1);
+        g[0] += a.x; g[1] += a.y; g[2] += a.z; g[3] += a.w;
+        g[4] += b.x; g[5] += b.y; g[6] += b.z; g[7] += b.w;
+        return;
+    }
+    const int x = (int)(pix % w);
+    const int y = (int)((pix / w) % h);
+    const long long n = pix / ((long long)w * h);
+    const long long base = ((n * (2 * h) + 2 * y) * (2 * w) + 2 * x) * s.c_total + s.c_off + c;
+    const long long row = (long long)(2 * w) * s.c_total;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float4* p = reinterpret_cast<const float4*>(s.ptr + base + (k >> 1) * row + (k & 1) * s.c_total);
+        const float4 a = __ldg(p), b = __ldg(p + 1);
+        g[0] += a.x; g[1] += a.y; g[2] += a.z; g[3] += a.w;
+        g[4] += b.x; g[5] += b.y; g[6] += b.z; g[7] += b.w;
+    }
+}
+
+// Per-channel reduction over all pixels.  Thread t owns the 8-channel group t % (C/8) and the pixel lane t / (C/8):
+// 16-byte loads, 8 + 8 fp32 accumulators per thread, two pixels in flight per iteration; then a shared-memory
+// reduction over the block's pixel lanes and one double-precision atomic per channel and block.
+// MODE 0: sum z, sum z^2.   MODE 1: sum g, sum g*xhat with g = (sum of gradient sources) * [relu gate].
 template <int MODE>
 __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const disco_bn_desc d, long long M) {
-    __shared__ float s_a[kThreads * 2], s_b[kThreads * 2];
-    const int C = d.c;
-    const int Cb = C < kThreads ? C : kThreads;
-    const int lanes = kThreads / Cb;              // pixel lanes per block
-    const int cpt = (C + kThreads - 1) / kThreads;  // channels per thread (1, or 2 for C = 512)
+    __shared__ float s_a[kThreads * 8 + 8], s_b[kThreads * 8 + 8];
+    const int C = d.c, groups = C >> 3;
     const int t = threadIdx.x;
-    const int lane = t / Cb, c0 = t - lane * Cb;
-    const bool active = lane < lanes;
-    float a[2] = {0.f, 0.f}, b[2] = {0.f, 0.f};
-    if (active) {
-        // kUnroll independent rows per iteration: the loop is latency-bound otherwise (one 4-byte load in flight
-        // per thread); out-of-range rows are predicated off
-        constexpr int kUnroll = 8;
+    const int lanes = kThreads / groups;            // pixel lanes per block (groups <= 64)
+    const int lane = t / groups, c = (t - lane * groups) * 8;
+    float a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = 0.f; b[i] = 0.f; }
+    float mean[8], rstd[8], gam[8], bet[8];
+    if (MODE == 1 && lane < lanes) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { mean[i] = d.stats[c + i]; rstd[i] = d.stats[C + c + i]; gam[i] = d.gamma[c + i]; bet[i] = d.beta[c + i]; }
+    }
+    if (lane < lanes) {
+        constexpr int kUnroll = 2;
         const long long stride = (long long)gridDim.x * lanes;
         for (long long p0 = (long long)blockIdx.x * lanes + lane; p0 < M; p0 += stride * kUnroll) {
+            float z[kUnroll][8], g[kUnroll][8];
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                if (k >= cpt) break;
-                const int c = c0 + k * kThreads;
-                float zv[kUnroll], gv[kUnroll];
+            for (int u = 0; u < kUnroll; ++u) {
+                const long long p = p0 + u * stride;
+                const bool ok = p < M;
 #pragma unroll
-                for (int u = 0; u < kUnroll; ++u) {
-                    const long long p = p0 + u * stride;
-                    const bool ok = p < M;
-                    zv[u] = ok ? __ldg(d.z + p * C + c) : 0.f;
-                    gv[u] = 0.f;
-                    if (MODE == 1 && ok)
-                        for (int s = 0; s < d.n_g; ++s) gv[u] += grad_src_load(d.g[s], p, d.h, d.w, c);
+                for (int i = 0; i < 8; ++i) { z[u][i] = 0.f; g[u][i] = 0.f; }
+                if (ok) {
+                    const float4* zp = reinterpret_cast<const float4*>(d.z + p * C + c);
+                    const float4 z0 = __ldg(zp), z1 = __ldg(zp + 1);
+                    z[u][0] = z0.x; z[u][1] = z0.y; z[u][2] = z0.z; z[u][3] = z0.w;
+                    z[u][4] = z1.x; z[u][5] = z1.y; z[u][6] = z1.z; z[u][7] = z1.w;
+                    if (MODE == 1)
+                        for (int s = 0; s < d.n_g; ++s) grad_src_add8(d.g[s], p, d.h, d.w, c, g[u]);
                 }
                 if (MODE == 0) {
 #pragma unroll
-                    for (int u = 0; u < kUnroll; ++u) {
-                        a[k] += zv[u];
-                        b[k] = fmaf(zv[u], zv[u], b[k]);
-                    }
-                } else {
-                    const float mean = d.stats[c], rstd = d.stats[C + c], gam = d.gamma[c], bet = d.beta[c];
+                    for (int i = 0; i < 8; ++i) { a[i] += z[u][i]; b[i] = fmaf(z[u][i], z[u][i], b[i]); }
+                } else if (ok) {
 #pragma unroll
-                    for (int u = 0; u < kUnroll; ++u) {
-                        const float xh = (zv[u] - mean) * rstd;
-                        float g = gv[u];
-                        if (d.relu && fmaf(xh, gam, bet) <= 0.f) g = 0.f;
-                        a[k] += g;
-                        b[k] = fmaf(g, xh, b[k]);
+                    for (int i = 0; i < 8; ++i) {
+                        const float xh = (z[u][i] - mean[i]) * rstd[i];
+                        float gi = g[u][i];
+                        if (d.relu && fmaf(xh, gam[i], bet[i]) <= 0.f) gi = 0.f;
+                        a[i] += gi;
+                        b[i] = fmaf(gi, xh, b[i]);
                     }
                 }
             }
         }
     }
-    for (int k = 0; k < cpt; ++k) {
-        s_a[k * kThreads + t] = a[k];
-        s_b[k * kThreads + t] = b[k];
+    // [lane][channel] in shared memory (channel fastest: the final sum over lanes reads conflict-free)
+    if (lane < lanes) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s_a[lane * C + c + i] = a[i]; s_b[lane * C + c + i] = b[i]; }
     }
     __syncthreads();
-    if (t < Cb) {
-        for (int k = 0; k < cpt; ++k) {
-            double sa = 0.0, sb = 0.0;
-            for (int l = 0; l < lanes; ++l) {
-                sa += (double)s_a[k * kThreads + l * Cb + t];
-                sb += (double)s_b[k * kThreads + l * Cb + t];
-            }
-            atomicAdd(d.sums + t + k * kThreads, sa);
-            atomicAdd(d.sums + C + t + k * kThreads, sb);
-        }
+    for (int ch = t; ch < C; ch += kThreads) {
+        double sa = 0.0, sb = 0.0;
+        for (int l = 0; l < lanes; ++l) { sa += (double)s_a[l * C + ch]; sb += (double)s_b[l * C + ch]; }
+        atomicAdd(d.sums + ch, sa);
+        atomicAdd(d.sums + C + ch, sb);
     }
 }
 
@@ -184,18 +204,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const disco_bn_d
         const float4 z1 = __ldg(reinterpret_cast<const float4*>(d.z + p * C + c + 4));
         const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
         float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int s = 0; s < d.n_g; ++s) {
-            const disco_grad_src& gs = d.g[s];
-            if (!gs.pool) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(gs.ptr + p * gs.c_total + gs.c_off + c));
-                const float4 b = __ldg(reinterpret_cast<const float4*>(gs.ptr + p * gs.c_total + gs.c_off + c + 4));
-                g[0] += a.x; g[1] += a.y; g[2] += a.z; g[3] += a.w;
-                g[4] += b.x; g[5] += b.y; g[6] += b.z; g[7] += b.w;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) g[i] += grad_src_load(gs, p, d.h, d.w, c + i);
-            }
-        }
+        for (int s = 0; s < d.n_g; ++s) grad_src_add8(d.g[s], p, d.h, d.w, c, g);
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -344,8 +353,7 @@ int grid_for(long long work_items, int per_block, int cap_blocks = 148 * 8) {
 int check_bn(const disco_bn_desc* d) {
     DISCO_REQUIRE(d && d->z && d->gamma && d->beta && d->sums && d->stats, "bn: null tensor");
     DISCO_REQUIRE(d->c >= 8 && d->c % 8 == 0 && d->c <= kMaxC, "bn: channels %d unsupported", d->c);
-    DISCO_REQUIRE((d->c <= kThreads && kThreads % d->c == 0) || d->c == 2 * kThreads,
-                  "bn: channels %d must divide %d (or be %d)", d->c, kThreads, 2 * kThreads);
+    DISCO_REQUIRE(kThreads % (d->c / 8) == 0, "bn: channels/8 = %d must divide %d", d->c / 8, kThreads);
     DISCO_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0, "bn: empty input");
     return DISCO_OK;
 }
@@ -359,8 +367,8 @@ int disco_bn_train_forward_launch(const disco_bn_desc* d, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const long long M = (long long)d->n * d->h * d->w;
     DISCO_CHECK_CUDA(cudaMemsetAsync(d->sums, 0, sizeof(double) * 2 * d->c, s));
-    const int lanes = d->c < kThreads ? kThreads / d->c : 1;
-    bn_reduce_kernel<0><<<grid_for(M, lanes * 16, 148 * 4), kThreads, 0, s>>>(*d, M);
+    const int lanes = kThreads / (d->c / 8);
+    bn_reduce_kernel<0><<<grid_for(M, lanes * 4, 148 * 4), kThreads, 0, s>>>(*d, M);
     bn_finalize_kernel<<<(d->c + 127) / 128, 128, 0, s>>>(*d, M);
     bn_apply_kernel<<<grid_for(M * (d->c / 8), kThreads * 4), kThreads, 0, s>>>(*d, M);
     DISCO_CHECK_CUDA(cudaGetLastError());
@@ -378,8 +386,8 @@ int disco_bn_train_backward_launch(const disco_bn_desc* d, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const long long M = (long long)d->n * d->h * d->w;
     DISCO_CHECK_CUDA(cudaMemsetAsync(d->sums, 0, sizeof(double) * 2 * d->c, s));
-    const int lanes = d->c < kThreads ? kThreads / d->c : 1;
-    bn_reduce_kernel<1><<<grid_for(M, lanes * 16, 148 * 4), kThreads, 0, s>>>(*d, M);
+    const int lanes = kThreads / (d->c / 8);
+    bn_reduce_kernel<1><<<grid_for(M, lanes * 4, 148 * 4), kThreads, 0, s>>>(*d, M);
     bn_bwd_apply_kernel<<<grid_for(M * (d->c / 8), kThreads * 4), kThreads, 0, s>>>(*d, M);
     DISCO_CHECK_CUDA(cudaGetLastError());
     return DISCO_OK;
