@@ -599,11 +599,18 @@ int check_desc(const disco_pwf_train_desc* d) {
     return DISCO_OK;
 }
 
+// once per (kernel, device): keeps attribute calls out of CUDA-graph captures of later steps
 template <typename K>
 int set_smem_attr(K kernel) {
+    static const void* seen[16 * 8];     // (kernel, device) pairs already configured (8 kernels here)
+    static int n_seen = 0;
     int dev = 0;
     DISCO_CHECK_CUDA(cudaGetDevice(&dev));
+    const void* key = reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(kernel) ^ ((uintptr_t)(dev + 1) << 48));
+    for (int i = 0; i < n_seen; ++i)
+        if (seen[i] == key) return DISCO_OK;
     DISCO_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairSmem)));
+    if (n_seen < 16 * 8) seen[n_seen++] = key;
     return DISCO_OK;
 }
 

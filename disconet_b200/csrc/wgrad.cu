@@ -25,7 +25,8 @@
 namespace {
 
 constexpr int kProdThreads = 128;
-constexpr int kThreads = kProdThreads + 32;
+constexpr int kIssuers = 2;     // MMA-issuing warps; each owns a disjoint set of taps (= of TMEM accumulators)
+constexpr int kThreads = kProdThreads + 32 * kIssuers;
 constexpr int kMaxStages = 4;
 constexpr int kCtlBytes = 128;
 
@@ -93,9 +94,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WGeom g) {
     if (tid == 0) {
         for (int s = 0; s < g.stages; ++s) {
             mbar_init(smem_u32(&ctl->full[s]), kProdThreads);
-            mbar_init(smem_u32(&ctl->empty[s]), 1);
+            mbar_init(smem_u32(&ctl->empty[s]), TAPS > 1 ? kIssuers : 1);
         }
-        mbar_init(smem_u32(&ctl->acc_full), 1);
+        mbar_init(smem_u32(&ctl->acc_full), TAPS > 1 ? kIssuers : 1);
         fence_mbar_init();
     }
     if (warp == 4) {
@@ -208,7 +209,14 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WGeom g) {
         }
         tc_fence_before();
     } else {
-        // =========================== MMA issuer ===================================================
+        // =========================== MMA issuers ==================================================
+        // One issuing thread sustains only ~80 cycles per small tcgen05.mma here (measured on the forward kernel,
+        // profiles/r01_mma_issue_rate.txt); two warps issuing to DISJOINT accumulators (taps 0-4 / 5-8) reach the
+        // shared-memory operand-port pace.  1x1 layers have a single accumulator: one issuer.
+        const int iss = warp - 4;
+        if (TAPS == 1 && iss > 0) goto done;
+        const int tap_lo = (TAPS == 1) ? 0 : (iss == 0 ? 0 : 5);
+        const int tap_hi = (TAPS == 1) ? 1 : (iss == 0 ? 5 : TAPS);
         const uint32_t idesc = wgrad_idesc(128, g.nb);
         // descriptor halves: lo = start>>4 | (LBO>>4)<<16 ; hi = SBO>>4 | version(1)<<14
         uint32_t a_lbo = 128u >> 4, a_sbo = (uint32_t)g.plane_a >> 4;
@@ -233,6 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WGeom g) {
                     const uint32_t b_ks = sb + (uint32_t)(2 * ks) * (uint32_t)g.lbo_b;
 #pragma unroll
                     for (int tap = 0; tap < TAPS; ++tap) {
+                        if (tap < tap_lo || tap >= tap_hi) continue;
                         const int kh = tap / 3, kw = tap - kh * 3;
                         const uint32_t toff = (MODE == 0) ? (uint32_t)(kh * 10 + kw) * 16u
                                             : (MODE == 1) ? (uint32_t)(kw & 1) * (uint32_t)g.parplane + (uint32_t)(kh * 9 + (kw >> 1)) * 16u
@@ -254,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WGeom g) {
         if (elect_one()) umma_commit(smem_u32(&ctl->acc_full));
         __syncwarp();
     }
-
+done:
     tc_fence_before();
     __syncthreads();
     if (warp == 4) tmem_dealloc(tmem_d, (uint32_t)g.tmem_cols);

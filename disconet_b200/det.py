@@ -372,12 +372,14 @@ class DiscoNet(_DetBase):
         dev = bevs.device
         N, _, H, W, _ = bevs.shape
         A = self.agent_num
-        key = (N, H, W, B, str(dev), bool(self.only_v2i), self.layer)
+        fused_key = "x3f" if self.layer == 3 else "x2f"
+        kd_keys = ["x8", "x7", "x6", "x5", fused_key] if self.kd_flag == 1 else []
+        key = (N, H, W, B, str(dev), bool(self.only_v2i), self.layer, tuple(kd_keys))
         runner = self._runners.get(key)
         if runner is None:
             runner = train_mod.TrainRunner(self._getter(), N, H, W, dev, "u_encoder.", "decoder.", heads=True,
                                            pwf_prefix="pixel_weighted_fusion.", batch_size=B, agents=A,
-                                           fusion_level=self.layer, only_v2i=bool(self.only_v2i))
+                                           fusion_level=self.layer, only_v2i=bool(self.only_v2i), kd_keys=kd_keys)
             self._runners[key] = runner
         runner.get = self._getter()
         outage_host = None
@@ -387,7 +389,6 @@ class DiscoNet(_DetBase):
             for b in range(B):
                 for i in range(int(na_host[b])):
                     outage_host[b, i] = int(self.outage())
-        kd_keys = ["x8", "x7", "x6", "x5", runner.fused_key] if self.kd_flag == 1 else []
         result, maps = self._train_step(runner, bevs, trans_matrices, num_agent_tensor, outage_host, kd_keys)
         if self.kd_flag == 1:
             return (result, *maps)
@@ -433,12 +434,12 @@ class _StpnModel(_DetBase):
             self._ws[key] = ws
         return ws
 
-    def _train_runner(self, bevs, heads: bool):
+    def _train_runner(self, bevs, heads: bool, kd_keys=()):
         N, _, H, W, _ = bevs.shape
-        key = (N, H, W, str(bevs.device), heads)
+        key = (N, H, W, str(bevs.device), heads, tuple(kd_keys))
         runner = self._runners.get(key)
         if runner is None:
-            runner = train_mod.TrainRunner(self._getter(), N, H, W, bevs.device, "stpn.", "stpn.", heads=heads)
+            runner = train_mod.TrainRunner(self._getter(), N, H, W, bevs.device, "stpn.", "stpn.", heads=heads, kd_keys=kd_keys)
             self._runners[key] = runner
         runner.get = self._getter()
         return runner
@@ -460,8 +461,8 @@ class FaFNet(_StpnModel):
     def forward(self, bevs, maps=None, vis=None, batch_size=None):
         if self.training:
             self._check_inputs(bevs)
-            runner = self._train_runner(bevs, heads=True)
             kd_keys = ["x8", "x7", "x6", "x5", "x3"] if self.kd_flag == 1 else []
+            runner = self._train_runner(bevs, heads=True, kd_keys=kd_keys)
             result, maps_ = self._train_step(runner, bevs, None, None, None, kd_keys)
             return (result, *maps_) if self.kd_flag == 1 else result
         ws, stream = self._backbone(bevs)
@@ -481,8 +482,9 @@ class TeacherNet(_StpnModel):
     def forward(self, bevs, maps=None, vis=None):
         if self.training:
             self._check_inputs(bevs)
-            runner = self._train_runner(bevs, heads=False)
-            _, maps_ = self._train_step(runner, bevs, None, None, None, ["x8", "x7", "x6", "x5", "x3", "x4"])
+            kd_keys = ["x8", "x7", "x6", "x5", "x3", "x4"]
+            runner = self._train_runner(bevs, heads=False, kd_keys=kd_keys)
+            _, maps_ = self._train_step(runner, bevs, None, None, None, kd_keys)
             return tuple(maps_)
         ws, _ = self._backbone(bevs)
         return (self._nchw(ws, "x8"), self._nchw(ws, "x7"), self._nchw(ws, "x6"), self._nchw(ws, "x5"),

@@ -19,6 +19,7 @@ Weights are re-packed into the UMMA operand images every step (they change with 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -109,12 +110,20 @@ class _LayerState:
         self.wg: Optional[WgradDesc] = None
 
 
+USE_GRAPH = os.environ.get("DISCO_B200_TRAIN_GRAPH", "1") != "0"
+
+
 class TrainRunner:
-    """Training-mode workspace of one model for one (N, H, W, B) problem size."""
+    """Training-mode workspace of one model for one (N, H, W, B) problem size.
+
+    Every buffer, descriptor and gradient-source wiring is static, so a step is a flat list of prebuilt C-ABI calls
+    (`fwd_ops`, `bwd_ops`: ~150 + ~200 launches) and, after two eager steps, two CUDA-graph replays.  The descriptors
+    hold raw pointers into the parameters; `_signature()` detects re-allocated parameters and rebuilds.
+    """
 
     def __init__(self, get, n: int, h: int, w: int, device, enc_prefix: str, dec_prefix: str, *, heads: bool = True,
                  pwf_prefix: Optional[str] = None, batch_size: int = 1, agents: int = 1, fusion_level: int = 3,
-                 only_v2i: bool = False):
+                 only_v2i: bool = False, kd_keys: Sequence[str] = ()):
         if h % 16 or w % 16:
             raise ValueError(f"BEV size {h}x{w} must be a multiple of 16")
         self.get, self.n, self.h, self.w, self.dev = get, n, h, w, device
@@ -136,13 +145,14 @@ class TrainRunner:
                 Layer("h1", "heads.1x1", None, ["hh"], [0], "", [64], 48, taps=1, level=0),
             ]
         self.layers = E + D + self.head_layers
+        self.kd_keys = tuple(kd_keys)            # activation buffers that may receive an external (NCHW) gradient
         self.res = [(h >> k, w >> k) for k in range(5)]
         self.act: Dict[str, torch.Tensor] = {}
         self.st: Dict[str, _LayerState] = {}
         A_ = lambda hh, ww, c: ops.alloc_act(n, hh, ww, c, self.prec, device)
         self.act["a0"] = A_(h, w, 16)
+        self.bev_in = torch.zeros((n, 1, h, w, 13), dtype=torch.float32, device=device)
         self.sums = torch.zeros(1024, dtype=torch.float64, device=device)
-        max_partial = 0
         for L in self.layers:
             hi, wi = self.res[L.level]
             ho, wo = (hi - 1) // L.stride + 1, (wi - 1) // L.stride + 1
@@ -160,92 +170,61 @@ class TrainRunner:
             self.feat_key = "x3" if fusion_level == 3 else "x2"
             self.fuse_hw, self.fuse_c = (hf, wf), cf
             self.act[self.fused_key] = A_(hf, wf, cf)
-        self._build_static()
-        self.partial = None
-        self._max_partial = max_partial
+        if heads:
+            self.cls = torch.empty((n, h, w, 12), dtype=torch.float32, device=device)
+            self.loc = torch.empty((n, h, w, 36), dtype=torch.float32, device=device)
+            self.gcls, self.gloc = torch.zeros_like(self.cls), torch.zeros_like(self.loc)
+        # external (KD) gradients, converted NCHW -> NHWC into static buffers
+        self.ext: Dict[str, torch.Tensor] = {}
+        self.ext_dirty: Dict[str, bool] = {}
+        for k in self.kd_keys:
+            a = self.act[k]
+            self.ext[k] = torch.zeros(tuple(a.shape[1:]), dtype=torch.float32, device=device)
+            self.ext_dirty[k] = False
+        self._sig = None
+        self._graphs = {"fwd": None, "bwd": None}
+        self._steps = 0
+        self._build()
 
     # ------------------------------------------------------------------------------------------------
-    def _conv_params(self, L: Layer):
-        """(weight [co, ci_pad, k, k], bias [co]) of a layer from the current parameters."""
-        g = self.get
-        if L.name == "h3":
-            w = torch.cat((_f32(g("classification.conv1.weight")), _f32(g("regression.box_prediction.0.weight"))), 0)
-            b = torch.cat((_f32(g("classification.conv1.bias")), _f32(g("regression.box_prediction.0.bias"))), 0)
-        elif L.name == "h1":
-            wc, wr = _f32(g("classification.conv2.weight")), _f32(g("regression.box_prediction.3.weight"))
-            nc, nr, ch = wc.shape[0], wr.shape[0], wc.shape[1]
-            w = torch.zeros(nc + nr, 2 * ch, 1, 1, device=wc.device)
-            w[:nc, :ch] = wc
-            w[nc:, ch:] = wr
-            b = torch.cat((_f32(g("classification.conv2.bias")), _f32(g("regression.box_prediction.3.bias"))), 0)
-        else:
-            w, b = _w4(_f32(g(L.conv + ".weight"))), _f32(g(L.conv + ".bias"))
-        c_pad = sum(L.c_in)
-        if w.shape[1] != c_pad:
-            wp = torch.zeros(w.shape[0], c_pad, w.shape[2], w.shape[3], device=w.device)
-            wp[:, :w.shape[1]] = w
-            w = wp
-        return w, b
+    # parameters
+    def _p(self, name: str) -> torch.Tensor:
+        t = self.get(name)
+        if t.dtype not in (torch.float32, torch.int64) or not t.is_contiguous() or not t.is_cuda:
+            raise ValueError(f"parameter {name} must be a contiguous CUDA fp32 tensor for the training kernels")
+        return t.detach()
 
-    def _bn_params(self, L: Layer):
-        g = self.get
-        if L.name == "h3":
-            names = ("classification.bn1", "regression.box_prediction.1")
-            cat = lambda f: torch.cat([_f32(g(nm + "." + f)) for nm in names], 0)
-            return cat("weight"), cat("bias"), cat("running_mean"), cat("running_var")
-        return (_f32(g(L.bn + ".weight")), _f32(g(L.bn + ".bias")), g(L.bn + ".running_mean"), g(L.bn + ".running_var"))
+    def _signature(self):
+        return tuple(self.get(k).data_ptr() for k in self._ptr_names)
 
-    def _build_static(self):
-        """Allocate packed-weight buffers and prebuild every launch descriptor (pointers stay fixed; the
-        contents of the weight buffers are refreshed each step by `_repack`)."""
-        n = self.n
-        for L in self.layers:
-            S = self.st[L.name]
-            w, b = self._conv_params(L)
-            S.plan = pack_conv(w, b, src_channels=L.c_in, stride=L.stride, relu=False, precision=self.prec, name=L.conv)
-            srcs = [self.act[k] for k in L.srcs]
-            hi, wi = S.hw_in
-            if L.bn:
-                out = (S.z,)
-            else:
-                out = None   # head 1x1: result tensors are supplied per call
-            if out is not None:
-                S.fwd = ops.ConvCall(S.plan, srcs, L.ups, out, n=n, h_in=hi, w_in=wi)
-            # ---- BatchNorm descriptor (pointers to gamma/beta/running stats are refreshed per step) ----
-            if L.bn:
-                d = BnDesc()
-                ho, wo = S.hw_out
-                d.z, d.n, d.h, d.w, d.c = S.z.data_ptr(), n, ho, wo, L.c_out
-                d.momentum, d.eps = BN_MOMENTUM, BN_EPS
-                d.sums, d.stats = self.sums.data_ptr(), S.stats.data_ptr()
-                d.out_hi, d.out_lo_off = self.act[L.out].data_ptr(), ops._lo_off(self.act[L.out])
-                d.relu = 1
-                d.dz_hi, d.dz_lo_off = S.dz.data_ptr(), ops._lo_off(S.dz)
-                S.bn = d
-            # ---- data gradient: one conv per source with the transposed + flipped weights ----------
-            if L.need_dgrad:
-                c0 = 0
-                for si, (key, cs, up) in enumerate(zip(L.srcs, L.c_in, L.ups)):
-                    wt = self._dgrad_weight(w, c0, cs)
-                    dp = pack_conv(wt, torch.zeros(cs, device=w.device), src_channels=[L.c_out], stride=1, relu=False,
-                                   precision=self.prec, name=L.conv + f".dgrad{si}")
-                    gb = torch.empty((n, hi, wi, cs), dtype=torch.float32, device=self.dev)
-                    call = ops.ConvCall(dp, [S.dz], [2 if L.stride == 2 else 0], (gb,), n=n, h_in=hi, w_in=wi)
-                    S.dplans.append(dp); S.dcalls.append(call); S.gbufs.append(gb)
-                    c0 += cs
-            # ---- weight gradient -------------------------------------------------------------------------
-            wg = WgradDesc()
-            for i, s in enumerate(srcs):
-                wg.src[i], wg.src_lo_off[i], wg.src_c[i], wg.src_up[i] = s.data_ptr(), ops._lo_off(s), s.shape[-1], int(L.ups[i])
-            wg.n, wg.h_in, wg.w_in = n, hi, wi
-            wg.h_out, wg.w_out = S.hw_out
-            wg.stride, wg.taps = L.stride, L.taps
-            wg.dz_hi, wg.dz_lo_off, wg.c_out = S.dz.data_ptr(), ops._lo_off(S.dz), L.c_out
-            wg.c_in_real, wg.passes = L.c_in_real, 3
-            S.wg = wg
+    def _special_refresh(self):
+        """Composite weights of the fused heads / PWF conv1_1 halves -> static buffers (plain tensor bookkeeping)."""
+        p = self._p
+        sp = self.sp
+        if self.head_layers:
+            torch.cat((p("classification.conv1.weight"), p("regression.box_prediction.0.weight")), 0, out=sp["h3.w"])
+            torch.cat((p("classification.conv1.bias"), p("regression.box_prediction.0.bias")), 0, out=sp["h3.b"])
+            wc, wr = p("classification.conv2.weight"), p("regression.box_prediction.3.weight")
+            sp["h1.w"][:12, :32] = wc
+            sp["h1.w"][12:, 32:] = wr
+            torch.cat((p("classification.conv2.bias"), p("regression.box_prediction.3.bias")), 0, out=sp["h1.b"])
+            for f, key in (("weight", "h3.gamma"), ("bias", "h3.beta"), ("running_mean", "h3.rm"), ("running_var", "h3.rv")):
+                torch.cat((p("classification.bn1." + f), p("regression.box_prediction.1." + f)), 0, out=sp[key])
         if self.fused_key:
-            self._build_fusion()
+            pp, Cc = self.pwf_prefix, self.fuse_c
+            w1 = p(pp + "conv1_1.weight")                # [128, 2C, 1, 1]
+            sp["en.w"][:128] = w1[:, :Cc]
+            sp["en.w"][128:] = w1[:, Cc:]
+            sp["en.b"][:128] = p(pp + "conv1_1.bias")
 
+    def _h3_writeback(self):
+        sp, g = self.sp, self.get
+        for nm, sl in (("classification.bn1", slice(0, 32)), ("regression.box_prediction.1", slice(32, 64))):
+            g(nm + ".running_mean").copy_(sp["h3.rm"][sl])
+            g(nm + ".running_var").copy_(sp["h3.rv"][sl])
+            g(nm + ".num_batches_tracked").add_(1)
+
+    # ------------------------------------------------------------------------------------------------
     @staticmethod
     def _dgrad_weight(w: torch.Tensor, c0: int, cs: int) -> torch.Tensor:
         """W [co, ci, k, k] -> weights of the data-gradient conv for input channels [c0, c0+cs):
@@ -254,7 +233,12 @@ class TrainRunner:
 
     def _pack(self, plan: ConvPlan, w: torch.Tensor, bias: Optional[torch.Tensor], stream, transpose=False, c0=0,
               n_real=None):
-        """Device-side re-pack of `w` [co, ci, k, k] (fp32, contiguous) into plan.wpack (+ plan.bias)."""
+        """Device-side re-pack of `w` [co, ci, k, k] (fp32, contiguous) into plan.wpack (+ plan.bias), immediately."""
+        d = self._pack_desc(plan, w, bias, transpose, c0, n_real)
+        check(self.lib.disco_pack_weights(C.byref(d), stream), f"pack_weights[{plan.name}]")
+
+    @staticmethod
+    def _pack_desc(plan: ConvPlan, w: torch.Tensor, bias, transpose=False, c0=0, n_real=None) -> PackDesc:
         d = PackDesc()
         d.w = w.data_ptr()
         d.co_src, d.ci_src, d.taps = w.shape[0], w.shape[1], plan.taps
@@ -266,69 +250,227 @@ class TrainRunner:
         d.wpack = plan.wpack.data_ptr()
         d.bias_src = bias.data_ptr() if bias is not None else None
         d.bias = plan.bias.data_ptr() if bias is not None else None
-        check(self.lib.disco_pack_weights(C.byref(d), stream), f"pack_weights[{plan.name}]")
+        return d
 
-    def _raw_params(self, L: Layer):
-        """(weight [co, ci_real, k, k] contiguous fp32, bias) WITHOUT channel padding (the pack kernel pads)."""
-        if L.name in ("h3", "h1"):
-            return self._conv_params(L)
-        g = self.get
-        return _w4(_f32(g(L.conv + ".weight"))), _f32(g(L.conv + ".bias"))
+    # ------------------------------------------------------------------------------------------------
+    def _galloc(self, name: str, shape) -> int:
+        """Reserve a slice of the flat gradient buffer; returns its offset."""
+        numel = 1
+        for s_ in shape:
+            numel *= s_
+        off = self._g_size
+        self._g_index[name] = (off, numel, tuple(shape))
+        self._g_size += (numel + 3) // 4 * 4          # 16-byte aligned slices
+        return off
 
-    def _repack(self, stream=None):
-        """Refresh the packed operand images from the current parameter values (same pointers): one pack_weights
-        launch per forward / data-gradient weight image."""
-        if stream is None:
-            stream = torch.cuda.current_stream(self.dev).cuda_stream
-        keep = self._pack_keep = []
+    def _gview(self, buf: torch.Tensor, name: str) -> torch.Tensor:
+        off, numel, shape = self._g_index[name]
+        return buf[off:off + numel].view(shape)
+
+    def _build(self):
+        """(Re)build packed-weight buffers, descriptors and the flat op lists for the current parameter storage."""
+        n, dev, lib = self.n, self.dev, self.lib
+        p = self._p
+        self._keep = []
+        self._g_index: Dict[str, tuple] = {}
+        self._g_size = 0
+        self._ptr_names: List[str] = []
+        sp = self.sp = {}
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
+        if self.head_layers:
+            sp.update({"h3.w": z(64, 32, 3, 3), "h3.b": z(64), "h1.w": z(48, 64, 1, 1), "h1.b": z(48),
+                       "h3.gamma": z(64), "h3.beta": z(64), "h3.rm": z(64), "h3.rv": z(64)})
+        if self.fused_key:
+            sp.update({"en.w": z(256, self.fuse_c, 1, 1), "en.b": z(256)})
+        self._special_refresh()
+
+        def raw(L: Layer):
+            if L.name in ("h3", "h1"):
+                return sp[L.name + ".w"], sp[L.name + ".b"]
+            self._ptr_names += [L.conv + ".weight", L.conv + ".bias"]
+            return _w4(p(L.conv + ".weight")), p(L.conv + ".bias")
+
+        pre: list = [("py", self._special_refresh)]
+        fwd_layer: Dict[str, list] = {}
+        bwd_layer: Dict[str, list] = {}
+        wg_list: List[WgradDesc] = []
+        # gradient sources per activation buffer: external KD gradients first
+        gsrc: Dict[str, list] = {k: [(self.ext[k], self.ext[k].shape[-1], 0, 0)] for k in self.kd_keys}
+
+        # ---- forward descriptors + packs --------------------------------------------------------------------
         for L in self.layers:
             S = self.st[L.name]
-            w, b = self._raw_params(L)
-            keep += [w, b]
-            self._pack(S.plan, w, b, stream)
-            c0 = 0
+            w, b = raw(L)
+            c_pad = sum(L.c_in)
+            wz = torch.zeros(w.shape[0], c_pad, w.shape[2], w.shape[3], device=dev)
+            S.plan = pack_conv(wz, torch.zeros(w.shape[0], device=dev), src_channels=L.c_in, stride=L.stride, relu=False,
+                               precision=self.prec, name=L.conv)
+            pd = self._pack_desc(S.plan, w, b)
+            pre.append((lib.disco_pack_weights, pd, f"pack[{L.name}]"))
+            srcs = [self.act[k] for k in L.srcs]
+            hi, wi = S.hw_in
+            ho, wo = S.hw_out
+            ops_f = []
+            if L.bn:
+                S.fwd = ops.ConvCall(S.plan, srcs, L.ups, (S.z,), n=n, h_in=hi, w_in=wi)
+            else:
+                S.fwd = ops.ConvCall(S.plan, srcs, L.ups, (self.cls, self.loc), n=n, h_in=hi, w_in=wi, out_split=12)
+            ops_f.append((lib.disco_conv_forward, S.fwd.desc, f"conv[{L.name}]"))
+            if L.bn:
+                d = BnDesc()
+                d.z, d.n, d.h, d.w, d.c = S.z.data_ptr(), n, ho, wo, L.c_out
+                d.momentum, d.eps = BN_MOMENTUM, BN_EPS
+                d.sums, d.stats = self.sums.data_ptr(), S.stats.data_ptr()
+                d.out_hi, d.out_lo_off = self.act[L.out].data_ptr(), ops._lo_off(self.act[L.out])
+                d.relu = 1
+                d.dz_hi, d.dz_lo_off = S.dz.data_ptr(), ops._lo_off(S.dz)
+                if L.name == "h3":
+                    d.gamma, d.beta = sp["h3.gamma"].data_ptr(), sp["h3.beta"].data_ptr()
+                    d.running_mean, d.running_var, d.num_batches_tracked = sp["h3.rm"].data_ptr(), sp["h3.rv"].data_ptr(), None
+                else:
+                    names = [L.bn + f for f in (".weight", ".bias", ".running_mean", ".running_var", ".num_batches_tracked")]
+                    self._ptr_names += names
+                    d.gamma, d.beta = p(names[0]).data_ptr(), p(names[1]).data_ptr()
+                    d.running_mean, d.running_var = p(names[2]).data_ptr(), p(names[3]).data_ptr()
+                    d.num_batches_tracked = p(names[4]).data_ptr()
+                S.bn = d
+                ops_f.append((lib.disco_bn_train_forward, d, f"bn_fwd[{L.name}]"))
+                if L.name == "h3":
+                    ops_f.append(("py", self._h3_writeback))
+            fwd_layer[L.name] = ops_f
+
+        # ---- backward descriptors, in backward order so that the gradient-source lists are complete ------------
+        def wgrad_desc(srcs, ups, hw_in, hw_out, stride, taps, dz, c_out, c_in_real, gname):
+            wg = WgradDesc()
+            for i, s_ in enumerate(srcs):
+                wg.src[i], wg.src_lo_off[i], wg.src_c[i], wg.src_up[i] = s_.data_ptr(), ops._lo_off(s_), s_.shape[-1], int(ups[i])
+            wg.n, wg.h_in, wg.w_in = n, hw_in[0], hw_in[1]
+            wg.h_out, wg.w_out = hw_out
+            wg.stride, wg.taps = stride, taps
+            wg.dz_hi, wg.dz_lo_off, wg.c_out = dz.data_ptr(), ops._lo_off(dz), c_out
+            wg.c_in_real, wg.passes = c_in_real, 3
+            wg._goff = self._galloc(gname, (c_out, c_in_real, taps))
+            wg_list.append(wg)
+            return wg
+
+        def layer_bwd_ops(L: Layer):
+            S = self.st[L.name]
+            out_ops = []
+            if L.bn:
+                d = S.bn
+                srcs = gsrc.get(L.out, [])
+                if not srcs:
+                    raise RuntimeError(f"no gradient reaches {L.out} (kd_keys={self.kd_keys})")
+                if len(srcs) > 3:
+                    raise RuntimeError(f"{L.out}: more than 3 gradient sources")
+                d.n_g = len(srcs)
+                for i, (t, ct, co, pool) in enumerate(srcs):
+                    d.g[i].ptr, d.g[i].c_total, d.g[i].c_off, d.g[i].pool = t.data_ptr(), ct, co, pool
+                d._goff = (self._galloc("_dgamma." + L.name, (L.c_out,)), self._galloc("_dbeta." + L.name, (L.c_out,)))
+                out_ops.append((lib.disco_bn_train_backward, d, f"bn_bwd[{L.name}]"))
+            S.wg = wgrad_desc([self.act[k] for k in L.srcs], L.ups, S.hw_in, S.hw_out, L.stride, L.taps, S.dz, L.c_out,
+                              L.c_in_real, "_dw." + L.name)
+            out_ops.append((lib.disco_conv_wgrad, S.wg, f"wgrad[{L.name}]"))
             if L.need_dgrad:
-                for si, cs in enumerate(L.c_in):
-                    self._pack(S.dplans[si], w, None, stream, transpose=True, c0=c0, n_real=cs)
+                w, _ = raw_cache[L.name]
+                hi, wi = S.hw_in
+                c0 = 0
+                for si, (key, cs, up) in enumerate(zip(L.srcs, L.c_in, L.ups)):
+                    dp = pack_conv(torch.zeros(cs, L.c_out, w.shape[2], w.shape[3], device=dev), torch.zeros(cs, device=dev),
+                                   src_channels=[L.c_out], stride=1, relu=False, precision=self.prec, name=L.conv + f".dgrad{si}")
+                    pre.append((lib.disco_pack_weights, self._pack_desc(dp, w, None, transpose=True, c0=c0, n_real=cs),
+                                f"pack[{L.name}.dgrad{si}]"))
+                    gb = torch.empty((n, hi, wi, cs), dtype=torch.float32, device=dev)
+                    call = ops.ConvCall(dp, [S.dz], [2 if L.stride == 2 else 0], (gb,), n=n, h_in=hi, w_in=wi)
+                    S.dplans.append(dp); S.dcalls.append(call); S.gbufs.append(gb)
+                    out_ops.append((lib.disco_conv_forward, call.desc, f"dgrad[{L.name}.{si}]"))
+                    gsrc.setdefault(key, []).append((gb, cs, 0, 1 if up else 0))
                     c0 += cs
+            return out_ops
+
+        raw_cache = {}
+        for L in self.layers:
+            if L.name in ("h3", "h1"):
+                raw_cache[L.name] = (sp[L.name + ".w"], sp[L.name + ".b"])
+            else:
+                raw_cache[L.name] = (_w4(p(L.conv + ".weight")), p(L.conv + ".bias"))
+
+        bwd: list = []
+        if self.head_layers:
+            S1 = self.st["h1"]
+            npix = n * self.h * self.w
+            ob_c, ob_l = self._galloc("classification.conv2.bias", (12,)), self._galloc("regression.box_prediction.3.bias", (36,))
+            self._head_bias_off = (ob_c, ob_l)
+            bwd.append(("grad_pack_heads", npix))
+            bwd += layer_bwd_ops(self.head_layers[1])
+            bwd += layer_bwd_ops(self.head_layers[0])
+        for L in reversed(self.dec):
+            bwd += layer_bwd_ops(L)
         if self.fused_key:
-            w, b = self._pwf_en_params()
-            keep += [w, b]
-            self._pack(self.en_plan, w, b, stream)
-            self._pack(self.en_dplan, w, None, stream, transpose=True, c0=0, n_real=self.fuse_c)
+            bwd += self._build_fusion(pre, gsrc, wgrad_desc)
+        for L in reversed(self.enc):
+            bwd += layer_bwd_ops(L)
+
+        # ---- flat gradient buffer, wgrad partial workspace, final pointer fix-ups --------------------------------
+        self._galloc("_zero", (512,))
+        self.G = torch.zeros(self._g_size, dtype=torch.float32, device=dev)
+        gbase = self.G.data_ptr()
+        need = 0
+        for wg in wg_list:
+            wg.dw = gbase + 4 * wg._goff
+            wg.partial, wg.splits = None, 0
+            sp_ = lib.disco_conv_wgrad_splits(C.byref(wg))
+            check(sp_, "wgrad_splits")
+            wg.splits = sp_
+            need = max(need, sp_ * wg.c_out * wg.taps * (wg.src_c[0] + wg.src_c[1]))
+        self.partial = torch.empty(need, dtype=torch.float32, device=dev)
+        for wg in wg_list:
+            wg.partial = self.partial.data_ptr()
+        for L in self.layers:
+            d = self.st[L.name].bn
+            if d is not None and hasattr(d, "_goff"):
+                d.dgamma, d.dbeta = gbase + 4 * d._goff[0], gbase + 4 * d._goff[1]
+        if self.fused_key:
+            self.pwf.dparams = gbase + 4 * self._g_index["_pwf.dparams"][0]
+
+        # ---- op lists ---------------------------------------------------------------------------------------------
+        fwd: list = list(pre)
+        fwd.append(("bev_pack",))
+        for L in self.enc:
+            fwd += fwd_layer[L.name]
+        if self.fused_key:
+            fwd += self.ops_fusion_fwd
+        for L in self.dec:
+            fwd += fwd_layer[L.name]
+        for L in self.head_layers:
+            fwd += fwd_layer[L.name]
+        self.ops_pre, self.fwd_ops, self.bwd_ops = pre, fwd, bwd
+        self._ptr_names = sorted(set(self._ptr_names))
+        self._sig = self._signature()
+        self._graphs = {"fwd": None, "bwd": None}
+        self._steps = 0
 
     # ------------------------------------------------------------------------------------------------
     # fusion block
-    def _pwf_en_params(self):
-        g, p = self.get, self.pwf_prefix
-        w1 = _f32(g(p + "conv1_1.weight"))           # [128, 2C, 1, 1]
-        Cc = w1.shape[1] // 2
-        w = torch.cat((w1[:, :Cc], w1[:, Cc:]), 0)   # [256, C, 1, 1]: ego half | neighbour half
-        b1 = _f32(g(p + "conv1_1.bias"))
-        return w, torch.cat((b1, torch.zeros_like(b1)), 0)
-
-    def _build_fusion(self):
-        n, dev, B, A = self.n, self.dev, self.B, self.A
+    def _build_fusion(self, pre, gsrc, wgrad_desc):
+        n, dev, B, A, lib = self.n, self.dev, self.B, self.A, self.lib
+        p, pp, sp = self._p, self.pwf_prefix, self.sp
         hf, wf = self.fuse_hw
         cf = self.fuse_c
         feat = self.act[self.feat_key]
-        w, b = self._pwf_en_params()
-        self.en_plan = pack_conv(w, b, src_channels=[cf], relu=False, precision=self.prec, name="pwf.conv1_1")
+        self.en_plan = pack_conv(torch.zeros(256, cf, 1, 1, device=dev), torch.zeros(256, device=dev), src_channels=[cf], relu=False,
+                                 precision=self.prec, name="pwf.conv1_1")
+        pre.append((lib.disco_pack_weights, self._pack_desc(self.en_plan, sp["en.w"], sp["en.b"]), "pack[en]"))
         self.en = torch.empty((n, hf, wf, 256), dtype=torch.float32, device=dev)
         self.en_call = ops.ConvCall(self.en_plan, [feat], [0], (self.en,), n=n, h_in=hf, w_in=wf)
         self.den = torch.zeros((n, hf, wf, 256), dtype=torch.float32, device=dev)
         self.den_act = ops.alloc_act(n, hf, wf, 256, self.prec, dev)
-        self.en_dplan = pack_conv(self._dgrad_weight(w, 0, cf), torch.zeros(cf, device=dev), src_channels=[256], relu=False,
+        self.en_dplan = pack_conv(torch.zeros(cf, 256, 1, 1, device=dev), torch.zeros(cf, device=dev), src_channels=[256], relu=False,
                                   precision=self.prec, name="pwf.conv1_1.dgrad")
+        pre.append((lib.disco_pack_weights, self._pack_desc(self.en_dplan, sp["en.w"], None, transpose=True, c0=0, n_real=cf),
+                    "pack[en.dgrad]"))
         self.en_gbuf = torch.empty((n, hf, wf, cf), dtype=torch.float32, device=dev)
         self.en_dcall = ops.ConvCall(self.en_dplan, [self.den_act], [0], (self.en_gbuf,), n=n, h_in=hf, w_in=wf)
-        wg = WgradDesc()
-        wg.src[0], wg.src_lo_off[0], wg.src_c[0], wg.src_up[0] = feat.data_ptr(), ops._lo_off(feat), cf, 0
-        wg.n, wg.h_in, wg.w_in, wg.h_out, wg.w_out = n, hf, wf, hf, wf
-        wg.stride, wg.taps = 1, 1
-        wg.dz_hi, wg.dz_lo_off, wg.c_out = self.den_act.data_ptr(), ops._lo_off(self.den_act), 256
-        wg.c_in_real, wg.passes = cf, 3
-        self.en_wg = wg
         self.trans = torch.zeros((B, A, A, 4, 4), dtype=torch.float64, device=dev)
         self.na = torch.zeros((B,), dtype=torch.int32, device=dev)
         self.outage = torch.zeros((B, A), dtype=torch.int32, device=dev)
@@ -339,7 +481,6 @@ class TrainRunner:
         self.weights = torch.zeros((B, A, A, hf, wf), dtype=torch.float32, device=dev)
         self.dfeat = torch.zeros((n, hf, wf, cf), dtype=torch.float32, device=dev)
         self.dfused = torch.zeros((n, hf, wf, cf), dtype=torch.float32, device=dev)
-        self.dparams = torch.zeros(4697, dtype=torch.float32, device=dev)
         f = FusionDesc()
         f.feat_hi, f.feat_lo_off, f.precision = feat.data_ptr(), ops._lo_off(feat), self.prec
         f.hid = 128
@@ -353,247 +494,191 @@ class TrainRunner:
         f.row_begin, f.row_end = 0, n
         f.wpre = self.wlogit.data_ptr()
         self.fusion = f
-        p = PwfTrainDesc()
-        p.feat_hi, p.feat_lo_off, p.en, p.hid = feat.data_ptr(), ops._lo_off(feat), self.en.data_ptr(), 128
-        p.eps, p.momentum = BN_EPS, BN_MOMENTUM
-        p.trans, p.num_agent, p.outage = self.trans.data_ptr(), self.na.data_ptr(), self.outage.data_ptr()
-        p.B, p.A, p.h, p.w, p.C = B, A, hf, wf, cf
-        p.only_v2i, p.trans_scale = int(bool(self.only_v2i)), 4.0 / 128.0
-        p.psum, p.wlogit, p.gsum = self.psum.data_ptr(), self.wlogit.data_ptr(), self.gsum.data_ptr()
-        p.dfused, p.dwlogit = self.dfused.data_ptr(), self.dwlogit.data_ptr()
-        p.dfeat, p.den, p.dparams = self.dfeat.data_ptr(), self.den.data_ptr(), self.dparams.data_ptr()
-        self.pwf = p
+        q = PwfTrainDesc()
+        q.feat_hi, q.feat_lo_off, q.en, q.hid = feat.data_ptr(), ops._lo_off(feat), self.en.data_ptr(), 128
+        q.eps, q.momentum = BN_EPS, BN_MOMENTUM
+        q.trans, q.num_agent, q.outage = self.trans.data_ptr(), self.na.data_ptr(), self.outage.data_ptr()
+        q.B, q.A, q.h, q.w, q.C = B, A, hf, wf, cf
+        q.only_v2i, q.trans_scale = int(bool(self.only_v2i)), 4.0 / 128.0
+        q.psum, q.wlogit, q.gsum = self.psum.data_ptr(), self.wlogit.data_ptr(), self.gsum.data_ptr()
+        q.dwlogit, q.dfeat, q.den = self.dwlogit.data_ptr(), self.dfeat.data_ptr(), self.den.data_ptr()
+        names = {"g1": "bn1_1.weight", "be1": "bn1_1.bias", "w2": "conv1_2.weight", "b2": "conv1_2.bias", "g2": "bn1_2.weight",
+                 "be2": "bn1_2.bias", "w3": "conv1_3.weight", "b3": "conv1_3.bias", "g3": "bn1_3.weight", "be3": "bn1_3.bias",
+                 "w4": "conv1_4.weight", "b4": "conv1_4.bias", "rm1": "bn1_1.running_mean", "rv1": "bn1_1.running_var",
+                 "rm2": "bn1_2.running_mean", "rv2": "bn1_2.running_var", "rm3": "bn1_3.running_mean", "rv3": "bn1_3.running_var",
+                 "nbt1": "bn1_1.num_batches_tracked", "nbt2": "bn1_2.num_batches_tracked", "nbt3": "bn1_3.num_batches_tracked"}
+        for field_, nm in names.items():
+            setattr(q, field_, p(pp + nm).data_ptr())
+            self._ptr_names.append(pp + nm)
+        self._ptr_names += [pp + "conv1_1.weight", pp + "conv1_1.bias"]
+        self.pwf = q
+        self._galloc("_pwf.dparams", (4697,))
+        self.ops_fusion_fwd = [(lib.disco_conv_forward, self.en_call.desc, "conv[en]"),
+                               (lib.disco_pwf_train_forward, q, "pwf_train_forward"),
+                               (lib.disco_fusion_forward, f, "fusion")]
+        # ---- backward ----
+        srcs = gsrc.get(self.fused_key, [])
+        if not srcs or len(srcs) > 2:
+            raise RuntimeError("the fused map needs one or two gradient sources")
+        ops_b = []
+        for (t, ct, co, pl) in srcs:
+            assert ct == cf and co == 0 and pl == 0
+        if len(srcs) == 1:
+            q.dfused = srcs[0][0].data_ptr()
+        else:
+            ops_b.append(("add_f32", self.dfused, srcs[0][0], srcs[1][0]))
+            q.dfused = self.dfused.data_ptr()
+        ops_b.append(("py", self._fusion_zero))
+        ops_b.append((lib.disco_fusion_combine_backward, q, "fusion_combine_backward"))
+        ops_b.append((lib.disco_pwf_train_backward, q, "pwf_train_backward"))
+        ops_b.append(("grad_pack_den", n * hf * wf))
+        self.en_wg = wgrad_desc([feat], [0], (hf, wf), (hf, wf), 1, 1, self.den_act, 256, cf, "_dw.en")
+        ops_b.append((lib.disco_conv_wgrad, self.en_wg, "wgrad[en]"))
+        ops_b.append((lib.disco_conv_forward, self.en_dcall.desc, "dgrad[en]"))
+        gsrc.setdefault(self.feat_key, []).append((self.en_gbuf, cf, 0, 0))
+        gsrc[self.feat_key].append((self.dfeat, cf, 0, 0))
+        self.ops_bwd_fusion = ops_b
+        return ops_b
 
-    def _refresh_pwf_params(self):
-        g, pp, p = self.get, self.pwf_prefix, self.pwf
-        keep = self._pwf_keep = {}
-
-        def ptr(name, reshape=None):
-            t = _f32(g(pp + name))
-            if reshape:
-                t = t.reshape(reshape).contiguous()
-            keep[name] = t
-            return t.data_ptr()
-
-        p.g1, p.be1 = ptr("bn1_1.weight"), ptr("bn1_1.bias")
-        p.w2, p.b2, p.g2, p.be2 = ptr("conv1_2.weight", (32, 128)), ptr("conv1_2.bias"), ptr("bn1_2.weight"), ptr("bn1_2.bias")
-        p.w3, p.b3, p.g3, p.be3 = ptr("conv1_3.weight", (8, 32)), ptr("conv1_3.bias"), ptr("bn1_3.weight"), ptr("bn1_3.bias")
-        p.w4, p.b4 = ptr("conv1_4.weight", (1, 8)), ptr("conv1_4.bias")
-        for k, nm in (("1", "bn1_1"), ("2", "bn1_2"), ("3", "bn1_3")):
-            setattr(p, "rm" + k, g(pp + nm + ".running_mean").data_ptr())
-            setattr(p, "rv" + k, g(pp + nm + ".running_var").data_ptr())
-            setattr(p, "nbt" + k, g(pp + nm + ".num_batches_tracked").data_ptr())
+    def _fusion_zero(self):
+        self.dfeat.zero_(); self.den.zero_()
+        self._gview(self.G, "_pwf.dparams").zero_()
 
     # ------------------------------------------------------------------------------------------------
+    def run_ops(self, op_list, stream):
+        lib = self.lib
+        for op in op_list:
+            f = op[0]
+            if f == "py":
+                op[1]()
+            elif f == "bev_pack":
+                ops.bev_pack(self.bev_in, self.act["a0"], self.prec)
+            elif f == "add_f32":
+                check(lib.disco_add_f32(op[1].data_ptr(), op[2].data_ptr(), op[3].data_ptr(), op[1].numel(), stream), "add_f32")
+            elif f == "grad_pack_heads":
+                S = self.st["h1"]
+                gb = self.G.data_ptr()
+                check(lib.disco_grad_pack(self.gcls.data_ptr(), 12, self.gloc.data_ptr(), 36, op[1], S.dz.data_ptr(),
+                                          ops._lo_off(S.dz), stream), "grad_pack[heads]")
+                check(lib.disco_channel_sum(self.gcls.data_ptr(), op[1], 12, self.sums.data_ptr(), gb + 4 * self._head_bias_off[0],
+                                            stream), "channel_sum")
+                check(lib.disco_channel_sum(self.gloc.data_ptr(), op[1], 36, self.sums.data_ptr(), gb + 4 * self._head_bias_off[1],
+                                            stream), "channel_sum")
+            elif f == "grad_pack_den":
+                check(lib.disco_grad_pack(self.den.data_ptr(), 256, None, 0, op[1], self.den_act.data_ptr(),
+                                          ops._lo_off(self.den_act), stream), "grad_pack[den]")
+            else:
+                check(f(C.byref(op[1]), stream), op[2])
+
+    def _run(self, which: str, op_list, stream):
+        """Eager for the first two steps (lazy kernel attributes, allocator warm-up), then one CUDA-graph replay."""
+        g = self._graphs[which]
+        if USE_GRAPH and g is None and self._steps >= 2 and not torch.cuda.is_current_stream_capturing():
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self.run_ops(op_list, torch.cuda.current_stream(self.dev).cuda_stream)
+                g = self._graphs[which] = graph
+            except Exception:           # capture unsupported in this context: stay eager
+                g = self._graphs[which] = False
+                torch.cuda.synchronize()
+        if g:
+            g.replay()
+        else:
+            self.run_ops(op_list, stream)
+
     def forward(self, bevs: torch.Tensor, trans=None, num_agent=None, outage_host=None):
-        """Runs the training-mode forward; returns dict of result tensors (cls, loc fp32 NHWC) ."""
+        """Runs the training-mode forward; returns {"cls", "loc"} (fp32 NHWC, fresh tensors) when the model has heads."""
         dev = self.dev
+        if self._signature() != self._sig:
+            self._build()                      # parameters were re-allocated (e.g. .to(), new load)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        self._repack()
-        bev = bevs.detach()
-        if bev.dtype != torch.float32:
-            bev = bev.float()
-        ops.bev_pack(bev.contiguous(), self.act["a0"], self.prec)
-        self._keep = []
+        self.bev_in.copy_(bevs.detach().reshape(self.bev_in.shape), non_blocking=True)
         if self.fused_key:
             self.trans.copy_(trans.detach(), non_blocking=True)
             self.na.copy_(num_agent.detach()[:, 0], non_blocking=True)
             if outage_host is not None:
                 self.outage.copy_(outage_host, non_blocking=True)
-            else:
+                self._outage_dirty = True
+            elif getattr(self, "_outage_dirty", False):
                 self.outage.zero_()
-            self._refresh_pwf_params()
-        for L in self.enc:
-            self._layer_fwd(L, stream)
-        if self.fused_key and self.fusion_level in (2, 3):
-            self._fusion_fwd(stream)
-        for L in self.dec:
-            self._layer_fwd(L, stream)
+                self._outage_dirty = False
+        self._run("fwd", self.fwd_ops, stream)
         out = {}
         if self.head_layers:
-            self._layer_fwd(self.head_layers[0], stream)
-            L = self.head_layers[1]
-            S = self.st["h1"]
-            n, h, w = self.n, self.h, self.w
-            cls = torch.empty((n, h, w, 12), dtype=torch.float32, device=dev)
-            loc = torch.empty((n, h, w, 36), dtype=torch.float32, device=dev)
-            call = ops.ConvCall(S.plan, [self.act["hh"]], [0], (cls, loc), n=n, h_in=h, w_in=w, out_split=12)
-            call.launch(stream)
-            out["cls"], out["loc"] = cls, loc
+            out["cls"], out["loc"] = self.cls.clone(), self.loc.clone()
         return out
-
-    def _layer_fwd(self, L: Layer, stream):
-        S = self.st[L.name]
-        S.fwd.launch(stream)
-        gam, bet, rm, rv = self._bn_params(L)
-        self._keep += [gam, bet]
-        d = S.bn
-        d.gamma, d.beta = gam.data_ptr(), bet.data_ptr()
-        if L.name == "h3":
-            # two BatchNorm modules side by side: run on concatenated copies of the running stats, write back
-            self._keep += [rm, rv]
-            d.running_mean, d.running_var, d.num_batches_tracked = rm.data_ptr(), rv.data_ptr(), None
-            check(self.lib.disco_bn_train_forward(C.byref(d), stream), "bn_fwd[h3]")
-            g = self.get
-            for nm, sl in (("classification.bn1", slice(0, 32)), ("regression.box_prediction.1", slice(32, 64))):
-                g(nm + ".running_mean").copy_(rm[sl]); g(nm + ".running_var").copy_(rv[sl])
-                g(nm + ".num_batches_tracked").add_(1)
-        else:
-            d.running_mean, d.running_var = rm.data_ptr(), rv.data_ptr()
-            d.num_batches_tracked = self.get(L.bn + ".num_batches_tracked").data_ptr()
-            check(self.lib.disco_bn_train_forward(C.byref(d), stream), f"bn_fwd[{L.name}]")
-
-    def _fusion_fwd(self, stream):
-        self.en_call.launch(stream)
-        check(self.lib.disco_pwf_train_forward(C.byref(self.pwf), stream), "pwf_train_forward")
-        ops.fusion_forward(self.fusion, stream)
 
     def kd_map(self, key: str) -> torch.Tensor:
         return ops.act_to_nchw_f32(self.act[key], self.prec)
 
     # ------------------------------------------------------------------------------------------------
     def backward(self, grads: Dict[str, Optional[torch.Tensor]]) -> Dict[str, torch.Tensor]:
-        """grads: {"cls": [n,h,w,12] fp32 NHWC, "loc": [n,h,w,36], "x8"/"x7"/"x6"/"x5"/fused_key: NCHW fp32 or None}.
+        """grads: {"cls": [n,h,w,12] fp32 NHWC, "loc": [n,h,w,36], <kd key>: NCHW fp32 or None}.
         Returns {parameter name: gradient}."""
         dev, lib = self.dev, self.lib
         stream = torch.cuda.current_stream(dev).cuda_stream
-        out: Dict[str, torch.Tensor] = {}
-        gsrc: Dict[str, list] = {}
         keep = []
-
-        def add_src(key, t, c_total, c_off, pool):
-            gsrc.setdefault(key, []).append((t, c_total, c_off, pool))
-
-        # external gradients of the KD maps arrive NCHW
         for key, g in grads.items():
-            if key in ("cls", "loc") or g is None:
+            if key in ("cls", "loc"):
                 continue
-            if key not in self.act:
-                raise KeyError(f"no activation buffer {key!r} to receive a gradient")
+            if key not in self.ext:
+                if g is None:
+                    continue
+                raise KeyError(f"no static gradient buffer for {key!r} (kd_keys={self.kd_keys})")
+            if g is None:
+                if self.ext_dirty[key]:
+                    self.ext[key].zero_()
+                    self.ext_dirty[key] = False
+                continue
             g = g.detach().float().contiguous()
             nn_, c, hh, ww = g.shape
-            t = torch.empty((nn_, hh, ww, c), dtype=torch.float32, device=dev)
-            check(lib.disco_nchw_to_nhwc(g.data_ptr(), nn_, c, hh, ww, t.data_ptr(), stream), "nchw_to_nhwc")
-            keep += [g, t]
-            add_src(key, t, c, 0, 0)
-
-        def run_wgrad(wg: WgradDesc, shape) -> torch.Tensor:
-            dw = torch.empty(shape, dtype=torch.float32, device=dev)
-            wg.dw = dw.data_ptr()
-            wg.partial, wg.splits = None, 0
-            need = lib.disco_conv_wgrad_splits(C.byref(wg))
-            check(need, "wgrad_splits")
-            c_in = wg.src_c[0] + wg.src_c[1]
-            numel = need * wg.c_out * wg.taps * c_in
-            if self.partial is None or self.partial.numel() < numel:
-                self.partial = torch.empty(numel, dtype=torch.float32, device=dev)
-            wg.partial, wg.splits = self.partial.data_ptr(), need
-            check(lib.disco_conv_wgrad(C.byref(wg), stream), "wgrad")
-            return dw
-
-        def layer_bwd(L: Layer):
-            S = self.st[L.name]
-            n = self.n
-            if L.bn:
-                d = S.bn
-                srcs = gsrc.get(L.out, [])
-                if not srcs:
-                    raise RuntimeError(f"no gradient reaches {L.out}")
-                d.n_g = len(srcs)
-                for i, (t, ct, co, pool) in enumerate(srcs):
-                    d.g[i].ptr, d.g[i].c_total, d.g[i].c_off, d.g[i].pool = t.data_ptr(), ct, co, pool
-                gam, bet, _, _ = self._bn_params(L)
-                dgam = torch.empty(L.c_out, dtype=torch.float32, device=dev)
-                dbet = torch.empty(L.c_out, dtype=torch.float32, device=dev)
-                keep.extend([gam, bet])
-                d.gamma, d.beta, d.dgamma, d.dbeta = gam.data_ptr(), bet.data_ptr(), dgam.data_ptr(), dbet.data_ptr()
-                check(lib.disco_bn_train_backward(C.byref(d), stream), f"bn_bwd[{L.name}]")
-            dw = run_wgrad(S.wg, (L.c_out, L.c_in_real, L.taps))
-            for call, gb, key, cs, up in zip(S.dcalls, S.gbufs, L.srcs, L.c_in, L.ups):
-                call.launch(stream)
-                add_src(key, gb, cs, 0, 1 if up else 0)
-            k = 3 if L.taps == 9 else 1
-            if L.name == "h3":
-                out["classification.conv1.weight"] = dw[:32].reshape(32, 32, 3, 3)
-                out["regression.box_prediction.0.weight"] = dw[32:].reshape(32, 32, 3, 3)
-                out["classification.bn1.weight"], out["regression.box_prediction.1.weight"] = dgam[:32], dgam[32:]
-                out["classification.bn1.bias"], out["regression.box_prediction.1.bias"] = dbet[:32], dbet[32:]
-                # a conv bias in front of a BatchNorm has an exactly zero gradient
-                out["classification.conv1.bias"] = torch.zeros(32, device=dev)
-                out["regression.box_prediction.0.bias"] = torch.zeros(32, device=dev)
-            elif L.name == "h1":
-                out["classification.conv2.weight"] = dw[:12, :32].reshape(12, 32, 1, 1)
-                out["regression.box_prediction.3.weight"] = dw[12:, 32:].reshape(36, 32, 1, 1)
-            else:
-                pshape = self.get(L.conv + ".weight").shape
-                out[L.conv + ".weight"] = dw.reshape(pshape)
-                out[L.conv + ".bias"] = torch.zeros(L.c_out, device=dev)
-                out[L.bn + ".weight"], out[L.bn + ".bias"] = dgam, dbet
-
-        # ---- heads ------------------------------------------------------------------------------------
+            check(lib.disco_nchw_to_nhwc(g.data_ptr(), nn_, c, hh, ww, self.ext[key].data_ptr(), stream), "nchw_to_nhwc")
+            self.ext_dirty[key] = True
+            keep.append(g)
         if self.head_layers:
-            gc, gl = grads.get("cls"), grads.get("loc")
-            n, h, w = self.n, self.h, self.w
-            gc = torch.zeros((n, h, w, 12), device=dev) if gc is None else gc.detach().float().contiguous()
-            gl = torch.zeros((n, h, w, 36), device=dev) if gl is None else gl.detach().float().contiguous()
-            keep += [gc, gl]
-            S = self.st["h1"]
-            npix = n * h * w
-            check(lib.disco_grad_pack(gc.data_ptr(), 12, gl.data_ptr(), 36, npix, S.dz.data_ptr(), ops._lo_off(S.dz), stream),
-                  "grad_pack[heads]")
-            bc = torch.empty(12, dtype=torch.float32, device=dev)
-            bl = torch.empty(36, dtype=torch.float32, device=dev)
-            check(lib.disco_channel_sum(gc.data_ptr(), npix, 12, self.sums.data_ptr(), bc.data_ptr(), stream), "channel_sum")
-            check(lib.disco_channel_sum(gl.data_ptr(), npix, 36, self.sums.data_ptr(), bl.data_ptr(), stream), "channel_sum")
-            out["classification.conv2.bias"], out["regression.box_prediction.3.bias"] = bc, bl
-            layer_bwd(self.head_layers[1])
-            layer_bwd(self.head_layers[0])
-        for L in reversed(self.dec):
-            layer_bwd(L)
-        if self.fused_key:
-            self._fusion_bwd(gsrc, add_src, run_wgrad, out, stream, keep)
-        for L in reversed(self.enc):
-            layer_bwd(L)
+            for name, buf in (("cls", self.gcls), ("loc", self.gloc)):
+                g = grads.get(name)
+                if g is None:
+                    buf.zero_()
+                else:
+                    buf.copy_(g.detach().reshape(buf.shape), non_blocking=True)
+        self._run("bwd", self.bwd_ops, stream)
+        self._steps += 1
         self._bwd_keep = keep
-        return out
+        return self._collect(self.G.clone())
 
-    def _fusion_bwd(self, gsrc, add_src, run_wgrad, out, stream, keep):
-        lib, p, dev = self.lib, self.pwf, self.dev
-        srcs = gsrc.get(self.fused_key, [])
-        if not srcs:
-            raise RuntimeError("no gradient reaches the fused map")
-        # gradient wrt the fused map = decoder data gradient (+ KD gradient)
-        n_el = self.dfused.numel()
-        (t0, ct0, co0, pl0) = srcs[0]
-        assert ct0 == self.fuse_c and co0 == 0 and pl0 == 0
-        if len(srcs) == 1:
-            p.dfused = t0.data_ptr()
-        else:
-            (t1, ct1, co1, pl1) = srcs[1]
-            assert ct1 == self.fuse_c and co1 == 0 and pl1 == 0 and len(srcs) == 2
-            check(lib.disco_add_f32(self.dfused.data_ptr(), t0.data_ptr(), t1.data_ptr(), n_el, stream), "add_f32")
-            p.dfused = self.dfused.data_ptr()
-        self.dfeat.zero_(); self.den.zero_(); self.dparams.zero_()
-        check(lib.disco_fusion_combine_backward(C.byref(p), stream), "fusion_combine_backward")
-        check(lib.disco_pwf_train_backward(C.byref(p), stream), "pwf_train_backward")
-        hf, wf = self.fuse_hw
-        npix = self.n * hf * wf
-        check(lib.disco_grad_pack(self.den.data_ptr(), 256, None, 0, npix, self.den_act.data_ptr(), ops._lo_off(self.den_act),
-                                  stream), "grad_pack[den]")
-        dw = run_wgrad(self.en_wg, (256, self.fuse_c, 1))
-        self.en_dcall.launch(stream)
-        add_src(self.feat_key, self.en_gbuf, self.fuse_c, 0, 0)
-        add_src(self.feat_key, self.dfeat, self.fuse_c, 0, 0)
-        pp = self.pwf_prefix
-        dp = self.dparams
-        out[pp + "conv1_1.weight"] = torch.cat((dw[:128], dw[128:]), 1).reshape(128, 2 * self.fuse_c, 1, 1)
-        out[pp + "conv1_1.bias"] = torch.zeros(128, device=dev)
-        out[pp + "bn1_1.weight"], out[pp + "bn1_1.bias"] = dp[0:128].clone(), dp[128:256].clone()
-        out[pp + "conv1_2.weight"] = dp[256:4352].clone().reshape(32, 128, 1, 1)
-        out[pp + "conv1_2.bias"] = torch.zeros(32, device=dev)
-        out[pp + "bn1_2.weight"], out[pp + "bn1_2.bias"] = dp[4352:4384].clone(), dp[4384:4416].clone()
-        out[pp + "conv1_3.weight"] = dp[4416:4672].clone().reshape(8, 32, 1, 1)
-        out[pp + "conv1_3.bias"] = torch.zeros(8, device=dev)
-        out[pp + "bn1_3.weight"], out[pp + "bn1_3.bias"] = dp[4672:4680].clone(), dp[4680:4688].clone()
-        out[pp + "conv1_4.weight"] = dp[4688:4696].clone().reshape(1, 8, 1, 1)
-        out[pp + "conv1_4.bias"] = dp[4696:4697].clone()
+    def _collect(self, G: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Views of the (cloned) flat gradient buffer under the reference's parameter names."""
+        out: Dict[str, torch.Tensor] = {}
+        v = lambda name: self._gview(G, name)
+        zero = v("_zero")
+        for L in self.enc + self.dec:
+            out[L.conv + ".weight"] = v("_dw." + L.name).view(self.get(L.conv + ".weight").shape)
+            out[L.conv + ".bias"] = zero[:L.c_out]     # conv bias in front of a BatchNorm: exactly zero gradient
+            out[L.bn + ".weight"], out[L.bn + ".bias"] = v("_dgamma." + L.name), v("_dbeta." + L.name)
+        if self.head_layers:
+            dw3, dw1 = v("_dw.h3"), v("_dw.h1").view(48, 64)
+            out["classification.conv1.weight"] = dw3[:32].view(32, 32, 3, 3)
+            out["regression.box_prediction.0.weight"] = dw3[32:].view(32, 32, 3, 3)
+            dg, db = v("_dgamma.h3"), v("_dbeta.h3")
+            out["classification.bn1.weight"], out["regression.box_prediction.1.weight"] = dg[:32], dg[32:]
+            out["classification.bn1.bias"], out["regression.box_prediction.1.bias"] = db[:32], db[32:]
+            out["classification.conv1.bias"], out["regression.box_prediction.0.bias"] = zero[:32], zero[:32]
+            out["classification.conv2.weight"] = dw1[:12, :32].reshape(12, 32, 1, 1)
+            out["regression.box_prediction.3.weight"] = dw1[12:, 32:].reshape(36, 32, 1, 1)
+            out["classification.conv2.bias"], out["regression.box_prediction.3.bias"] = v("classification.conv2.bias"), v("regression.box_prediction.3.bias")
+        if self.fused_key:
+            pp, dp, dw = self.pwf_prefix, v("_pwf.dparams"), v("_dw.en").view(256, self.fuse_c)
+            out[pp + "conv1_1.weight"] = torch.cat((dw[:128], dw[128:]), 1).reshape(128, 2 * self.fuse_c, 1, 1)
+            out[pp + "conv1_1.bias"] = zero[:128]
+            out[pp + "bn1_1.weight"], out[pp + "bn1_1.bias"] = dp[0:128], dp[128:256]
+            out[pp + "conv1_2.weight"] = dp[256:4352].view(32, 128, 1, 1)
+            out[pp + "conv1_2.bias"] = zero[:32]
+            out[pp + "bn1_2.weight"], out[pp + "bn1_2.bias"] = dp[4352:4384], dp[4384:4416]
+            out[pp + "conv1_3.weight"] = dp[4416:4672].view(8, 32, 1, 1)
+            out[pp + "conv1_3.bias"] = zero[:8]
+            out[pp + "bn1_3.weight"], out[pp + "bn1_3.bias"] = dp[4672:4680], dp[4680:4688]
+            out[pp + "conv1_4.weight"] = dp[4688:4696].view(1, 8, 1, 1)
+            out[pp + "conv1_4.bias"] = dp[4696:4697]
+        return out
