@@ -147,6 +147,8 @@ EXPORTS = {
     "disco_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "disco_add_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "disco_kd_kl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
+    "disco_focal_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_float, C.c_int, C.c_void_p,
+                                   C.c_longlong, C.c_void_p, C.c_void_p]),
     "disco_conv_wgrad": (C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
     "disco_conv_wgrad_reference": (C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
     "disco_conv_wgrad_splits": (C.c_int, [C.POINTER(WgradDesc)]),

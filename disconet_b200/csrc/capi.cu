@@ -107,6 +107,10 @@ int disco_kd_kl(const float* student, const float* teacher, int n, int c, long l
                 float grad_scale, void* stream) {
     return disco_kd_kl_launch(student, teacher, n, c, hw, loss_sum, grad, grad_scale, stream);
 }
+int disco_focal_loss(const float* logits, const float* target, int k, long long n_anchor, float gamma, float alpha, int use_alpha,
+                     const float* grad_out, long long grad_out_stride, float* out, void* stream) {
+    return disco_focal_loss_launch(logits, target, k, n_anchor, gamma, alpha, use_alpha, grad_out, grad_out_stride, out, stream);
+}
 int disco_pack_weights(const disco_pack_desc* d, void* stream) {
     if (!d) { disco_set_error("null descriptor"); return DISCO_EINVAL; }
     return disco_pack_weights_launch(d, stream);

@@ -501,3 +501,102 @@ int disco_kd_kl_launch(const float* student, const float* teacher, int n, int c,
     DISCO_CHECK_CUDA(cudaGetLastError());
     return DISCO_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Softmax focal classification loss (SoftmaxFocalClassificationLoss._compute_loss, utils/loss.py:
+// 322-394, with _softmax_cross_entropy_with_logits :213-219), per anchor with K <= 8 classes:
+//   idx = argmax(target), ce = -log_softmax(logits)[idx], p = softmax(logits)
+//   p_t[c] = t[c] p[c] + (1 - t[c]) (1 - p[c]),   alpha_w = (t[0] == 1) ? 1 - alpha : alpha
+//   loss[c] = (1 - p_t[c])^gamma * alpha_w * ce * t[c]
+// forward writes loss[anchor][c]; backward writes dlogits[anchor][j] = sum_c gout[c] * dloss[c]/dlogit[j].
+// One thread per anchor, 2K loads + K stores (the reference chain is ~15 elementwise ops + CrossEntropy + autograd).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kMaxCls = 8;
+
+template <bool BWD>
+__global__ void __launch_bounds__(kThreads) focal_kernel(const float* __restrict__ logits, const float* __restrict__ target, int K,
+                                                         long long n_anchor, float gamma, float alpha, int use_alpha,
+                                                         const float* __restrict__ gout, long long gout_stride, float* __restrict__ out) {
+    for (long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x; a < n_anchor; a += (long long)gridDim.x * blockDim.x) {
+        float z[kMaxCls], t[kMaxCls], p[kMaxCls];
+        float m = -INFINITY;
+        int idx = 0;
+        float tmax = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < kMaxCls; ++c) {
+            if (c >= K) break;
+            z[c] = __ldg(logits + a * K + c);
+            t[c] = __ldg(target + a * K + c);
+            m = fmaxf(m, z[c]);
+            if (t[c] > tmax) { tmax = t[c]; idx = c; }   // first maximum, like torch.max(dim)[1]
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < kMaxCls; ++c) {
+            if (c >= K) break;
+            p[c] = expf(z[c] - m);
+            s += p[c];
+        }
+        const float inv = 1.f / s, ls = logf(s);
+        float zi = 0.f;
+#pragma unroll
+        for (int c = 0; c < kMaxCls; ++c) {
+            if (c >= K) break;
+            p[c] *= inv;
+            if (c == idx) zi = z[c];
+        }
+        const float ce = -(zi - m - ls);
+        const float aw = use_alpha ? ((t[0] == 1.f) ? 1.f - alpha : alpha) : 1.f;
+        if (!BWD) {
+#pragma unroll
+            for (int c = 0; c < kMaxCls; ++c) {
+                if (c >= K) break;
+                const float pt = t[c] * p[c] + (1.f - t[c]) * (1.f - p[c]);
+                const float mod = (gamma != 0.f) ? powf(fmaxf(1.f - pt, 0.f), gamma) : 1.f;
+                out[a * K + c] = mod * aw * ce * t[c];
+            }
+        } else {
+            float dz[kMaxCls];
+#pragma unroll
+            for (int j = 0; j < kMaxCls; ++j) dz[j] = 0.f;
+#pragma unroll
+            for (int c = 0; c < kMaxCls; ++c) {
+                if (c >= K) break;
+                const float g = gout[(a * K + c) * gout_stride] * aw * t[c];
+                if (g == 0.f) continue;
+                const float pt = t[c] * p[c] + (1.f - t[c]) * (1.f - p[c]);
+                const float om = fmaxf(1.f - pt, 0.f);
+                const float mod = (gamma != 0.f) ? powf(om, gamma) : 1.f;
+                // d mod / d p_t = -gamma (1-p_t)^(gamma-1);  d p_t / d z_j = (2 t_c - 1) p_c (delta_cj - p_j)
+                const float dmod = (gamma != 0.f) ? -gamma * powf(om, gamma - 1.f) * (2.f * t[c] - 1.f) * p[c] : 0.f;
+#pragma unroll
+                for (int j = 0; j < kMaxCls; ++j) {
+                    if (j >= K) break;
+                    const float dpt = dmod * ((c == j ? 1.f : 0.f) - p[j]);
+                    const float dce = p[j] - (j == idx ? 1.f : 0.f);
+                    dz[j] += g * (dpt * ce + mod * dce);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kMaxCls; ++j) {
+                if (j >= K) break;
+                out[a * K + j] = dz[j];
+            }
+        }
+    }
+}
+
+}  // namespace
+
+int disco_focal_loss_launch(const float* logits, const float* target, int k, long long n_anchor, float gamma, float alpha,
+                            int use_alpha, const float* grad_out, long long grad_out_stride, float* out, void* stream) {
+    DISCO_REQUIRE(logits && target && out && k >= 1 && k <= kMaxCls && n_anchor > 0, "focal_loss: bad arguments (1 <= classes <= 8)");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = grid_for(n_anchor, kThreads, 148 * 16);
+    if (grad_out) focal_kernel<true><<<grid, kThreads, 0, s>>>(logits, target, k, n_anchor, gamma, alpha, use_alpha, grad_out, grad_out_stride, out);
+    else focal_kernel<false><<<grid, kThreads, 0, s>>>(logits, target, k, n_anchor, gamma, alpha, use_alpha, nullptr, 0, out);
+    DISCO_CHECK_CUDA(cudaGetLastError());
+    return DISCO_OK;
+}

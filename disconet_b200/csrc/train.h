@@ -80,6 +80,12 @@ int disco_pack_weights_launch(const disco_pack_desc* d, void* stream);
 int disco_kd_kl_launch(const float* student, const float* teacher, int n, int c, long long hw, double* loss_sum, float* grad,
                        float grad_scale, void* stream);
 
+// Softmax focal classification loss per anchor (k <= 8 classes).  grad_out == null: out = loss [n_anchor, k];
+// else out = d(sum grad_out * loss)/d logits [n_anchor, k] (grad_out element stride grad_out_stride: 1, or 0 for a
+// broadcast scalar -- the backward of torch.sum).
+int disco_focal_loss_launch(const float* logits, const float* target, int k, long long n_anchor, float gamma, float alpha,
+                            int use_alpha, const float* grad_out, long long grad_out_stride, float* out, void* stream);
+
 // Weight gradient of a 3x3 / 1x1 conv:  dW[co][tap][ci] = sum_pixels dz[p][co] * x[p (+) tap][ci]
 // on the tensor cores (MN-major operands: both dz and x are pixel-major NHWC, the contraction runs over pixels).
 struct disco_wgrad_desc {

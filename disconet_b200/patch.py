@@ -29,6 +29,13 @@ def patch_coperception(classes=("DiscoNet", "FaFNet", "TeacherNet")) -> None:
         mod.FaFModule.get_kd_loss = kd.get_kd_loss
     except Exception:
         pass
+    # focal classification loss (train_codet.py:173-176 builds it from coperception.utils.loss)
+    try:
+        lmod = importlib.import_module("coperception.utils.loss")
+        from . import loss as ours_loss
+        lmod.SoftmaxFocalClassificationLoss = ours_loss.SoftmaxFocalClassificationLoss
+    except Exception:
+        pass
     # BEV segmentation (tools/seg/*.py do `from coperception.models.seg import *`)
     try:
         seg_pkg = importlib.import_module("coperception.models.seg")

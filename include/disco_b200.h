@@ -218,6 +218,12 @@ int disco_add_f32(float* dst, const float* a, const float* b, long long n, void*
 int disco_kd_kl(const float* student, const float* teacher, int n, int c, long long hw, double* loss_sum, float* grad,
                 float grad_scale, void* stream);
 
+/* SoftmaxFocalClassificationLoss._compute_loss (utils/loss.py:322-394) per anchor, k <= 8 classes, logits / one-hot
+ * targets [n_anchor, k] fp32.  grad_out == NULL: out = loss [n_anchor, k].  Otherwise out = gradient wrt the logits of
+ * sum(grad_out * loss); grad_out_stride = 1 for a dense grad_out, 0 for a broadcast scalar (backward of torch.sum). */
+int disco_focal_loss(const float* logits, const float* target, int k, long long n_anchor, float gamma, float alpha, int use_alpha,
+                     const float* grad_out, long long grad_out_stride, float* out, void* stream);
+
 /* Weight gradient dW[co][ci][kh][kw] = sum_pixels dz[p][co] * x[p (+) tap][ci] of a conv layer on the tensor cores
  * (MN-major tcgen05 operands, split-K over pixel tiles). */
 typedef struct disco_wgrad_desc {

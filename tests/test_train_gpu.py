@@ -421,3 +421,39 @@ def test_kd_loss_kernel_matches_reference_formula(cuda_dev):
         torch.cuda.synchronize()
         assert abs(got.item() - ref.item()) <= 1e-5 * abs(ref.item()), (got.item(), ref.item())
         assert rel_max(sg.grad.cpu(), sd.grad) < 1e-5
+
+
+def test_focal_loss_kernel_matches_reference_formula(cuda_dev):
+    """f4: fused focal loss forward / backward == the reference chain (loss.py:213-219,322-394), incl. sum()/N."""
+    from disconet_b200.loss import SoftmaxFocalClassificationLoss
+    dev = cuda_dev
+    rng = np.random.default_rng(13)
+    gamma, alpha = 2.0, 0.25
+    for (n, m, k) in [(3, 4096, 2), (2, 1000, 5)]:
+        z = torch.from_numpy((rng.standard_normal((n, m, k)) * 2).astype(np.float32))
+        lab = rng.integers(0, k, (n, m))
+        lab[rng.random((n, m)) < 0.9] = 0
+        t = torch.nn.functional.one_hot(torch.from_numpy(lab), k).float()
+        zd = z.double().requires_grad_(True)
+        td = t.double()
+        ce = F.cross_entropy(zd.permute(0, 2, 1), td.max(dim=-1)[1], reduction="none").unsqueeze(-1) * td
+        p = F.softmax(zd, dim=-1)
+        pt = td * p + (1 - td) * (1 - p)
+        aw = torch.where(td[..., 0] == 1, torch.tensor(1 - alpha, dtype=torch.float64), torch.tensor(alpha, dtype=torch.float64)).unsqueeze(-1)
+        ref = torch.pow(1.0 - pt, gamma) * aw * ce
+        (ref.sum() / n).backward()
+        zg = z.to(dev).requires_grad_(True)
+        got = SoftmaxFocalClassificationLoss(gamma, alpha)(zg, t.to(dev))
+        (got.sum() / n).backward()
+        torch.cuda.synchronize()
+        assert got.shape == ref.shape
+        assert rel_max(got.detach().cpu(), ref.detach()) < 1e-5
+        assert rel_max(zg.grad.cpu(), zd.grad) < 1e-5
+        # dense (non-broadcast) upstream gradient
+        w = torch.from_numpy(rng.random((n, m, k)).astype(np.float32))
+        zd.grad = None
+        (torch.pow(1.0 - (td * F.softmax(zd, -1) + (1 - td) * (1 - F.softmax(zd, -1))), gamma) * aw *
+         (F.cross_entropy(zd.permute(0, 2, 1), td.max(dim=-1)[1], reduction="none").unsqueeze(-1) * td) * w.double()).sum().backward()
+        zg.grad = None
+        (SoftmaxFocalClassificationLoss(gamma, alpha)(zg, t.to(dev)) * w.to(dev)).sum().backward()
+        assert rel_max(zg.grad.cpu(), zd.grad) < 1e-5
