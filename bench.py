@@ -154,10 +154,10 @@ def cpu_oracle_train_ms(threads: int):
 
 
 def train_leg(dev, dist, world, steps: int, warmup: int, scenes: int = 4):
-    """Training step of the same model (BASELINE configs[2] per-GPU batch: 4 scenes x 5 agents): DiscoNet(kd_flag=1)
-    in train() mode -- batch-statistics BatchNorm forward, backward of a synthetic loss over cls/loc/x_7/x_6/x_5/fused
-    (the tensors FaFModule.step differentiates, CoDetModule.py:249-291,340-382), Adam step -- plus, timed separately,
-    the KD teacher's eval forward.  With several ranks the model is wrapped in DistributedDataParallel (scene-sharded,
+    """Training step of the same model (BASELINE configs[2] per-GPU batch: 4 scenes x 5 agents): KD teacher eval
+    forward, DiscoNet(kd_flag=1) in train() mode -- batch-statistics BatchNorm forward --, the fused focal / KD losses
+    over cls/loc/x_7/x_6/x_5/fused (the tensors FaFModule.step differentiates, CoDetModule.py:249-291,340-382),
+    backward, Adam step.  The teacher's forward is also timed on its own.  With several ranks the model is wrapped in DistributedDataParallel (scene-sharded,
     NCCL all-reduce of the gradients)."""
     from disconet_b200 import DiscoNet, TeacherNet
     from disconet_b200 import synth as O
@@ -176,9 +176,24 @@ def train_leg(dev, dist, world, steps: int, warmup: int, scenes: int = 4):
     bev, T, na = synth_inputs(scenes, seed=300 + rank)
     bev, na = bev.to(dev), na.to(dev)
 
+    from disconet_b200.kd import kd_kl_mean
+    from disconet_b200.loss import SoftmaxFocalClassificationLoss
+    focal = SoftmaxFocalClassificationLoss()
+    g = torch.Generator().manual_seed(7 + rank)
+    n_img = AGENTS * scenes
+    pos = (torch.rand((n_img, H * W * 6), generator=g) < 1e-3)                     # Bernoulli(1e-3) positives
+    labels = torch.stack((~pos, pos), -1).float().to(dev)                         # one-hot [N, anchors, 2]
+    kd_weight = 1.0
+
     def step():
+        """One FaFModule.step-shaped iteration (CoDetModule.py:217-310): teacher forward (eval, no grad), student
+        forward, focal classification loss / N + a regression stand-in (the corner loss gathers a few hundred positive
+        anchors: negligible work) + kd_weight * 4 KD terms, backward, Adam."""
+        with torch.no_grad():
+            _, t7, t6, t5, t3, _ = teacher(bev)
         res, x8, x7, x6, x5, fused = net(bev, T, na, batch_size=scenes)
-        loss = res["cls"].square().mean() + res["loc"].square().mean() + x7.mean() + x6.mean() + x5.mean() + fused.mean()
+        loss = focal(res["cls"], labels).sum() / n_img + res["loc"].square().mean()
+        loss = loss + kd_weight * (kd_kl_mean(x7, t7) + kd_kl_mean(x6, t6) + kd_kl_mean(x5, t5) + kd_kl_mean(fused, t3))
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
@@ -210,9 +225,10 @@ def train_leg(dev, dist, world, steps: int, warmup: int, scenes: int = 4):
         "metric": "scenes/sec, training step", "value": world * scenes / (ms_step / 1e3), "unit": "scenes/s",
         "ms_per_step": ms_step, "teacher_forward_ms": ms_teacher, "scenes_per_step_per_gpu": scenes, "steps": steps,
         "algorithmic_tflops": 3 * ALGO_GFLOP_PER_SCENE * scenes / ms_step,
-        "config": "DiscoNet kd_flag=1 train(): forward (batch-stat BN) + backward + Adam on a synthetic loss over "
-                  "cls/loc/x_7/x_6/x_5/fused; 5 agents, 256x256x13" + ("; DistributedDataParallel over scenes" if dist else ""),
-        "loss": float(loss.detach()), "wall_ms_per_step_incl_teacher": wall / steps,
+        "config": "FaFModule.step-shaped iteration: TeacherNet eval forward + DiscoNet kd_flag=1 train() forward (batch-stat BN) "
+                  "+ fused focal cls loss + loc stand-in + 4 fused KD terms + backward + Adam; 5 agents, 256x256x13"
+                  + ("; DistributedDataParallel over scenes" if dist else ""),
+        "loss": float(loss.detach()), "wall_ms_per_step_plus_extra_teacher_pass": wall / steps,
     }
 
 
