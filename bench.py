@@ -199,7 +199,7 @@ def train_leg(dev, dist, world, steps: int, warmup: int, scenes: int = 4):
         opt.step()
         return loss
 
-    for _ in range(warmup):
+    for _ in range(max(warmup, 5)):      # (the runner replays CUDA graphs from its 3rd step on: capture stays untimed)
         step()
     if dist:
         import torch.distributed as td
@@ -325,6 +325,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if dist:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line
         import torch.distributed as td
         import datetime
         td.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=4))
