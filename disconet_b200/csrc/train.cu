@@ -451,41 +451,64 @@ int disco_add_f32_launch(float* dst, const float* a, const float* b, long long n
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
 
+constexpr int kKdLanes = kThreads / 32;   // channel lanes per pixel (one warp per lane: loads stay coalesced along pixels)
+
+// Block = 32 consecutive pixels x 8 channel lanes; lane l owns channels l, l+8, ...  Two passes over the block's
+// [32 px, C] slab: online max / sum-of-exponentials per lane combined through shared memory, then the KL terms and the
+// gradient.  (One thread per pixel was latency-bound on the 32x32 maps: 20 K threads walking 256 channels each.)
 __global__ void __launch_bounds__(kThreads) kd_kl_kernel(const float* __restrict__ s, const float* __restrict__ t, int C, long long hw,
                                                          long long total, double* loss_sum, float* __restrict__ grad, float gscale) {
-    __shared__ double s_part[kThreads / 32];
+    __shared__ float s_ms[kKdLanes][32], s_zs[kKdLanes][32], s_mt[kKdLanes][32], s_zt[kKdLanes][32];
+    __shared__ double s_part[kKdLanes];
+    const int px = threadIdx.x & 31, lane = threadIdx.x >> 5;
     double local = 0.0;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const long long img = e / hw, p = e - img * hw;
+    for (long long e0 = (long long)blockIdx.x * 32; e0 < total; e0 += (long long)gridDim.x * 32) {
+        const long long e = e0 + px;
+        const bool ok = e < total;
+        const long long img = ok ? e / hw : 0, p = ok ? e - img * hw : 0;
         const float* sp = s + img * C * hw + p;
         const float* tp = t + img * C * hw + p;
-        // pass 1: online max / sum of exponentials of both logit vectors (coalesced: consecutive threads = consecutive pixels)
         float ms = -INFINITY, mt = -INFINITY, zs = 0.f, zt = 0.f;
-        for (int c = 0; c < C; ++c) {
-            const float a = __ldg(sp + (long long)c * hw), b = __ldg(tp + (long long)c * hw);
-            if (a > ms) { zs *= expf(ms - a); ms = a; }
-            zs += expf(a - ms);
-            if (b > mt) { zt *= expf(mt - b); mt = b; }
-            zt += expf(b - mt);
+        if (ok) {
+            for (int c = lane; c < C; c += kKdLanes) {
+                const float a = __ldg(sp + (long long)c * hw), b = __ldg(tp + (long long)c * hw);
+                if (a > ms) { zs *= expf(ms - a); ms = a; }
+                zs += expf(a - ms);
+                if (b > mt) { zt *= expf(mt - b); mt = b; }
+                zt += expf(b - mt);
+            }
         }
-        const float lzs = logf(zs), lzt = logf(zt), izs = 1.f / zs, izt = 1.f / zt;
-        // pass 2: KL terms and the gradient (softmax(s) - softmax(t)) * gscale
-        float acc = 0.f;
-        for (int c = 0; c < C; ++c) {
-            const float a = __ldg(sp + (long long)c * hw) - ms, b = __ldg(tp + (long long)c * hw) - mt;
-            const float pt = expf(b) * izt;
-            if (pt > 0.f) acc = fmaf(pt, (b - lzt) - (a - lzs), acc);
-            if (grad) grad[img * C * hw + (long long)c * hw + p] = (expf(a) * izs - pt) * gscale;
+        s_ms[lane][px] = ms; s_zs[lane][px] = zs; s_mt[lane][px] = mt; s_zt[lane][px] = zt;
+        __syncthreads();
+        float Ms = -INFINITY, Mt = -INFINITY;
+#pragma unroll
+        for (int l = 0; l < kKdLanes; ++l) { Ms = fmaxf(Ms, s_ms[l][px]); Mt = fmaxf(Mt, s_mt[l][px]); }
+        float Zs = 0.f, Zt = 0.f;
+#pragma unroll
+        for (int l = 0; l < kKdLanes; ++l) {
+            if (s_zs[l][px] > 0.f) Zs += s_zs[l][px] * expf(s_ms[l][px] - Ms);
+            if (s_zt[l][px] > 0.f) Zt += s_zt[l][px] * expf(s_mt[l][px] - Mt);
         }
-        local += (double)acc;
+        __syncthreads();   // shared statistics are rewritten by the next slab
+        if (ok) {
+            const float lzs = logf(Zs), lzt = logf(Zt), izs = 1.f / Zs, izt = 1.f / Zt;
+            float acc = 0.f;
+            for (int c = lane; c < C; c += kKdLanes) {
+                const float a = __ldg(sp + (long long)c * hw) - Ms, b = __ldg(tp + (long long)c * hw) - Mt;
+                const float pt = expf(b) * izt;
+                if (pt > 0.f) acc = fmaf(pt, (b - lzt) - (a - lzs), acc);
+                if (grad) grad[img * C * hw + (long long)c * hw + p] = (expf(a) * izs - pt) * gscale;
+            }
+            local += (double)acc;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = local;
+    if (px == 0) s_part[lane] = local;
     __syncthreads();
     if (threadIdx.x == 0) {
         double a = 0.0;
-        for (int i = 0; i < kThreads / 32; ++i) a += s_part[i];
+        for (int i = 0; i < kKdLanes; ++i) a += s_part[i];
         atomicAdd(loss_sum, a);
     }
 }
@@ -496,7 +519,7 @@ int disco_kd_kl_launch(const float* student, const float* teacher, int n, int c,
                        float grad_scale, void* stream) {
     DISCO_REQUIRE(student && teacher && loss_sum && n > 0 && c > 0 && hw > 0, "kd_kl: bad arguments");
     const long long total = (long long)n * hw;
-    kd_kl_kernel<<<grid_for(total, kThreads, 148 * 8), kThreads, 0, (cudaStream_t)stream>>>(student, teacher, c, hw, total, loss_sum,
+    kd_kl_kernel<<<grid_for(total, 32, 148 * 16), kThreads, 0, (cudaStream_t)stream>>>(student, teacher, c, hw, total, loss_sum,
                                                                                            grad, grad_scale);
     DISCO_CHECK_CUDA(cudaGetLastError());
     return DISCO_OK;

@@ -273,3 +273,25 @@ def test_seg_state_dict_layout_matches_reference():
     assert [[k, list(v.shape)] for k, v in m.state_dict().items()] == keys
     with pytest.raises(ValueError, match="CUDA"):
         m.eval()(torch.zeros(2, 13, 32, 32), torch.zeros(1, 2, 2, 4, 4), torch.ones(1, 2, dtype=torch.int64))
+
+
+def test_training_layer_tables_match_the_reference_parameters():
+    """Host logic of the training driver: every conv / BatchNorm the layer tables name exists in the reference
+    state_dict with the channel counts the tables claim (Backbone.py:11-47), and the set of parameters the autograd node
+    differentiates is exactly the set that receives a gradient in the reference (golden `grad_none`)."""
+    from disconet_b200.det import runner_param_names
+    from disconet_b200.train import backbone_layers
+    shapes = dict((k, tuple(s)) for k, s in json.load(open(os.path.join(GOLD, "state_dict_keys.json")))["train_a2_b1"])
+    E, D = backbone_layers("u_encoder.", "decoder.", "x3f", 3)
+    for L in E + D:
+        w = shapes[L.conv + ".weight"]
+        assert w[0] == L.c_out and w[1] == L.c_in_real and w[2] * w[3] == L.taps, L.name
+        assert shapes[L.bn + ".weight"] == (L.c_out,) and (L.bn + ".running_var") in shapes, L.name
+        assert sum(L.c_in) >= L.c_in_real and all(c % 16 == 0 for c in L.c_in), L.name
+
+    class R:
+        enc, dec, head_layers, pwf_prefix = E, D, [1], "pixel_weighted_fusion."
+    live = runner_param_names(R)
+    rec = np.load(os.path.join(GOLD, "train_a2_b1.npz"))
+    params = set(rec["grad_names"].tolist())
+    assert live == params - set(rec["grad_none"].tolist())
