@@ -15,17 +15,6 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kMaxC = 512;
 
-__device__ __forceinline__ float grad_src_load(const disco_grad_src& s, long long pix, int h, int w, int c) {
-    if (!s.pool) return __ldg(s.ptr + pix * s.c_total + s.c_off + c);
-    const int x = (int)(pix % w);
-    const int y = (int)((pix / w) % h);
-    const long long n = pix / ((long long)w * h);
-    const long long base = ((n * (2 * h) + 2 * y) * (2 * w) + 2 * x) * s.c_total + s.c_off + c;
-    const long long row = (long long)(2 * w) * s.c_total;
-    return __ldg(s.ptr + base) + __ldg(s.ptr + base + s.c_total) + __ldg(s.ptr + base + row) +
-           __ldg(s.ptr + base + row + s.c_total);
-}
-
 // 8 consecutive channels [c, c+8) of one gradient source at pixel `pix` (2x2 block sum for pooled sources)
 __device__ __forceinline__ void grad_src_add8(const disco_grad_src& s, long long pix, int h, int w, int c, float* g) {
     if (!s.pool) {

@@ -47,7 +47,6 @@ struct WGeom {
     int splits;
     int tmem_cols;
     int smem_bytes;
-    int swap_desc;            // debug (DISCO_WGRAD_SWAP=1): exchange LBO/SBO in the descriptors
 };
 
 struct __align__(8) WCtl {
@@ -219,12 +218,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WGeom g) {
         const int tap_hi = (TAPS == 1) ? 1 : (iss == 0 ? 5 : TAPS);
         const uint32_t idesc = wgrad_idesc(128, g.nb);
         // descriptor halves: lo = start>>4 | (LBO>>4)<<16 ; hi = SBO>>4 | version(1)<<14
-        uint32_t a_lbo = 128u >> 4, a_sbo = (uint32_t)g.plane_a >> 4;
-        uint32_t b_lbo = (uint32_t)g.lbo_b >> 4, b_sbo = (uint32_t)g.plane_b >> 4;
-        if (g.swap_desc) {
-            uint32_t x = a_lbo; a_lbo = a_sbo; a_sbo = x;
-            x = b_lbo; b_lbo = b_sbo; b_sbo = x;
-        }
+        // MN-major SWIZZLE_NONE: LBO = pitch between 8-pixel (K) groups, SBO = pitch between 8-channel (M/N) groups
+        const uint32_t a_lbo = 128u >> 4, a_sbo = (uint32_t)g.plane_a >> 4;
+        const uint32_t b_lbo = (uint32_t)g.lbo_b >> 4, b_sbo = (uint32_t)g.plane_b >> 4;
         const uint32_t a_hi = a_sbo | (1u << 14), b_hi = b_sbo | (1u << 14);
         const int passes = d.passes;
         for (int t = t0; t < t1; ++t) {
@@ -391,8 +387,6 @@ int build_wgeom(const disco_wgrad_desc* d, WGeom* g) {
     if (splits > 2 * g_sms) splits = 2 * g_sms;
     if (splits < 1) splits = 1;
     g->splits = splits;
-    const char* sw = getenv("DISCO_WGRAD_SWAP");
-    g->swap_desc = (sw && sw[0] == '1') ? 1 : 0;
     return DISCO_OK;
 }
 

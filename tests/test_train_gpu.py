@@ -457,3 +457,66 @@ def test_focal_loss_kernel_matches_reference_formula(cuda_dev):
         zg.grad = None
         (SoftmaxFocalClassificationLoss(gamma, alpha)(zg, t.to(dev)) * w.to(dev)).sum().backward()
         assert rel_max(zg.grad.cpu(), zd.grad) < 1e-5
+
+
+# ---- more of the path's flags in train() mode, against the oracle's autograd (no extra golden: the oracle itself is pinned
+# ---- to the live reference for eval with these flags and for train() on the two cases above) ----
+EXTRA_TRAIN_CASES = {
+    # two scenes with different agent counts, infrastructure-only links, one ego in communication outage
+    "b2_v2i_outage": dict(A=3, B=2, num_agent=[3, 2], kd_flag=1, only_v2i=True, compress_level=0, seed=61, layer=3,
+                          outage=[[0, 1, 0], [0, 0, 0]]),
+    # collaboration on the 128-channel 64x64 level (--layer 2)
+    "layer2": dict(A=2, B=1, num_agent=[2], kd_flag=1, only_v2i=False, compress_level=0, seed=62, layer=2, outage=None),
+}
+
+
+@pytest.mark.parametrize("name", list(EXTRA_TRAIN_CASES))
+def test_training_step_flags_match_oracle(name, cuda_dev):
+    from disconet_b200 import DiscoNet
+    case = EXTRA_TRAIN_CASES[name]
+    A, B = case["A"], case["B"]
+    m = DiscoNet(_Cfg(), layer=case["layer"], kd_flag=1, num_agent=A, only_v2i=case["only_v2i"])
+    sd, bev, T, na = golden_case_inputs(case, m.state_dict())
+    m.load_state_dict(sd)
+    # ---- oracle ----
+    sdo = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
+    with O.training(sdo) as ctx:
+        ref = O.disconet_forward_graph(sdo, bev, T, na, B, agent_num=A, layer=case["layer"], only_v2i=case["only_v2i"],
+                                       return_all=True, outage=case["outage"])
+    ref_t = {k: ref[k] for k in TRAIN_OUT_KEYS}
+    lref, _ = O.probe_loss(ref_t, seed=case["seed"] + 300)
+    lref.backward()
+    # ---- ours ----
+    m = m.to(cuda_dev).train()
+    if case["outage"] is not None:
+        m.p_com_outage = 0.5
+        draws = iter([bool(case["outage"][b][i]) for b in range(B) for i in range(case["num_agent"][b])])
+        m.outage = lambda: next(draws)            # the reference draws once per (scene, present ego) in this order
+    out = m(bev.to(cuda_dev), T, na, batch_size=B)
+    got_t = dict(zip(TRAIN_OUT_KEYS, (out[0]["cls"], out[0]["loc"]) + tuple(out[1:])))
+    loss, _ = O.probe_loss(got_t, seed=case["seed"] + 300)
+    loss.backward()
+    torch.cuda.synchronize()
+    for k in TRAIN_OUT_KEYS:
+        e = rel_max(got_t[k].detach().cpu(), ref_t[k].detach())
+        print(f"{name} fwd {k}: rel-max {e:.2e}")
+        assert e <= 1e-3, (k, e)
+    a, b = [], []
+    for k, p in m.named_parameters():
+        g = sdo[k].grad
+        if g is None:
+            assert p.grad is None, k
+            continue
+        assert p.grad is not None, k
+        if p.grad.abs().max() == 0:          # BN-shadowed conv bias
+            continue
+        a.append(p.grad.detach().cpu().flatten()); b.append(g.flatten())
+    a, b = torch.cat(a).double(), torch.cat(b).double()
+    cos = (a @ b / (a.norm() * b.norm())).item()
+    print(f"{name} all gradients: cos {cos:.6f} rel-l2 {((a - b).norm() / b.norm()).item():.3e}")
+    assert cos >= 0.999
+    for k, v in ctx.buffers.items():
+        if k.startswith(("u_encoder.bn5", "u_encoder.bn6", "u_encoder.bn7", "u_encoder.bn8", "decoder.bn_pre", "decoder.bn1", "decoder.bn2",
+                         "decoder.bn3", "decoder.bn4", "decoder.conv3d")) or "num_batches" in k:
+            continue
+        assert rel_max(m.state_dict()[k].float().cpu(), v.float()) <= 1e-3, k
