@@ -149,8 +149,8 @@ class _DetBase(nn.Module):
         load()  # raises if libdisco_b200.so is missing
         if self.training and self.precision_name != "bf16x3":
             raise NotImplementedError("training mode runs in the default bf16x3 precision only")
-        if self.training and getattr(self, "compress_level", 0) > 0:
-            raise NotImplementedError("training mode with compress_level > 0 is not implemented")
+        if self.training and getattr(self, "compress_level", 0) > 4:
+            raise NotImplementedError("training mode supports compress_level <= 4 (bottleneck width a multiple of 16)")
         if not bevs.is_cuda:
             raise ValueError("disconet_b200 runs on CUDA tensors only (no CPU fallback); got a CPU `bevs`")
         if bevs.dim() != 5 or bevs.shape[1] != 1 or bevs.shape[4] != self.in_channels:
@@ -379,7 +379,8 @@ class DiscoNet(_DetBase):
         if runner is None:
             runner = train_mod.TrainRunner(self._getter(), N, H, W, dev, "u_encoder.", "decoder.", heads=True,
                                            pwf_prefix="pixel_weighted_fusion.", batch_size=B, agents=A,
-                                           fusion_level=self.layer, only_v2i=bool(self.only_v2i), kd_keys=kd_keys)
+                                           fusion_level=self.layer, only_v2i=bool(self.only_v2i), kd_keys=kd_keys,
+                                           compress_level=self.compress_level)
             self._runners[key] = runner
         runner.get = self._getter()
         outage_host = None
@@ -439,7 +440,8 @@ class _StpnModel(_DetBase):
         key = (N, H, W, str(bevs.device), heads, tuple(kd_keys))
         runner = self._runners.get(key)
         if runner is None:
-            runner = train_mod.TrainRunner(self._getter(), N, H, W, bevs.device, "stpn.", "stpn.", heads=heads, kd_keys=kd_keys)
+            runner = train_mod.TrainRunner(self._getter(), N, H, W, bevs.device, "stpn.", "stpn.", heads=heads, kd_keys=kd_keys,
+                                           compress_level=self.compress_level)
             self._runners[key] = runner
         runner.get = self._getter()
         return runner
@@ -461,7 +463,8 @@ class FaFNet(_StpnModel):
     def forward(self, bevs, maps=None, vis=None, batch_size=None):
         if self.training:
             self._check_inputs(bevs)
-            kd_keys = ["x8", "x7", "x6", "x5", "x3"] if self.kd_flag == 1 else []
+            x3 = "x3d" if self.compress_level > 0 else "x3"
+            kd_keys = ["x8", "x7", "x6", "x5", x3] if self.kd_flag == 1 else []
             runner = self._train_runner(bevs, heads=True, kd_keys=kd_keys)
             result, maps_ = self._train_step(runner, bevs, None, None, None, kd_keys)
             return (result, *maps_) if self.kd_flag == 1 else result

@@ -53,8 +53,10 @@ class Layer:
             self.c_in_real = sum(self.c_in)
 
 
-def backbone_layers(pe: str, pd: str, fused_key: Optional[str], fusion_level: int = 3) -> Tuple[List[Layer], List[Layer]]:
-    """Backbone.encode / decode layer tables (Backbone.py:89-143,145-242)."""
+def backbone_layers(pe: str, pd: str, fused_key: Optional[str], fusion_level: int = 3,
+                    compress_cc: int = 0) -> Tuple[List[Layer], List[Layer]]:
+    """Backbone.encode / decode layer tables (Backbone.py:89-143,145-242).  compress_cc > 0: the 1x1 bottleneck pair
+    on x_3 (Backbone.py:73-87,139-141; applied AFTER conv4 has read the uncompressed x_3)."""
     E = [
         Layer("pre1", pe + "conv_pre_1", pe + "bn_pre_1", ["a0"], [0], "t0", [16], 32, level=0, c_in_real=13, need_dgrad=False),
         Layer("pre2", pe + "conv_pre_2", pe + "bn_pre_2", ["t0"], [0], "x", [32], 32, level=0),
@@ -69,7 +71,14 @@ def backbone_layers(pe: str, pd: str, fused_key: Optional[str], fusion_level: in
         Layer("c4_1", pe + "conv4_1", pe + "bn4_1", ["x3"], [0], "t4", [256], 512, stride=2, level=3),
         Layer("c4_2", pe + "conv4_2", pe + "bn4_2", ["t4"], [0], "x4", [512], 512, level=4),
     ]
-    x3d = fused_key if (fused_key and fusion_level == 3) else "x3"
+    x3_key = "x3"
+    if compress_cc:
+        E += [
+            Layer("compress", pe + "com_compresser", pe + "bn_compress", ["x3"], [0], "x3c", [256], compress_cc, taps=1, level=3),
+            Layer("decompress", pe + "com_decompresser", pe + "bn_decompress", ["x3c"], [0], "x3d", [compress_cc], 256, taps=1, level=3),
+        ]
+        x3_key = "x3d"
+    x3d = fused_key if (fused_key and fusion_level == 3) else x3_key
     x2d = fused_key if (fused_key and fusion_level == 2) else "x2"
     D = [
         Layer("c5_1", pd + "conv5_1", pd + "bn5_1", ["x4", x3d], [1, 0], "t5", [512, 256], 256, level=3),
@@ -123,7 +132,7 @@ class TrainRunner:
 
     def __init__(self, get, n: int, h: int, w: int, device, enc_prefix: str, dec_prefix: str, *, heads: bool = True,
                  pwf_prefix: Optional[str] = None, batch_size: int = 1, agents: int = 1, fusion_level: int = 3,
-                 only_v2i: bool = False, kd_keys: Sequence[str] = ()):
+                 only_v2i: bool = False, kd_keys: Sequence[str] = (), compress_level: int = 0):
         if h % 16 or w % 16:
             raise ValueError(f"BEV size {h}x{w} must be a multiple of 16")
         self.get, self.n, self.h, self.w, self.dev = get, n, h, w, device
@@ -136,7 +145,11 @@ class TrainRunner:
             if fusion_level not in (2, 3):
                 raise NotImplementedError("DiscoNet builds its PixelWeightedFusion for layer 2 or 3 only")
             self.fused_key = "x3f" if fusion_level == 3 else "x2f"
-        E, D = backbone_layers(enc_prefix, dec_prefix, self.fused_key, fusion_level)
+        cc = 256 // (2 ** compress_level) if compress_level > 0 else 0
+        if cc and cc % 16:
+            raise NotImplementedError("training mode supports compress_level <= 4 (bottleneck width a multiple of 16)")
+        self.x3_key = "x3d" if cc else "x3"
+        E, D = backbone_layers(enc_prefix, dec_prefix, self.fused_key, fusion_level, compress_cc=cc)
         self.enc, self.dec = E, D
         self.head_layers: List[Layer] = []
         if heads:
@@ -167,7 +180,7 @@ class TrainRunner:
         if self.fused_key:
             hf, wf = self.res[fusion_level]
             cf = 256 if fusion_level == 3 else 128
-            self.feat_key = "x3" if fusion_level == 3 else "x2"
+            self.feat_key = self.x3_key if fusion_level == 3 else "x2"
             self.fuse_hw, self.fuse_c = (hf, wf), cf
             self.act[self.fused_key] = A_(hf, wf, cf)
         if heads:

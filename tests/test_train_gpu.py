@@ -467,6 +467,8 @@ EXTRA_TRAIN_CASES = {
                           outage=[[0, 1, 0], [0, 0, 0]]),
     # collaboration on the 128-channel 64x64 level (--layer 2)
     "layer2": dict(A=2, B=1, num_agent=[2], kd_flag=1, only_v2i=False, compress_level=0, seed=62, layer=2, outage=None),
+    # the communication bottleneck 256 -> 64 -> 256 on x_3 (Backbone.py:139-141)
+    "compress2": dict(A=2, B=1, num_agent=[2], kd_flag=1, only_v2i=False, compress_level=2, seed=63, layer=3, outage=None),
 }
 
 
@@ -475,7 +477,7 @@ def test_training_step_flags_match_oracle(name, cuda_dev):
     from disconet_b200 import DiscoNet
     case = EXTRA_TRAIN_CASES[name]
     A, B = case["A"], case["B"]
-    m = DiscoNet(_Cfg(), layer=case["layer"], kd_flag=1, num_agent=A, only_v2i=case["only_v2i"])
+    m = DiscoNet(_Cfg(), layer=case["layer"], kd_flag=1, num_agent=A, only_v2i=case["only_v2i"], compress_level=case["compress_level"])
     sd, bev, T, na = golden_case_inputs(case, m.state_dict())
     m.load_state_dict(sd)
     # ---- oracle ----
