@@ -47,6 +47,8 @@ struct WGeom {
     int splits;
     int tmem_cols;
     int smem_bytes;
+    int sw;                   // 1: operand-swapped kernel (A = input patch, B = dz) for the skinny 3x3 stride-1 layers
+    int kws;                  // sw: kw-shifted patch copies stacked along M (3 when 3*c_in <= 128, else 1)
 };
 
 struct __align__(8) WCtl {
@@ -265,6 +267,163 @@ done:
     if (warp == 4) tmem_dealloc(tmem_d, (uint32_t)g.tmem_cols);
 }
 
+// Operand-swapped variant for the skinny 3x3 stride-1 layers (c_out <= 64 at the 256^2 / 128^2 resolutions, where the
+// kernel above is MMA-issue-bound: ~45 cycles per tcgen05.mma whatever its N, 216 of them per 128-pixel tile, with
+// M = c_out padded to 128):
+//   A = the input patch (M = channels of c_in), B = the dz tile (N = c_out), D[ci][co].
+// When 3*c_in <= 128 the patch is staged THREE times, shifted by kw = 0,1,2 pixels, as consecutive channel-group planes,
+// so one MMA covers a whole filter row: M = (kw, ci), one accumulator per kh, 72 MMAs per tile instead of 216.
+// Otherwise (conv8_1: c_in = 96 > c_out = 32) plain swap: M = c_in, nine accumulators, 216 MMAs instead of 432.
+__global__ void __launch_bounds__(kThreads, 1) wgrad_sw_kernel(const WGeom g) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    WCtl* ctl = reinterpret_cast<WCtl*>(smem_raw);
+    const uint32_t stage_base = smem_u32(smem_raw) + kCtlBytes;
+    const disco_wgrad_desc& d = g.d;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int split = blockIdx.x;
+    const int t0 = (int)((long long)split * g.n_tiles / g.splits);
+    const int t1 = (int)((long long)(split + 1) * g.n_tiles / g.splits);
+    const int KWS = g.kws;
+    const int NACC = (KWS == 3) ? 3 : 9;          // accumulators: one per kh (stacked) or per tap
+
+    if (tid == 0) {
+        for (int s = 0; s < g.stages; ++s) {
+            mbar_init(smem_u32(&ctl->full[s]), kProdThreads);
+            mbar_init(smem_u32(&ctl->empty[s]), kIssuers);
+        }
+        mbar_init(smem_u32(&ctl->acc_full), kIssuers);
+        fence_mbar_init();
+    }
+    if (warp == 4) {
+        tmem_alloc(smem_u32(&ctl->tmem_base), (uint32_t)g.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = ctl->tmem_base;
+    // stage layout: [A hi | A lo | B hi | B lo];  A part = kws * chunks_b planes of plane_b, B part = chunks_a planes of plane_a
+    const int a_part = KWS * g.chunks_b * g.plane_b, b_part = g.chunks_a * g.plane_a;
+
+    if (warp < 4) {
+        const uint16_t* dz = reinterpret_cast<const uint16_t*>(d.dz_hi);
+        for (int t = t0; t < t1; ++t) {
+            const int i = t - t0, slot = i % g.stages;
+            mbar_wait(smem_u32(&ctl->empty[slot]), ((uint32_t)(i / g.stages) & 1u) ^ 1u);
+            const uint32_t sa = stage_base + slot * g.stage_bytes;
+            const uint32_t sb = sa + 2 * a_part;
+            const int per_img = g.tiles_h * g.tiles_w;
+            const int img = t / per_img;
+            const int rem = t - img * per_img;
+            const int th = rem / g.tiles_w;
+            const int h0 = th * 16, w0 = (rem - th * g.tiles_w) * 8;
+            // ---- B: dz tile [c_out/8][128 px][8 ch] ----
+            for (int e = tid; e < 128 * g.chunks_a; e += kProdThreads) {
+                const int m = e / g.chunks_a, chunk = e - m * g.chunks_a;
+                const int oh = h0 + (m >> 3), ow = w0 + (m & 7);
+                const bool valid = (oh < d.h_out) && (ow < d.w_out);
+                const long long pix = ((long long)img * d.h_out + oh) * d.w_out + ow;
+                const uint16_t* gp = valid ? dz + pix * d.c_out + chunk * 8 : dz;
+                const uint32_t dst = sb + chunk * g.plane_a + m * 16;
+                cp_async16(dst, gp, valid ? 16u : 0u);
+                cp_async16(dst + b_part, valid ? gp + d.dz_lo_off : dz, valid ? 16u : 0u);
+            }
+            // ---- A: input patch 18x10, kws shifted copies ----
+            const int hi0 = h0 - 1, wi0 = w0 - 1;
+            for (int e = tid; e < 180 * g.chunks_b; e += kProdThreads) {
+                const int pi = e / g.chunks_b, chunk = e - pi * g.chunks_b;
+                const int ch = chunk * 8;
+                const int sidx = (ch >= d.src_c[0]) ? 1 : 0;
+                const uint16_t* src = reinterpret_cast<const uint16_t*>(d.src[sidx]);
+                const int Cs = d.src_c[sidx];
+                const int cl = sidx ? ch - d.src_c[0] : ch;
+                const long long lo_off = d.src_lo_off[sidx];
+                const int upm = d.src_up[sidx], up = upm ? 1 : 0;
+                const int r = pi / 10, c = pi - r * 10;
+                const int hi = hi0 + r, wi = wi0 + c;
+                const bool valid = (hi >= 0) && (hi < d.h_in) && (wi >= 0) && (wi < d.w_in) && !(upm == 2 && ((hi | wi) & 1));
+                const int Hs = d.h_in >> up, Ws = d.w_in >> up;
+                const uint16_t* gp = valid ? src + (((long long)img * Hs + (hi >> up)) * Ws + (wi >> up)) * Cs + cl : src;
+                for (int kw = 0; kw < KWS; ++kw) {
+                    if (pi < kw) continue;     // copy kw holds patch pixel (slot + kw)
+                    const uint32_t dst = sa + (uint32_t)(kw * g.chunks_b + chunk) * g.plane_b + (uint32_t)(pi - kw) * 16u;
+                    cp_async16(dst, gp, valid ? 16u : 0u);
+                    cp_async16(dst + a_part, valid ? gp + lo_off : src, valid ? 16u : 0u);
+                }
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+            fence_proxy_async_smem();
+            mbar_arrive(smem_u32(&ctl->full[slot]));
+        }
+        // ---- epilogue: D[acc][m = (kw, ci)][co] -> partial[split][co][tap][ci] ----
+        mbar_wait(smem_u32(&ctl->acc_full), 0);
+        tc_fence_after();
+        const int m = warp * 32 + lane;
+        const int kw_m = (KWS == 3) ? m / g.c_in : 0;
+        const int ci = (KWS == 3) ? m - kw_m * g.c_in : m;
+        const bool row_ok = (KWS == 3) ? (m < 3 * g.c_in) : (m < g.c_in);
+        const uint32_t t_lane = tmem_d + ((uint32_t)(warp * 32) << 16);
+        float* pbase = d.partial + (long long)split * d.c_out * 9 * g.c_in;
+        for (int a = 0; a < NACC; ++a) {
+            const int tap = (KWS == 3) ? a * 3 + kw_m : a;
+            for (int j = 0; j < d.c_out; j += 16) {
+                uint32_t v[16];
+                tmem_ld16(t_lane + (uint32_t)(a * d.c_out + j), v);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q)
+                        pbase[((long long)(j + q) * 9 + tap) * g.c_in + ci] = __uint_as_float(v[q]);
+                }
+            }
+        }
+        tc_fence_before();
+    } else {
+        // ---- MMA issuers: accumulators split between the two warps ----
+        const int iss = warp - 4;
+        const int a_lo_acc = (iss == 0) ? 0 : (NACC + 1) / 2, a_hi_acc = (iss == 0) ? (NACC + 1) / 2 : NACC;
+        const uint32_t idesc = wgrad_idesc(128, d.c_out);
+        const uint32_t a_lbo = 160u >> 4, a_sbo = (uint32_t)g.plane_b >> 4;     // A = patch: next tile row / next channel group
+        const uint32_t b_lbo = 128u >> 4, b_sbo = (uint32_t)g.plane_a >> 4;     // B = dz tile
+        const uint32_t a_hi = a_sbo | (1u << 14), b_hi = b_sbo | (1u << 14);
+        for (int t = t0; t < t1; ++t) {
+            const int i = t - t0, slot = i % g.stages;
+            mbar_wait(smem_u32(&ctl->full[slot]), (uint32_t)(i / g.stages) & 1u);
+            tc_fence_after();
+            const uint32_t sa = stage_base + slot * g.stage_bytes;
+            const uint32_t sb = sa + 2 * a_part;
+            if (elect_one()) {
+#pragma unroll 1
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint32_t b_lo0 = ((sb + (uint32_t)ks * 256u) >> 4) | (b_lbo << 16);
+                    const uint32_t a_ks = sa + (uint32_t)(2 * ks) * 160u;
+#pragma unroll
+                    for (int a = 0; a < 9; ++a) {            // straight-line issue: a rolled MMA loop serialises
+                        if (a < a_lo_acc || a >= a_hi_acc) continue;
+                        const int kh = (KWS == 3) ? a : a / 3, kw = (KWS == 3) ? 0 : a - (a / 3) * 3;
+                        const uint32_t a_lo0 = ((a_ks + (uint32_t)(kh * 10 + kw) * 16u) >> 4) | (a_lbo << 16);
+                        const uint32_t td = tmem_d + (uint32_t)(a * d.c_out);
+                        const uint32_t acc = (i > 0 || ks > 0) ? 1u : 0u;
+                        umma_f16_parts(td, a_lo0, a_hi, b_lo0, b_hi, idesc, acc);                                  // hi * hi
+                        if (d.passes == 3) {
+                            umma_f16_parts(td, a_lo0 + ((uint32_t)a_part >> 4), a_hi, b_lo0, b_hi, idesc, 1u);     // lo * hi
+                            umma_f16_parts(td, a_lo0, a_hi, b_lo0 + ((uint32_t)b_part >> 4), b_hi, idesc, 1u);     // hi * lo
+                        }
+                    }
+                }
+                umma_commit(smem_u32(&ctl->empty[slot]));
+            }
+            __syncwarp();
+        }
+        if (elect_one()) umma_commit(smem_u32(&ctl->acc_full));
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_d, (uint32_t)g.tmem_cols);
+}
+
 // dw[co][ci][tap] = sum_s partial[s][co][tap][ci]   (PyTorch OIHW order; drops padded input channels)
 __global__ void wgrad_reduce_kernel(const float* partial, int splits, int c_out, int taps, int c_in, int c_in_real,
                                     float* dw) {
@@ -380,6 +539,36 @@ int build_wgeom(const disco_wgrad_desc* d, WGeom* g) {
     while (cols < d->taps * nb) cols *= 2;
     DISCO_REQUIRE(cols <= 512, "wgrad: accumulators exceed TMEM");
     g->tmem_cols = cols;
+    // operand-swapped kernel for the skinny 3x3 stride-1 layers (see wgrad_sw_kernel)
+    g->sw = 0; g->kws = 1;
+    {
+        const char* e = getenv("DISCO_WGRAD_SW");
+        const bool allow = !(e && e[0] == '0');
+        const bool stack = 3 * g->c_in <= 128 && d->c_out <= 64;                      // M = (kw, ci), 3 accumulators
+        const bool swap = g->c_in <= 128 && d->c_out <= 48 && g->c_in > d->c_out;     // M = ci, 9 accumulators
+        if (allow && g->mode == 0 && (stack || swap)) {
+            const int kws = stack ? 3 : 1;
+            const int chunks_b = g->c_in / 8;           // the whole c_in in one item
+            const int a_part = kws * chunks_b * g->plane_b, b_part = g->chunks_a * g->plane_a;
+            const int stage_bytes = ((2 * a_part + 2 * b_part + 127) / 128) * 128;
+            const int win = a_part + 16 * g->plane_b + 8 * 320 + 128;   // M = 128 reads 16 channel groups of the patch planes
+            int st = kMaxStages, sm = 0;
+            for (; st >= 1; --st) {
+                sm = kCtlBytes + st * stage_bytes;
+                const int need = kCtlBytes + (st - 1) * stage_bytes + win;
+                if (need > sm) sm = need;
+                if (sm <= 227 * 1024) break;
+            }
+            int c2 = 32;
+            while (c2 < (kws == 3 ? 3 : 9) * d->c_out) c2 *= 2;
+            if (st >= 1 && c2 <= 512) {
+                g->sw = 1; g->kws = kws;
+                g->chunks_b = chunks_b; g->nb = g->c_in; g->nblks = 1; g->mblks = 1;
+                g->a_part = a_part; g->b_part = b_part; g->stage_bytes = stage_bytes;
+                g->stages = st; g->smem_bytes = sm; g->tmem_cols = c2;
+            }
+        }
+    }
     // split-K: aim at ~2 waves of CTAs, at least 2 pixel tiles per CTA
     const int items = g->mblks * g->nblks;
     int splits = (2 * g_sms + items - 1) / items;
@@ -419,7 +608,18 @@ int disco_wgrad_tc_launch(const disco_wgrad_desc* d, void* stream) {
     DISCO_REQUIRE(d->partial, "wgrad: null partial workspace");
     DISCO_REQUIRE(d->splits >= g.splits, "wgrad: partial workspace sized for %d splits, need %d", d->splits, g.splits);
     cudaStream_t s = (cudaStream_t)stream;
-    if (g.mode == 0) rc = launch_wgrad<0>(g, s);
+    if (g.sw) {
+        static bool attr_set[64] = {false};
+        int dev = 0;
+        DISCO_CHECK_CUDA(cudaGetDevice(&dev));
+        if (dev < 64 && !attr_set[dev]) {
+            DISCO_CHECK_CUDA(cudaFuncSetAttribute(wgrad_sw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_set[dev] = true;
+        }
+        wgrad_sw_kernel<<<g.splits, kThreads, g.smem_bytes, s>>>(g);
+        DISCO_CHECK_CUDA(cudaGetLastError());
+        rc = DISCO_OK;
+    } else if (g.mode == 0) rc = launch_wgrad<0>(g, s);
     else if (g.mode == 1) rc = launch_wgrad<1>(g, s);
     else rc = launch_wgrad<2>(g, s);
     if (rc < 0) return rc;
