@@ -293,7 +293,7 @@ __global__ void pwf_running_kernel(const disco_pwf_train_desc d) {
 
 // PASS 0: sums of layer 3's gradient (+ dW4, db4); 1: layer 2 (+ dW3); 2: layer 1 (+ dW2); 3: gradient wrt `en`
 template <int PASS>
-__global__ void __launch_bounds__(kPW * 32, 1) pwf_bwd_pass_kernel(const disco_pwf_train_desc d) {
+__global__ void __launch_bounds__(kPW * 32, PASS == 2 ? 1 : 2) pwf_bwd_pass_kernel(const disco_pwf_train_desc d) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     PairSmem& s = *reinterpret_cast<PairSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
