@@ -295,3 +295,43 @@ def test_training_layer_tables_match_the_reference_parameters():
     rec = np.load(os.path.join(GOLD, "train_a2_b1.npz"))
     params = set(rec["grad_names"].tolist())
     assert live == params - set(rec["grad_none"].tolist())
+
+
+def test_patcher_swaps_the_reference_classes_in_place():
+    """The drop-in mechanism against the REAL package layout (build container only: /root/reference is absent on the
+    GPU box): after `patch_coperception()`, `from coperception.models.det import *` -- what tools/det/train_codet.py:12
+    and test_codet.py:14 do -- yields our classes, constructible with the reference's own Config object."""
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("reference tree not present")
+    ref_import.install_bypass(mock_heavy=True)
+    import importlib
+    det_pkg = importlib.import_module("coperception.models.det")
+    ref_disco = det_pkg.DiscoNet
+    originals = {n: getattr(det_pkg, n) for n in ("DiscoNet", "FaFNet", "TeacherNet")}
+    from disconet_b200 import patch
+    import disconet_b200
+    patch.patch_coperception()
+    try:
+        ns = {}
+        exec("from coperception.models.det import *", ns)
+        assert ns["DiscoNet"] is disconet_b200.DiscoNet and ns["FaFNet"] is disconet_b200.FaFNet
+        assert ns["TeacherNet"] is disconet_b200.TeacherNet
+        from coperception.configs.Config import Config
+        cfg = Config("train", binary=True, only_det=True)
+        m = ns["DiscoNet"](cfg, layer=3, kd_flag=1, num_agent=5, compress_level=0, only_v2i=False)   # train_codet.py:115-123
+        r = ref_disco(cfg, layer=3, kd_flag=1, num_agent=5, compress_level=0, only_v2i=False)
+        assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, tuple(v.shape)) for k, v in r.state_dict().items()]
+        assert [k for k, _ in m.named_parameters()] == [k for k, _ in r.named_parameters()]      # Adam state reload order
+        m.load_state_dict(r.state_dict())
+        # checkpoints written through nn.DataParallel carry the `module.` prefix (test_codet.py:190-196)
+        torch.nn.DataParallel(m).load_state_dict({"module." + k: v for k, v in r.state_dict().items()})
+        seg_pkg = importlib.import_module("coperception.models.seg")
+        assert seg_pkg.DiscoNet is disconet_b200.seg.SegDiscoNet
+    finally:
+        for name, cls in originals.items():
+            setattr(det_pkg, name, cls)
+            setattr(importlib.import_module(f"coperception.models.det.{name}"), name, cls)
+        seg_mod = importlib.import_module("coperception.models.seg.DiscoNet")
+        importlib.reload(seg_mod)
+        importlib.import_module("coperception.models.seg").DiscoNet = seg_mod.DiscoNet
