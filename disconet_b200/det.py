@@ -63,6 +63,7 @@ class _TrainFn(torch.autograd.Function):
     def forward(ctx, runner, bevs, trans, num_agent, outage_host, kd_keys, names, *params):
         out = runner.forward(bevs, trans, num_agent, outage_host)
         ctx.runner, ctx.kd_keys, ctx.names = runner, kd_keys, names
+        ctx.generation = runner.generation
         tensors = []
         if "cls" in out:
             tensors += [out["cls"], out["loc"]]
@@ -72,6 +73,11 @@ class _TrainFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *gs):
+        if ctx.generation != ctx.runner.generation:
+            raise RuntimeError(
+                "backward() of a stale forward: disconet_b200 keeps ONE set of saved activations per input shape, so the "
+                "backward has to run before the next training-mode forward of the same model and shape "
+                "(FaFModule.step does: forward, loss, backward, optimizer step)")
         grads = {}
         gs = list(gs)
         if ctx.has_heads:

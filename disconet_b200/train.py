@@ -197,6 +197,7 @@ class TrainRunner:
         self._sig = None
         self._graphs = {"fwd": None, "bwd": None}
         self._steps = 0
+        self.generation = 0          # bumped by every forward: the saved activations belong to the LAST forward only
         self._build()
 
     # ------------------------------------------------------------------------------------------------
@@ -606,6 +607,7 @@ class TrainRunner:
         if self._signature() != self._sig:
             self._build()                      # parameters were re-allocated (e.g. .to(), new load)
         stream = torch.cuda.current_stream(dev).cuda_stream
+        self.generation += 1
         self.bev_in.copy_(bevs.detach().reshape(self.bev_in.shape), non_blocking=True)
         if self.fused_key:
             self.trans.copy_(trans.detach(), non_blocking=True)

@@ -522,3 +522,18 @@ def test_training_step_flags_match_oracle(name, cuda_dev):
                          "decoder.bn3", "decoder.bn4", "decoder.conv3d")) or "num_batches" in k:
             continue
         assert rel_max(m.state_dict()[k].float().cpu(), v.float()) <= 1e-3, k
+
+
+def test_backward_of_a_stale_forward_raises(cuda_dev):
+    """One set of saved activations per shape: a second training forward invalidates the first one's backward, loudly."""
+    from disconet_b200 import FaFNet
+    m = FaFNet(_Cfg(), kd_flag=0, num_agent=2)
+    m.load_state_dict(O.synth_state_dict(m.state_dict(), seed=71))
+    m = m.to(cuda_dev).train()
+    bev = O.synth_bev(2, H=64, W=64, seed=72).to(cuda_dev)
+    r1 = m(bev)
+    r2 = m(bev)
+    with pytest.raises(RuntimeError, match="stale forward"):
+        r1["cls"].sum().backward()
+    r2["cls"].sum().backward()
+    assert all(p.grad is None or torch.isfinite(p.grad).all() for p in m.parameters())
