@@ -81,6 +81,13 @@ int disco_fusion_forward(const disco_fusion_desc* d, void* stream) {
     return disco_fusion_launch(d, stream);
 }
 
+int disco_det_candidates(const float* loc, const float* cls, const float* anchors, long long anchors_per_agent,
+                         long long anchor_agent_stride, int n_agents, float thresh, int max_cand, int* count, float* corners,
+                         float* scores, int* index, void* stream) {
+    return disco_det_candidates_launch(loc, cls, anchors, anchors_per_agent, anchor_agent_stride, n_agents, thresh, max_cand, count,
+                                       corners, scores, index, stream);
+}
+
 // ---- BEV segmentation U-Net ---------------------------------------------------------------
 int disco_maxpool2(const void* src_hi, long long src_lo_off, void* dst_hi, long long dst_lo_off, int precision, int n, int h,
                    int w, int c, void* stream) {

@@ -229,3 +229,63 @@ int disco_bev_scatter_launch(const int* voxel_indices, int n_voxels, const int* 
     }
     return DISCO_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Detection candidates: the per-anchor half of apply_nms_det (utils/detection_util.py:256-373)
+// on the device -- foreground probability softmax(cls)[1], threshold (postprocess.py:85: scores > 0.7), box decode
+// (bev_box_decode_torch :376-400) and the four rotated corners (obj_util.py:271-359) -- compacted with one atomic per
+// candidate.  The reference copies ALL scores and ALL decoded boxes of every agent to the host (11 MB per agent) and
+// filters there; this writes only the survivors (a few hundred boxes).  Order is restored by a sort on the scores.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256) det_candidates_kernel(const float* __restrict__ loc, const float* __restrict__ cls,
+                                                             const float* __restrict__ anchors, long long anchors_per_agent,
+                                                             long long anchor_agent_stride, int n_agents, float thresh,
+                                                             int max_cand, int* __restrict__ count, float* __restrict__ corners,
+                                                             float* __restrict__ scores, int* __restrict__ index) {
+    const long long total = anchors_per_agent * n_agents;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const float2 z = __ldg(reinterpret_cast<const float2*>(cls) + e);
+        const float m = fmaxf(z.x, z.y);
+        const float e0 = expf(z.x - m), e1 = expf(z.y - m);
+        const float score = e1 / (e0 + e1);
+        if (!(score > thresh)) continue;
+        const int agent = (int)(e / anchors_per_agent);
+        const long long a = e - agent * anchors_per_agent;
+        const int slot = atomicAdd(count + agent, 1);
+        if (slot >= max_cand) continue;
+        const float* p = loc + e * 6;
+        const float* q = anchors + agent * anchor_agent_stride + a * 6;
+        const float h = q[3] / expf(p[3]), w = q[2] / expf(p[2]);
+        const float x = q[0] - w * p[0], y = q[1] - h * p[1];
+        const float s = q[4] * p[5] + q[5] * p[4], c = q[5] * p[5] - q[4] * p[4];
+        const float nx[4] = {-0.5f, 0.5f, 0.5f, -0.5f}, ny[4] = {0.5f, 0.5f, -0.5f, -0.5f};
+        float* o = corners + ((long long)agent * max_cand + slot) * 8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float px = w * nx[k], py = h * ny[k];
+            o[2 * k] = px * c + py * s + x;
+            o[2 * k + 1] = -px * s + py * c + y;
+        }
+        scores[(long long)agent * max_cand + slot] = score;
+        index[(long long)agent * max_cand + slot] = (int)a;
+    }
+}
+
+}  // namespace
+
+int disco_det_candidates_launch(const float* loc, const float* cls, const float* anchors, long long anchors_per_agent,
+                                long long anchor_agent_stride, int n_agents, float thresh, int max_cand, int* count,
+                                float* corners, float* scores, int* index, void* stream) {
+    DISCO_REQUIRE(loc && cls && anchors && count && corners && scores && index, "det_candidates: null tensor");
+    DISCO_REQUIRE(anchors_per_agent > 0 && n_agents > 0 && max_cand > 0, "det_candidates: bad sizes");
+    cudaStream_t s = (cudaStream_t)stream;
+    DISCO_CHECK_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * n_agents, s));
+    long long blocks = (anchors_per_agent * n_agents + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    det_candidates_kernel<<<(unsigned)blocks, 256, 0, s>>>(loc, cls, anchors, anchors_per_agent, anchor_agent_stride, n_agents, thresh,
+                                                           max_cand, count, corners, scores, index);
+    DISCO_CHECK_CUDA(cudaGetLastError());
+    return DISCO_OK;
+}

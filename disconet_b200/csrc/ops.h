@@ -53,3 +53,8 @@ int disco_maxpool2_launch(const void* src_hi, long long src_lo_off, void* dst_hi
 int disco_upsample_bilinear2x_launch(const void* src_hi, long long src_lo_off, void* dst_hi, long long dst_lo_off, int precision,
                                      int n, int h, int w, int c, void* stream);
 int disco_nhwc_to_nchw_launch(const float* src, int n, int h, int w, int c_src, int c, float* dst, void* stream);
+
+// Detection candidates (misc.cu): score > thresh anchors of every agent -> corners / scores / anchor index, compacted
+int disco_det_candidates_launch(const float* loc, const float* cls, const float* anchors, long long anchors_per_agent,
+                                long long anchor_agent_stride, int n_agents, float thresh, int max_cand, int* count,
+                                float* corners, float* scores, int* index, void* stream);

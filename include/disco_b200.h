@@ -128,6 +128,15 @@ typedef struct disco_fusion_desc {
 
 int disco_fusion_forward(const disco_fusion_desc* d /* host */, void* stream);
 
+/* The per-anchor half of apply_nms_det (utils/detection_util.py:256-373) for n_agents agents: foreground probability
+ * softmax(cls)[1] of cls [n_agents*anchors_per_agent, 2], threshold (postprocess.py:85), bev_box_decode_torch (:376-400)
+ * of loc [.., 6] against anchors (agent stride anchor_agent_stride floats; 0 = shared), rotated corners (obj_util.py:271-359).
+ * Survivors are compacted per agent: count[agent] (may exceed max_cand: then only max_cand were stored), corners
+ * [n_agents, max_cand, 4, 2], scores / index [n_agents, max_cand] (index = anchor number inside the agent), unordered. */
+int disco_det_candidates(const float* loc, const float* cls, const float* anchors, long long anchors_per_agent,
+                         long long anchor_agent_stride, int n_agents, float thresh, int max_cand, int* count, float* corners,
+                         float* scores, int* index, void* stream);
+
 /* ---- BEV segmentation U-Net (models/seg/SegModelBase.py) around disco_conv_forward ------------------------
  * nn.MaxPool2d(2) of the Down blocks (:113-123): activation buffer [n,h,w,c] -> [n,h/2,w/2,c]. */
 int disco_maxpool2(const void* src_hi, long long src_lo_off, void* dst_hi, long long dst_lo_off, int precision, int n, int h,

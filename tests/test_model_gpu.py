@@ -195,3 +195,34 @@ def test_communication_outage_matches_reference_semantics(cuda_dev):
         assert rel_max(res[k].cpu(), ref[k]) <= 1e-3, k
     ref_w = [e for per_b in ref["weights"] for e in per_b]
     assert [len(e) for e in wl] == [len(e) for e in ref_w]
+
+
+def test_det_candidates_match_post_oracle(cuda_dev):
+    """f3: score / threshold / decode / corners kernel against the numpy oracle of apply_nms_det's per-anchor stage."""
+    from disconet_b200.post import det_candidates
+    from oracle import post_oracle as P
+    rng = np.random.default_rng(17)
+    n, H, W, A = 3, 32, 48, 6
+    cls = (rng.standard_normal((n, H * W * A, 2)) * 1.5).astype(np.float32)
+    loc = (rng.standard_normal((n, H, W, A, 1, 6)) * 0.3).astype(np.float32)
+    anchors = np.concatenate([rng.uniform(-32, 32, (n, H, W, A, 2)), rng.uniform(1, 5, (n, H, W, A, 2)),
+                              rng.uniform(-1, 1, (n, H, W, A, 2))], -1).astype(np.float32)
+    got = det_candidates(torch.from_numpy(loc).to(cuda_dev), torch.from_numpy(cls).to(cuda_dev), torch.from_numpy(anchors).to(cuda_dev),
+                         score_thresh=0.7)
+    assert len(got) == n
+    for a in range(n):
+        cor, sc, idx = P.det_candidates(loc[a], cls[a], anchors[a], 0.7)
+        g = got[a]
+        assert g["index"].shape[0] == idx.shape[0] > 50
+        # same set of anchors; order is by score (ties may permute) -> compare after sorting by anchor index
+        o_ref, o_got = np.argsort(idx), np.argsort(g["index"].cpu().numpy())
+        assert np.array_equal(idx[o_ref], g["index"].cpu().numpy()[o_got])
+        assert np.abs(sc[o_ref] - g["score"].cpu().numpy()[o_got]).max() < 1e-6
+        assert np.abs(cor[o_ref] - g["corners"].cpu().numpy()[o_got]).max() <= 2e-5 * np.abs(cor).max()
+        s = g["score"].cpu().numpy()
+        assert np.all(s[:-1] >= s[1:]) and s.min() > 0.7
+    # anchors shared by all agents ([H, W, A, 6])
+    got2 = det_candidates(torch.from_numpy(loc).to(cuda_dev), torch.from_numpy(cls).to(cuda_dev), torch.from_numpy(anchors[0]).to(cuda_dev))
+    cor, sc, idx = P.det_candidates(loc[1], cls[1], anchors[0], 0.7)
+    o_ref, o_got = np.argsort(idx), np.argsort(got2[1]["index"].cpu().numpy())
+    assert np.abs(cor[o_ref] - got2[1]["corners"].cpu().numpy()[o_got]).max() <= 2e-5 * np.abs(cor).max()

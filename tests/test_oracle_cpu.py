@@ -335,3 +335,21 @@ def test_patcher_swaps_the_reference_classes_in_place():
         seg_mod = importlib.import_module("coperception.models.seg.DiscoNet")
         importlib.reload(seg_mod)
         importlib.import_module("coperception.models.seg").DiscoNet = seg_mod.DiscoNet
+
+
+def test_post_oracle_matches_reference():
+    """f3: the numpy restatement of score / decode / corners against the reference's own functions (build container)."""
+    from oracle import post_oracle as P, ref_import
+    if not ref_import.available():
+        pytest.skip("reference tree not present")
+    ref_import.install_bypass(mock_heavy=True)
+    from coperception.utils.detection_util import bev_box_decode_torch
+    from coperception.utils.obj_util import center_to_corner_box2d
+    rng = np.random.default_rng(3)
+    enc = (rng.standard_normal((500, 6)) * 0.3).astype(np.float32)
+    anc = np.concatenate([rng.uniform(-30, 30, (500, 2)), rng.uniform(1, 5, (500, 2)), rng.uniform(-1, 1, (500, 2))], 1).astype(np.float32)
+    dec_ref = bev_box_decode_torch(torch.from_numpy(enc), torch.from_numpy(anc)).numpy()
+    dec = P.decode_boxes(enc, anc)
+    assert np.abs(dec - dec_ref).max() <= 1e-5 * np.abs(dec_ref).max()
+    cor_ref = center_to_corner_box2d(dec_ref[:, :2], dec_ref[:, 2:4], dec_ref[:, 4:])
+    assert np.abs(P.box_corners(dec_ref) - cor_ref).max() <= 1e-5 * np.abs(cor_ref).max()
