@@ -97,6 +97,13 @@ int disco_upsample_bilinear2x(const void* src_hi, long long src_lo_off, void* ds
                               int h, int w, int c, void* stream) {
     return disco_upsample_bilinear2x_launch(src_hi, src_lo_off, dst_hi, dst_lo_off, precision, n, h, w, c, stream);
 }
+int disco_maxpool2_backward(const void* x_hi, long long x_lo_off, int precision, const float* g, float* gx, int n, int h, int w, int c,
+                            void* stream) {
+    return disco_maxpool2_backward_launch(x_hi, x_lo_off, precision, g, gx, n, h, w, c, stream);
+}
+int disco_upsample_bilinear2x_backward(const float* g_up, float* gs, int n, int h, int w, int c, void* stream) {
+    return disco_upsample_bilinear2x_backward_launch(g_up, gs, n, h, w, c, stream);
+}
 int disco_nhwc_to_nchw(const float* src, int n, int h, int w, int c_src, int c, float* dst, void* stream) {
     return disco_nhwc_to_nchw_launch(src, n, h, w, c_src, c, dst, stream);
 }

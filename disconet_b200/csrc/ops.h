@@ -58,3 +58,6 @@ int disco_nhwc_to_nchw_launch(const float* src, int n, int h, int w, int c_src, 
 int disco_det_candidates_launch(const float* loc, const float* cls, const float* anchors, long long anchors_per_agent,
                                 long long anchor_agent_stride, int n_agents, float thresh, int max_cand, int* count,
                                 float* corners, float* scores, int* index, void* stream);
+int disco_maxpool2_backward_launch(const void* x_hi, long long x_lo_off, int precision, const float* g, float* gx, int n, int h, int w,
+                                   int c, void* stream);
+int disco_upsample_bilinear2x_backward_launch(const float* g_up, float* gs, int n, int h, int w, int c, void* stream);

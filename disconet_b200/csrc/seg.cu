@@ -114,6 +114,102 @@ __global__ void __launch_bounds__(kThreads) nhwc_to_nchw_kernel(const float* src
     }
 }
 
+// Backward of MaxPool2d(2): the gradient of a pooled cell goes to the FIRST maximum of its 2x2 block in scan order
+// (torch's argmax convention), zeros elsewhere.  x = the pool's input activation buffer; g fp32 [n, h/2, w/2, c].
+__global__ void __launch_bounds__(kThreads) maxpool2_bwd_kernel(const uint16_t* x, long long x_lo, int precision, const float* g,
+                                                                float* gx, int n, int h, int w, int c) {
+    const int ho = h >> 1, wo = w >> 1, groups = c >> 3;
+    const long long total = (long long)n * ho * wo * groups;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int gq = (int)(e % groups);
+        long long r = e / groups;
+        const int px = (int)(r % wo); r /= wo;
+        const int py = (int)(r % ho);
+        const long long img = r / ho;
+        const long long base = ((img * h + 2 * py) * w + 2 * px) * c + gq * 8;
+        const long long off[4] = {0, c, (long long)w * c, (long long)w * c + c};
+        float v[4][8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) load_act8(x + base + off[k], x_lo, precision, v[k]);
+        const float4* gp = reinterpret_cast<const float4*>(g + (((img * ho + py) * wo + px) * c + gq * 8));
+        const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        float o[4][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int best = 0;
+            float m = v[0][i];
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+                if (v[k][i] > m) { m = v[k][i]; best = k; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k][i] = (k == best) ? gg[i] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float4* dst = reinterpret_cast<float4*>(gx + base + off[k]);
+            dst[0] = make_float4(o[k][0], o[k][1], o[k][2], o[k][3]);
+            dst[1] = make_float4(o[k][4], o[k][5], o[k][6], o[k][7]);
+        }
+    }
+}
+
+// Backward of the bilinear x2 upsample (align_corners=True): transpose of upsample2x_kernel as a gather -- source cell
+// (y, x) collects w_y * w_x * g_up[oy, ox] from the output rows / columns whose interpolation footprint contains it
+// (the same float formulas as the forward, so the weights match bit for bit).  g_up fp32 [n, 2h, 2w, c] -> gs [n, h, w, c].
+__global__ void __launch_bounds__(kThreads) upsample2x_bwd_kernel(const float* g_up, float* gs, int n, int h, int w, int c) {
+    const int ho = 2 * h, wo = 2 * w, groups = c >> 3;
+    const float rh = ho > 1 ? (float)(h - 1) / (float)(ho - 1) : 0.f;
+    const float rw = wo > 1 ? (float)(w - 1) / (float)(wo - 1) : 0.f;
+    const long long total = (long long)n * h * w * groups;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int gq = (int)(e % groups);
+        long long r = e / groups;
+        const int x = (int)(r % w); r /= w;
+        const int y = (int)(r % h);
+        const long long img = r / h;
+        // candidate output rows / columns: sy = rh * oy in [y - 1, y + 1]
+        const int oy_lo = max(0, 2 * y - 3), oy_hi = min(ho - 1, 2 * y + 3);
+        const int ox_lo = max(0, 2 * x - 3), ox_hi = min(wo - 1, 2 * x + 3);
+        float wy[7], wx[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            wy[k] = 0.f; wx[k] = 0.f;
+            const int oy = oy_lo + k;
+            if (oy <= oy_hi) {
+                const float sy = rh * oy;
+                const int y0 = (int)sy, y1 = y0 + (y0 < h - 1 ? 1 : 0);
+                const float ly = sy - y0;
+                if (y0 == y) wy[k] += 1.f - ly;
+                if (y1 == y) wy[k] += ly;
+            }
+            const int ox = ox_lo + k;
+            if (ox <= ox_hi) {
+                const float sx = rw * ox;
+                const int x0 = (int)sx, x1 = x0 + (x0 < w - 1 ? 1 : 0);
+                const float lx = sx - x0;
+                if (x0 == x) wx[k] += 1.f - lx;
+                if (x1 == x) wx[k] += lx;
+            }
+        }
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int a = 0; a < 7; ++a) {
+            if (wy[a] == 0.f) continue;
+            for (int b = 0; b < 7; ++b) {
+                const float wgt = wy[a] * wx[b];
+                if (wgt == 0.f) continue;
+                const float4* p = reinterpret_cast<const float4*>(g_up + (((img * ho + oy_lo + a) * wo + ox_lo + b) * c + gq * 8));
+                const float4 u0 = __ldg(p), u1 = __ldg(p + 1);
+                acc[0] = fmaf(wgt, u0.x, acc[0]); acc[1] = fmaf(wgt, u0.y, acc[1]); acc[2] = fmaf(wgt, u0.z, acc[2]); acc[3] = fmaf(wgt, u0.w, acc[3]);
+                acc[4] = fmaf(wgt, u1.x, acc[4]); acc[5] = fmaf(wgt, u1.y, acc[5]); acc[6] = fmaf(wgt, u1.z, acc[6]); acc[7] = fmaf(wgt, u1.w, acc[7]);
+            }
+        }
+        float4* dst = reinterpret_cast<float4*>(gs + (((img * h + y) * w + x) * c + gq * 8));
+        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+}
+
 unsigned blocks_for(long long total) {
     long long b = (total + kThreads - 1) / kThreads;
     if (b > 148 * 16) b = 148 * 16;
@@ -144,6 +240,22 @@ int disco_nhwc_to_nchw_launch(const float* src, int n, int h, int w, int c_src, 
     DISCO_REQUIRE(src && dst && n > 0 && h > 0 && w > 0 && c > 0 && c <= c_src, "nhwc_to_nchw: bad arguments");
     const long long hw = (long long)h * w, total = hw * n;
     nhwc_to_nchw_kernel<<<blocks_for(total), kThreads, 0, (cudaStream_t)stream>>>(src, c_src, c, hw, total, dst);
+    DISCO_CHECK_CUDA(cudaGetLastError());
+    return DISCO_OK;
+}
+
+int disco_maxpool2_backward_launch(const void* x_hi, long long x_lo_off, int precision, const float* g, float* gx, int n, int h, int w,
+                                   int c, void* stream) {
+    DISCO_REQUIRE(x_hi && g && gx && n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0 && c % 8 == 0, "maxpool2_backward: bad arguments");
+    maxpool2_bwd_kernel<<<blocks_for((long long)n * (h / 2) * (w / 2) * (c / 8)), kThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint16_t*>(x_hi), x_lo_off, precision, g, gx, n, h, w, c);
+    DISCO_CHECK_CUDA(cudaGetLastError());
+    return DISCO_OK;
+}
+
+int disco_upsample_bilinear2x_backward_launch(const float* g_up, float* gs, int n, int h, int w, int c, void* stream) {
+    DISCO_REQUIRE(g_up && gs && n > 0 && h > 1 && w > 1 && c % 8 == 0, "upsample_bilinear2x_backward: bad arguments");
+    upsample2x_bwd_kernel<<<blocks_for((long long)n * h * w * (c / 8)), kThreads, 0, (cudaStream_t)stream>>>(g_up, gs, n, h, w, c);
     DISCO_CHECK_CUDA(cudaGetLastError());
     return DISCO_OK;
 }

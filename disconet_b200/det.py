@@ -64,10 +64,8 @@ class _TrainFn(torch.autograd.Function):
         out = runner.forward(bevs, trans, num_agent, outage_host)
         ctx.runner, ctx.kd_keys, ctx.names = runner, kd_keys, names
         ctx.generation = runner.generation
-        tensors = []
-        if "cls" in out:
-            tensors += [out["cls"], out["loc"]]
-        ctx.has_heads = "cls" in out
+        ctx.primary = tuple(k for k in ("cls", "loc", "logits") if k in out)
+        tensors = [out[k] for k in ctx.primary]
         tensors += [runner.kd_map(k) for k in kd_keys]
         return tuple(tensors)
 
@@ -80,9 +78,8 @@ class _TrainFn(torch.autograd.Function):
                 "(FaFModule.step does: forward, loss, backward, optimizer step)")
         grads = {}
         gs = list(gs)
-        if ctx.has_heads:
-            grads["cls"], grads["loc"] = gs[0], gs[1]
-            gs = gs[2:]
+        for k in ctx.primary:
+            grads[k] = gs.pop(0)
         for k, g in zip(ctx.kd_keys, gs):
             grads[k] = g
         res = ctx.runner.backward(grads)
@@ -406,7 +403,11 @@ def runner_param_names(runner) -> set:
     """Names of the parameters a TrainRunner differentiates (the reference's live parameters)."""
     names = set()
     for L in runner.enc + runner.dec:
-        names |= {L.conv + ".weight", L.conv + ".bias", L.bn + ".weight", L.bn + ".bias"}
+        if getattr(L, "kind", "conv") != "conv":
+            continue
+        names |= {L.conv + ".weight", L.conv + ".bias"}
+        if L.bn:
+            names |= {L.bn + ".weight", L.bn + ".bias"}
     if runner.head_layers:
         for m in ("classification.conv1", "classification.conv2", "classification.bn1", "regression.box_prediction.0",
                   "regression.box_prediction.1", "regression.box_prediction.3"):

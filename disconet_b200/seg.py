@@ -14,7 +14,7 @@ from typing import Dict, Optional
 import torch
 import torch.nn as nn
 
-from . import engine, ops
+from . import engine, ops, train as train_mod
 from ._lib import FusionDesc, check, load
 from .modules import ParamHolder, PixelWeightedFusionParams
 from .plan import fold_bn, pack_conv
@@ -86,6 +86,7 @@ class SegDiscoNet(nn.Module):
         self._plans = None
         self._plans_key = None
         self._ws: Dict[tuple, "_SegWorkspace"] = {}
+        self._runners: Dict[tuple, train_mod.TrainRunner] = {}
 
     @property
     def precision(self) -> int:
@@ -110,8 +111,8 @@ class SegDiscoNet(nn.Module):
         """x [A*B, n_channels, H, W] float (agent-major), trans_matrices [B, A, A, 4, 4], num_agent_tensor [B, A].
         Returns (logits, x9, x8, x7, x6, x5, feat_mat) if kd_flag else logits  (FusionBase.py:24-84)."""
         load()
-        if self.training:
-            raise NotImplementedError("disconet_b200.seg implements the eval-mode forward; call model.eval()")
+        if self.training and self.precision_name != "bf16x3":
+            raise NotImplementedError("training mode runs in the default bf16x3 precision only")
         if not x.is_cuda:
             raise ValueError("disconet_b200 runs on CUDA tensors only (no CPU fallback); got a CPU input")
         if x.dim() != 4 or x.shape[1] != self.n_channels:
@@ -124,6 +125,8 @@ class SegDiscoNet(nn.Module):
         if tuple(trans_matrices.shape) != (B, A, A, 4, 4):
             raise ValueError(f"trans_matrices must be [{B},{A},{A},4,4] (got {tuple(trans_matrices.shape)})")
         dev = x.device
+        if self.training:
+            return self._forward_train(x, trans_matrices, num_agent_tensor, B)
         P = self.plans()
         key = (N, H, W, str(dev))
         ws = self._ws.get(key)
@@ -142,6 +145,57 @@ class SegDiscoNet(nn.Module):
             nchw = lambda k: ops.act_to_nchw_f32(ws.buf[k], self.precision)
             return logits, nchw("x9"), nchw("x8"), nchw("x7"), nchw("x6"), nchw("x5"), nchw("feat")
         return logits
+
+    def _forward_train(self, x, trans_matrices, num_agent_tensor, B):
+        """model.train() forward + autograd (SegModule.step, utils/SegModule.py:45-120, calls it like this)."""
+        from .det import _TrainFn, runner_param_names
+        if self.n_channels != 13 or self.n_classes != 8:
+            raise NotImplementedError("segmentation training is built for the reference configuration (13 channels, 8 classes)")
+        N, _, H, W = x.shape
+        dev = x.device
+        kd_keys = list(SEG_KD_KEYS) if self.kd_flag else []
+        key = (N, H, W, str(dev), bool(self.only_v2i), tuple(kd_keys))
+        runner = self._runners.get(key)
+        if runner is None:
+            runner = train_mod.TrainRunner(self._getter(), N, H, W, dev, "", "", heads=False, pwf_prefix="pixel_weighted_fusion.",
+                                           batch_size=B, agents=self.num_agent, only_v2i=bool(self.only_v2i), kd_keys=kd_keys,
+                                           nodes=seg_layers(), fusion_spec=("x4", "feat", 3, 512))
+            self._runners[key] = runner
+        runner.get = self._getter()
+        live = runner_param_names(runner)
+        named = dict(self.named_parameters())
+        names = tuple(k for k in named if k in live)
+        bev = x.detach().permute(0, 2, 3, 1).unsqueeze(1)          # [N, 1, H, W, 13], the layout the pack kernel reads
+        outs = list(_TrainFn.apply(runner, bev, trans_matrices, num_agent_tensor, None, tuple(kd_keys), names,
+                                   *[named[k] for k in names]))
+        return (outs[0], *outs[1:]) if self.kd_flag else outs[0]
+
+
+SEG_KD_KEYS = ("x9", "x8", "x7", "x6", "x5", "feat")
+
+
+def seg_layers():
+    """U-Net layer tables for the training driver (SegModelBase.py:17-26,93-151; FusionBase.py:24-84)."""
+    L = train_mod.Layer
+
+    def dc(name, prefix, srcs, mid, out, cin, cmid, cout, level, c_in_real=0):
+        return [L(name + "a", f"{prefix}.0", f"{prefix}.1", srcs, [0] * len(srcs), mid, cin, cmid, level=level, c_in_real=c_in_real,
+                  need_dgrad=srcs != ["a0"]),          # the network input needs no gradient
+                L(name + "b", f"{prefix}.3", f"{prefix}.4", [mid], [0], out, [cmid], cout, level=level)]
+
+    pool = lambda name, src, out, c, level: L(name, "", None, [src], [0], out, [c], c, level=level, kind="pool")
+    up = lambda name, src, out, c, level: L(name, "", None, [src], [0], out, [c], c, level=level, kind="up")
+    E = (dc("inc", "inc.double_conv", ["a0"], "x1a", "x1", [16], 64, 64, 0, c_in_real=13) + [pool("pool1", "x1", "p1", 64, 0)] +
+         dc("d1", "down1.maxpool_conv.1.double_conv", ["p1"], "x2a", "x2", [64], 128, 128, 1) + [pool("pool2", "x2", "p2", 128, 1)] +
+         dc("d2", "down2.maxpool_conv.1.double_conv", ["p2"], "x3a", "x3", [128], 256, 256, 2) + [pool("pool3", "x3", "p3", 256, 2)] +
+         dc("d3", "down3.maxpool_conv.1.double_conv", ["p3"], "x4a", "x4", [256], 512, 512, 3))
+    D = ([pool("pool4", "feat", "p4", 512, 3)] + dc("d4", "down4.maxpool_conv.1.double_conv", ["p4"], "x5a", "x5", [512], 512, 512, 4) +
+         [up("up5", "x5", "u5", 512, 4)] + dc("u1", "up1.conv.double_conv", ["feat", "u5"], "x6a", "x6", [512, 512], 512, 256, 3) +
+         [up("up6", "x6", "u6", 256, 3)] + dc("u2", "up2.conv.double_conv", ["x3", "u6"], "x7a", "x7", [256, 256], 256, 128, 2) +
+         [up("up7", "x7", "u7", 128, 2)] + dc("u3", "up3.conv.double_conv", ["x2", "u7"], "x8a", "x8", [128, 128], 128, 64, 1) +
+         [up("up8", "x8", "u8", 64, 1)] + dc("u4", "up4.conv.double_conv", ["x1", "u8"], "x9a", "x9", [64, 64], 64, 64, 0) +
+         [L("outc", "outc.conv", None, ["x9"], [0], "", [64], 16, taps=1, level=0, n_real=8)])
+    return E, D
 
 
 def build_seg_plans(get, precision: int, n_channels: int, n_classes: int):

@@ -47,6 +47,8 @@ class Layer:
     level: int = 0               # resolution level of the conv INPUT (0: H, 1: H/2, ...)
     c_in_real: int = 0
     need_dgrad: bool = True
+    kind: str = "conv"           # "conv" | "pool" (MaxPool2d(2): srcs[0] -> out) | "up" (bilinear x2, align_corners: srcs[0] -> out)
+    n_real: int = 0              # real output channels when c_out is padded (seg OutConv: 8 of 16)
 
     def __post_init__(self):
         if not self.c_in_real:
@@ -132,7 +134,11 @@ class TrainRunner:
 
     def __init__(self, get, n: int, h: int, w: int, device, enc_prefix: str, dec_prefix: str, *, heads: bool = True,
                  pwf_prefix: Optional[str] = None, batch_size: int = 1, agents: int = 1, fusion_level: int = 3,
-                 only_v2i: bool = False, kd_keys: Sequence[str] = (), compress_level: int = 0):
+                 only_v2i: bool = False, kd_keys: Sequence[str] = (), compress_level: int = 0,
+                 nodes: Optional[Tuple[List[Layer], List[Layer]]] = None, fusion_spec: Optional[tuple] = None):
+        """`nodes` = (encoder, decoder) layer lists replacing the detection backbone tables (the segmentation U-Net
+        passes its own, incl. pool / up nodes and the `outc` output conv); `fusion_spec` = (feature key, fused key,
+        resolution level, channels) of the collaboration map when it is not x_3 / x_2 of the detection backbone."""
         if h % 16 or w % 16:
             raise ValueError(f"BEV size {h}x{w} must be a multiple of 16")
         self.get, self.n, self.h, self.w, self.dev = get, n, h, w, device
@@ -149,7 +155,13 @@ class TrainRunner:
         if cc and cc % 16:
             raise NotImplementedError("training mode supports compress_level <= 4 (bottleneck width a multiple of 16)")
         self.x3_key = "x3d" if cc else "x3"
-        E, D = backbone_layers(enc_prefix, dec_prefix, self.fused_key, fusion_level, compress_cc=cc)
+        self.fusion_spec = fusion_spec
+        if fusion_spec is not None:
+            self.fused_key = fusion_spec[1]
+        if nodes is not None:
+            E, D = nodes
+        else:
+            E, D = backbone_layers(enc_prefix, dec_prefix, self.fused_key, fusion_level, compress_cc=cc)
         self.enc, self.dec = E, D
         self.head_layers: List[Layer] = []
         if heads:
@@ -170,6 +182,11 @@ class TrainRunner:
             hi, wi = self.res[L.level]
             ho, wo = (hi - 1) // L.stride + 1, (wi - 1) // L.stride + 1
             S = self.st[L.name] = _LayerState()
+            if L.kind != "conv":
+                ho, wo = (hi // 2, wi // 2) if L.kind == "pool" else (hi * 2, wi * 2)
+                self.act[L.out] = A_(ho, wo, L.c_out)
+                S.hw_in, S.hw_out = (hi, wi), (ho, wo)
+                continue
             S.z = torch.empty((n, ho, wo, L.c_out), dtype=torch.float32, device=device) if L.bn else None
             if L.out:
                 self.act[L.out] = A_(ho, wo, L.c_out)
@@ -178,11 +195,20 @@ class TrainRunner:
             if L.bn:
                 S.stats = torch.zeros(2 * L.c_out, dtype=torch.float32, device=device)
         if self.fused_key:
-            hf, wf = self.res[fusion_level]
-            cf = 256 if fusion_level == 3 else 128
-            self.feat_key = self.x3_key if fusion_level == 3 else "x2"
+            if fusion_spec is not None:
+                self.feat_key, _, lvl, cf = fusion_spec
+                hf, wf = self.res[lvl]
+            else:
+                hf, wf = self.res[fusion_level]
+                cf = 256 if fusion_level == 3 else 128
+                self.feat_key = self.x3_key if fusion_level == 3 else "x2"
             self.fuse_hw, self.fuse_c = (hf, wf), cf
             self.act[self.fused_key] = A_(hf, wf, cf)
+        self.has_outc = any(L.name == "outc" for L in self.layers)
+        if self.has_outc:
+            self.logits = torch.empty((n, h, w, 16), dtype=torch.float32, device=device)
+            self.glogits = torch.zeros((n, h, w, 8), dtype=torch.float32, device=device)
+            self.gzero8 = torch.zeros((n, h, w, 8), dtype=torch.float32, device=device)
         if heads:
             self.cls = torch.empty((n, h, w, 12), dtype=torch.float32, device=device)
             self.loc = torch.empty((n, h, w, 36), dtype=torch.float32, device=device)
@@ -314,12 +340,19 @@ class TrainRunner:
         # ---- forward descriptors + packs --------------------------------------------------------------------
         for L in self.layers:
             S = self.st[L.name]
+            if L.kind != "conv":
+                src, dst = self.act[L.srcs[0]], self.act[L.out]
+                hi, wi = S.hw_in
+                fn = lib.disco_maxpool2 if L.kind == "pool" else lib.disco_upsample_bilinear2x
+                fwd_layer[L.name] = [("call", fn, (src.data_ptr(), ops._lo_off(src), dst.data_ptr(), ops._lo_off(dst), self.prec, n, hi, wi,
+                                                   L.c_out), f"{L.kind}[{L.name}]")]
+                continue
             w, b = raw(L)
             c_pad = sum(L.c_in)
-            wz = torch.zeros(w.shape[0], c_pad, w.shape[2], w.shape[3], device=dev)
-            S.plan = pack_conv(wz, torch.zeros(w.shape[0], device=dev), src_channels=L.c_in, stride=L.stride, relu=False,
+            wz = torch.zeros(L.c_out, c_pad, w.shape[2], w.shape[3], device=dev)
+            S.plan = pack_conv(wz, torch.zeros(L.c_out, device=dev), src_channels=L.c_in, stride=L.stride, relu=False,
                                precision=self.prec, name=L.conv)
-            pd = self._pack_desc(S.plan, w, b)
+            pd = self._pack_desc(S.plan, w, b, n_real=w.shape[0])
             pre.append((lib.disco_pack_weights, pd, f"pack[{L.name}]"))
             srcs = [self.act[k] for k in L.srcs]
             hi, wi = S.hw_in
@@ -327,6 +360,8 @@ class TrainRunner:
             ops_f = []
             if L.bn:
                 S.fwd = ops.ConvCall(S.plan, srcs, L.ups, (S.z,), n=n, h_in=hi, w_in=wi)
+            elif L.name == "outc":
+                S.fwd = ops.ConvCall(S.plan, srcs, L.ups, (self.logits,), n=n, h_in=hi, w_in=wi)
             else:
                 S.fwd = ops.ConvCall(S.plan, srcs, L.ups, (self.cls, self.loc), n=n, h_in=hi, w_in=wi, out_split=12)
             ops_f.append((lib.disco_conv_forward, S.fwd.desc, f"conv[{L.name}]"))
@@ -370,6 +405,23 @@ class TrainRunner:
         def layer_bwd_ops(L: Layer):
             S = self.st[L.name]
             out_ops = []
+            if L.kind != "conv":
+                srcs = gsrc.get(L.out, [])
+                if len(srcs) != 1 or srcs[0][1] != L.c_out or srcs[0][2] != 0 or srcs[0][3] != 0:
+                    raise RuntimeError(f"{L.name}: a {L.kind} node needs exactly one dense gradient source for {L.out}")
+                g_out = srcs[0][0]
+                hi, wi = S.hw_in
+                gx = torch.empty((n, hi, wi, L.c_out), dtype=torch.float32, device=dev)
+                S.gbufs.append(gx)
+                if L.kind == "pool":
+                    x = self.act[L.srcs[0]]
+                    out_ops.append(("call", lib.disco_maxpool2_backward, (x.data_ptr(), ops._lo_off(x), self.prec, g_out.data_ptr(),
+                                                                          gx.data_ptr(), n, hi, wi, L.c_out), f"pool_bwd[{L.name}]"))
+                else:
+                    out_ops.append(("call", lib.disco_upsample_bilinear2x_backward, (g_out.data_ptr(), gx.data_ptr(), n, hi, wi, L.c_out),
+                                    f"up_bwd[{L.name}]"))
+                gsrc.setdefault(L.srcs[0], []).append((gx, L.c_out, 0, 0))
+                return out_ops
             if L.bn:
                 d = S.bn
                 srcs = gsrc.get(L.out, [])
@@ -404,6 +456,8 @@ class TrainRunner:
 
         raw_cache = {}
         for L in self.layers:
+            if L.kind != "conv":
+                continue
             if L.name in ("h3", "h1"):
                 raw_cache[L.name] = (sp[L.name + ".w"], sp[L.name + ".b"])
             else:
@@ -419,6 +473,10 @@ class TrainRunner:
             bwd += layer_bwd_ops(self.head_layers[1])
             bwd += layer_bwd_ops(self.head_layers[0])
         for L in reversed(self.dec):
+            if L.name == "outc":
+                npix = n * self.h * self.w
+                self._outc_bias_off = self._galloc("outc.conv.bias", (8,))
+                bwd.append(("grad_pack_outc", npix))
             bwd += layer_bwd_ops(L)
         if self.fused_key:
             bwd += self._build_fusion(pre, gsrc, wgrad_desc)
@@ -532,8 +590,8 @@ class TrainRunner:
                                (lib.disco_fusion_forward, f, "fusion")]
         # ---- backward ----
         srcs = gsrc.get(self.fused_key, [])
-        if not srcs or len(srcs) > 2:
-            raise RuntimeError("the fused map needs one or two gradient sources")
+        if not srcs or len(srcs) > 3:
+            raise RuntimeError("the fused map needs one to three gradient sources")
         ops_b = []
         for (t, ct, co, pl) in srcs:
             assert ct == cf and co == 0 and pl == 0
@@ -541,6 +599,8 @@ class TrainRunner:
             q.dfused = srcs[0][0].data_ptr()
         else:
             ops_b.append(("add_f32", self.dfused, srcs[0][0], srcs[1][0]))
+            if len(srcs) == 3:
+                ops_b.append(("add_f32", self.dfused, self.dfused, srcs[2][0]))
             q.dfused = self.dfused.data_ptr()
         ops_b.append(("py", self._fusion_zero))
         ops_b.append((lib.disco_fusion_combine_backward, q, "fusion_combine_backward"))
@@ -578,6 +638,14 @@ class TrainRunner:
                                             stream), "channel_sum")
                 check(lib.disco_channel_sum(self.gloc.data_ptr(), op[1], 36, self.sums.data_ptr(), gb + 4 * self._head_bias_off[1],
                                             stream), "channel_sum")
+            elif f == "call":
+                check(op[1](*op[2], stream), op[3])
+            elif f == "grad_pack_outc":
+                S = self.st["outc"]
+                check(lib.disco_grad_pack(self.glogits.data_ptr(), 8, self.gzero8.data_ptr(), 8, op[1], S.dz.data_ptr(),
+                                          ops._lo_off(S.dz), stream), "grad_pack[outc]")
+                check(lib.disco_channel_sum(self.glogits.data_ptr(), op[1], 8, self.sums.data_ptr(),
+                                            self.G.data_ptr() + 4 * self._outc_bias_off, stream), "channel_sum")
             elif f == "grad_pack_den":
                 check(lib.disco_grad_pack(self.den.data_ptr(), 256, None, 0, op[1], self.den_act.data_ptr(),
                                           ops._lo_off(self.den_act), stream), "grad_pack[den]")
@@ -622,6 +690,10 @@ class TrainRunner:
         out = {}
         if self.head_layers:
             out["cls"], out["loc"] = self.cls.clone(), self.loc.clone()
+        if self.has_outc:
+            lg = torch.empty((self.n, 8, self.h, self.w), dtype=torch.float32, device=dev)
+            check(self.lib.disco_nhwc_to_nchw(self.logits.data_ptr(), self.n, self.h, self.w, 16, 8, lg.data_ptr(), stream), "nhwc_to_nchw")
+            out["logits"] = lg
         return out
 
     def kd_map(self, key: str) -> torch.Tensor:
@@ -635,7 +707,7 @@ class TrainRunner:
         stream = torch.cuda.current_stream(dev).cuda_stream
         keep = []
         for key, g in grads.items():
-            if key in ("cls", "loc"):
+            if key in ("cls", "loc", "logits"):
                 continue
             if key not in self.ext:
                 if g is None:
@@ -651,6 +723,14 @@ class TrainRunner:
             check(lib.disco_nchw_to_nhwc(g.data_ptr(), nn_, c, hh, ww, self.ext[key].data_ptr(), stream), "nchw_to_nhwc")
             self.ext_dirty[key] = True
             keep.append(g)
+        if self.has_outc:
+            g = grads.get("logits")
+            if g is None:
+                self.glogits.zero_()
+            else:
+                g = g.detach().float().contiguous()
+                check(lib.disco_nchw_to_nhwc(g.data_ptr(), self.n, 8, self.h, self.w, self.glogits.data_ptr(), stream), "nchw_to_nhwc")
+                keep.append(g)
         if self.head_layers:
             for name, buf in (("cls", self.gcls), ("loc", self.gloc)):
                 g = grads.get(name)
@@ -669,6 +749,12 @@ class TrainRunner:
         v = lambda name: self._gview(G, name)
         zero = v("_zero")
         for L in self.enc + self.dec:
+            if L.kind != "conv":
+                continue
+            if L.name == "outc":
+                out["outc.conv.weight"] = v("_dw.outc")[:8].reshape(8, 64, 1, 1)
+                out["outc.conv.bias"] = v("outc.conv.bias")
+                continue
             out[L.conv + ".weight"] = v("_dw." + L.name).view(self.get(L.conv + ".weight").shape)
             out[L.conv + ".bias"] = zero[:L.c_out]     # conv bias in front of a BatchNorm: exactly zero gradient
             out[L.bn + ".weight"], out[L.bn + ".bias"] = v("_dgamma." + L.name), v("_dbeta." + L.name)

@@ -145,6 +145,12 @@ int disco_maxpool2(const void* src_hi, long long src_lo_off, void* dst_hi, long 
  * the torch.cat([skip, up]) that follows is the two-source gather of disco_conv_forward. */
 int disco_upsample_bilinear2x(const void* src_hi, long long src_lo_off, void* dst_hi, long long dst_lo_off, int precision, int n,
                               int h, int w, int c, void* stream);
+/* autograd backward of the two: x = the pool's INPUT activation [n,h,w,c], g fp32 [n,h/2,w/2,c] -> gx fp32 [n,h,w,c] (first
+ * maximum of each 2x2 block, torch's convention);  g_up fp32 [n,2h,2w,c] -> gs fp32 [n,h,w,c] (transpose of the bilinear
+ * interpolation).  (h, w) are the sizes of the pool input / of the upsample source. */
+int disco_maxpool2_backward(const void* x_hi, long long x_lo_off, int precision, const float* g, float* gx, int n, int h, int w, int c,
+                            void* stream);
+int disco_upsample_bilinear2x_backward(const float* g_up, float* gs, int n, int h, int w, int c, void* stream);
 /* fp32 NHWC [n,h,w,c_src] -> fp32 NCHW [n,c,h,w] (first c channels): layout of the logits OutConv returns (:145-151). */
 int disco_nhwc_to_nchw(const float* src, int n, int h, int w, int c_src, int c, float* dst, void* stream);
 

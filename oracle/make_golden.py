@@ -41,6 +41,7 @@ SEG_CASES = {
     "seg_a2_b1": dict(A=2, B=1, num_agent=[2], only_v2i=False, seed=51),
     "seg_a4_b1_absent_v2i": dict(A=4, B=1, num_agent=[3], only_v2i=True, seed=52),
 }
+SEG_TRAIN_CASE = dict(A=2, B=1, num_agent=[2], only_v2i=False, seed=53)
 SEG_KEYS = ("logits", "x9", "x8", "x7", "x6", "x5", "feat")
 SEG_STRIDES = {"logits": 499, "x9": 1999, "x8": 1999, "x7": 997, "x6": 499, "x5": 251, "feat": 251}
 
@@ -147,6 +148,28 @@ def main():
             rec[k + "_shape"] = np.array(t.shape)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
         print(name, {k: v.shape for k, v in rec.items() if k.endswith("_shape")})
+
+    # seg DiscoNet in train() mode: outputs + parameter-gradient digest + updated BatchNorm buffers
+    name, case = "seg_train_a2_b1", SEG_TRAIN_CASE
+    m = RSeg(13, 8, num_agent=case["A"], kd_flag=True, only_v2i=case["only_v2i"]).train()
+    keys[name] = [[k, list(v.shape)] for k, v in m.state_dict().items()]
+    sd, bev, T, na = seg_case_inputs(case, m.state_dict())
+    m.load_state_dict(sd)
+    out = m(bev, T, na)
+    tensors = dict(zip(SEG_KEYS, out))
+    loss, _ = O.probe_loss(tensors, seed=case["seed"] + 300)
+    loss.backward()
+    rec = {"loss": np.array([loss.item()])}
+    for k, t in tensors.items():
+        rec[k + "_sub"], rec[k + "_stats"] = _sub(t, SEG_STRIDES[k])
+        rec[k + "_shape"] = np.array(t.shape)
+    grads = {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in m.named_parameters()}
+    rec["grad_sub"], rec["grad_table"] = grad_digest(grads)
+    rec["grad_names"] = np.array(sorted(grads))
+    rec["grad_none"] = np.array([k for k, p in m.named_parameters() if p.grad is None])
+    rec["buf_sub"], rec["buf_table"] = grad_digest({k: v.float() for k, v in m.named_buffers()}, stride=7)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+    print(name, "loss", loss.item())
 
     # FaFNet lower-bound plumbing config (BASELINE config 1): 2 agents, 128x128x13
     m = RFaF(cfg, kd_flag=0, num_agent=2).eval()

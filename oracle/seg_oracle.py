@@ -58,10 +58,12 @@ def fuse(sd, x4, trans_matrices, num_agent_tensor, batch_size, agent_num, only_v
     return torch.flip(fused, (2,))
 
 
-@torch.no_grad()
-def seg_disconet_forward(sd, x, trans_matrices, num_agent_tensor, agent_num=5, only_v2i=False, return_all=False):
-    """Eval-mode seg DiscoNet forward.  x [A*B, 13, H, W] float (agent-major) -> logits [A*B, n_classes, H, W]."""
-    x1 = _double_conv(x.float(), sd, "inc.double_conv.")
+def seg_disconet_forward_graph(sd, x, trans_matrices, num_agent_tensor, agent_num=5, only_v2i=False, return_all=False):
+    """seg DiscoNet forward (eval mode unless inside `disconet_oracle.training(sd)`; autograd flows through `sd`).
+    x [A*B, 13, H, W] float (agent-major) -> logits [A*B, n_classes, H, W]."""
+    if x.dtype != torch.float64:
+        x = x.float()
+    x1 = _double_conv(x, sd, "inc.double_conv.")
     x2 = _down(x1, sd, "down1")
     x3 = _down(x2, sd, "down2")
     x4 = _down(x3, sd, "down3")
@@ -76,3 +78,9 @@ def seg_disconet_forward(sd, x, trans_matrices, num_agent_tensor, agent_num=5, o
     if return_all:
         return {"logits": logits, "x9": x9, "x8": x8, "x7": x7, "x6": x6, "x5": x5, "feat": feat, "x4": x4}
     return {"logits": logits}
+
+
+@torch.no_grad()
+def seg_disconet_forward(*args, **kwargs):
+    """Eval-mode forward without autograd."""
+    return seg_disconet_forward_graph(*args, **kwargs)

@@ -353,3 +353,40 @@ def test_post_oracle_matches_reference():
     assert np.abs(dec - dec_ref).max() <= 1e-5 * np.abs(dec_ref).max()
     cor_ref = center_to_corner_box2d(dec_ref[:, :2], dec_ref[:, 2:4], dec_ref[:, 4:])
     assert np.abs(P.box_corners(dec_ref) - cor_ref).max() <= 1e-5 * np.abs(cor_ref).max()
+
+
+def oracle_seg_train_step(case, sd):
+    from oracle import seg_oracle as S
+    from oracle.make_golden import SEG_KEYS, seg_case_inputs
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
+    _, bev, T, na = seg_case_inputs(case, sd)
+    with O.training(sd) as ctx:
+        out = S.seg_disconet_forward_graph(sd, bev, T, na, agent_num=case["A"], only_v2i=case["only_v2i"], return_all=True)
+    tensors = {k: out[k] for k in SEG_KEYS}
+    loss, _ = O.probe_loss(tensors, seed=case["seed"] + 300)
+    loss.backward()
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in sd.items() if v.requires_grad}
+    return tensors, loss, grads, ctx.buffers
+
+
+def test_seg_oracle_training_matches_reference_golden():
+    """seg DiscoNet in train() mode: same pin as the detection model (outputs, gradient norms / cosine, BN buffers)."""
+    from oracle.make_golden import SEG_KEYS, SEG_STRIDES, SEG_TRAIN_CASE, grad_digest
+    name = "seg_train_a2_b1"
+    rec = np.load(os.path.join(GOLD, name + ".npz"))
+    sd, *_ = __import__("oracle.make_golden", fromlist=["x"]).seg_case_inputs(SEG_TRAIN_CASE, _template(name))
+    tensors, loss, grads, bufs = oracle_seg_train_step(SEG_TRAIN_CASE, sd)
+    for k in SEG_KEYS:
+        _check_sub(name, tensors[k], rec, k, tol=2e-4, stride=SEG_STRIDES[k])
+    assert sorted(grads) == rec["grad_names"].tolist()
+    sub, table = grad_digest(grads)
+    ref_table = rec["grad_table"]
+    for i, k in enumerate(sorted(grads)):
+        if k.endswith(".bias") and ".conv" in k or k.endswith((".0.bias", ".3.bias")) or (k.endswith(".bias") and "conv1_" in k and "conv1_4" not in k):
+            continue                       # conv biases (BatchNorm-shadowed ones are rounding noise on both sides)
+        if ref_table[i, 0] > 1e-6:
+            assert abs(table[i, 0] - ref_table[i, 0]) <= 3e-2 * ref_table[i, 0], (k, table[i, 0], ref_table[i, 0])
+    cos = float(np.dot(sub, rec["grad_sub"]) / (np.linalg.norm(sub) * np.linalg.norm(rec["grad_sub"])))
+    assert cos >= 0.999, cos
+    bsub, _ = grad_digest({k: v.float() for k, v in bufs.items()}, stride=7)
+    assert np.abs(bsub - rec["buf_sub"]).max() <= 5e-4 * np.abs(rec["buf_sub"]).max()
