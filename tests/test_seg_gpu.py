@@ -1,7 +1,6 @@
 """GPU parity of the BEV-segmentation DiscoNet (BASELINE config 5): U-Net on the tcgen05 conv kernel,
 MaxPool / bilinear-upsample streaming kernels, the fusion kernel at C = 512 -- against the CPU oracle on the same seeded
 inputs and against the live-reference goldens.  Tolerance: max|ours - ref| / max|ref| <= 1e-3 per returned tensor."""
-import ctypes as C
 import os
 
 import numpy as np
