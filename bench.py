@@ -317,6 +317,10 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE JSON line: anything libraries print meanwhile (NCCL's version banner on rank 0) goes to stderr
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -485,6 +489,8 @@ def main():
         "train": train,
         "agent_sharded": sharded,
     }
+    sys.stdout.flush()
+    os.dup2(stdout_fd, 1)
     print(json.dumps(line), flush=True)
     if dist:
         td.destroy_process_group()
