@@ -133,9 +133,16 @@ EXPORTS = {
                                         C.c_void_p]),
     "disco_bev_scatter": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_int,
                                     C.c_int, C.c_void_p]),
+    "disco_bev_scatter_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_longlong,
+                                            C.c_int, C.c_int, C.c_void_p]),
     "disco_fusion_forward": (C.c_int, [C.POINTER(FusionDesc), C.c_void_p]),
     "disco_det_candidates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_float, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "disco_nms_workspace_bytes": (C.c_longlong, [C.c_int, C.c_int]),
+    "disco_nms_rotated": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,
+                                    C.c_double, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "disco_corner_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
     # segmentation U-Net data movement
     "disco_maxpool2": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "disco_upsample_bilinear2x": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdisco_b200.so")
 STAMP = os.path.join(HERE, ".libdisco_b200.stamp")
-SOURCES = ["conv_tc.cu", "conv_ref.cu", "misc.cu", "fusion.cu", "train.cu", "wgrad.cu", "fusion_train.cu", "seg.cu", "capi.cu"]
+SOURCES = ["conv_tc.cu", "conv_ref.cu", "misc.cu", "fusion.cu", "train.cu", "wgrad.cu", "fusion_train.cu", "seg.cu", "post.cu", "capi.cu"]
 HEADERS = ["common.cuh", "conv.h", "ops.h", "train.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

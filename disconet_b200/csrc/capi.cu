@@ -76,6 +76,11 @@ int disco_bev_scatter(const int* voxel_indices, int n_voxels, const int* dims, f
     return disco_bev_scatter_launch(voxel_indices, n_voxels, dims, bev_f32, act_hi, act_c, precision, stream);
 }
 
+int disco_bev_scatter_batched(const int* voxel_indices, const int* counts, int n, int m_max, const int* dims, void* act_hi,
+                              long long act_lo_off, int act_c, int precision, void* stream) {
+    return disco_bev_scatter_batched_launch(voxel_indices, counts, n, m_max, dims, act_hi, act_lo_off, act_c, precision, stream);
+}
+
 int disco_fusion_forward(const disco_fusion_desc* d, void* stream) {
     if (!d) { disco_set_error("null descriptor"); return DISCO_EINVAL; }
     return disco_fusion_launch(d, stream);
@@ -86,6 +91,22 @@ int disco_det_candidates(const float* loc, const float* cls, const float* anchor
                          float* scores, int* index, void* stream) {
     return disco_det_candidates_launch(loc, cls, anchors, anchors_per_agent, anchor_agent_stride, n_agents, thresh, max_cand, count,
                                        corners, scores, index, stream);
+}
+
+// ---- detection post-processing (row f3) and the regression loss of the training step (row f4) -------------------
+long long disco_nms_workspace_bytes(int n_sets, int kmax) {
+    if (n_sets <= 0 || kmax <= 0) { disco_set_error("nms_workspace_bytes: bad sizes"); return DISCO_EINVAL; }
+    return (long long)disco_nms_workspace_bytes_impl(n_sets, kmax);
+}
+int disco_nms_rotated(const void* corners, int corners_f64, const float* scores, const int* ids, const int* count, int n_sets,
+                      int cap, int kmax, float score_thresh, double iou_thresh, void* workspace, long long workspace_bytes,
+                      int* keep, int* n_keep, int* n_valid, void* stream) {
+    return disco_nms_rotated_launch(corners, corners_f64, scores, ids, count, n_sets, cap, kmax, score_thresh, iou_thresh, workspace,
+                                    (size_t)workspace_bytes, keep, n_keep, n_valid, stream);
+}
+int disco_corner_loss(const float* pred, const float* target, const float* anchors, const unsigned char* mask, long long n_entries,
+                      int t_len, float inv_n, double* loss_sum, float* grad, void* stream) {
+    return disco_corner_loss_launch(pred, target, anchors, mask, n_entries, t_len, inv_n, loss_sum, grad, stream);
 }
 
 // ---- BEV segmentation U-Net ---------------------------------------------------------------

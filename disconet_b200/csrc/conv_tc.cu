@@ -34,10 +34,80 @@
 // per k-step (hi*hi + lo*hi + hi*lo) -> ~16 mantissa bits, which is what the <=1e-3 parity gate
 // against the fp32 reference needs (plain fp16 operands measure 2-3e-3).
 #include <stdlib.h>
+#include <cuda.h>
 #include "common.cuh"
 #include "conv.h"
 
 namespace {
+
+// ---- TMA (cp.async.bulk.tensor) plumbing: the A operand of every non-upsampled source is fetched by the TMA engine as one
+// box per (8-channel chunk, precision part) -- {8 ch, patch width, patch height, 1 image} of the NHWC tensor, zero-filled
+// outside the image (= the conv's zero padding) -- straight into the UMMA no-swizzle K-major plane [pixel][8 ch].  One
+// elected lane issues 4..16 instructions per K stage instead of ~1500 warp instructions of per-lane cp.async address math
+// (round-2 ncu source view: the four producer warps were the busiest warps of the C_out <= 64 layers).  A nearest-x2
+// upsampled source is fetched at its native (half) resolution into a small scratch box and expanded shared->shared.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// NHWC 16-bit tensor [N, H, W, C] -> 4-D map (innermost first: C, W, H, N); box {8, box_w, box_h, 1}; estride_w = 2 loads
+// every second column (stride-2 convs de-interleave even / odd columns into two planes)
+bool make_tmap4(CUtensorMap* m, const void* base, int C, int W, int H, int N, int box_w, int box_h, int estride_w) {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return false;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {8, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)estride_w, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// [pixels, C] view for the 1x1 convs; box {8, 128}
+bool make_tmap2(CUtensorMap* m, const void* base, int C, long long pixels) {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)pixels};
+    cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    cuuint32_t box[2] = {8, 128};
+    cuuint32_t es[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+constexpr int kScrBox = 1024;   // scratch bytes per (chunk, part) low-resolution box (10 x 6 pixels x 16 B = 960, 128-B aligned)
 
 constexpr int kEpiWarps = 8, kProdWarps = 4;   // two epilogue groups of 4 warps, each owning alternate items
 constexpr int kMmaWarps = 2;   // two independent issue streams (each owns alternate items) when weights are stationary
@@ -53,7 +123,33 @@ constexpr int kStageRow = 80;      // epilogue staging: per pixel 16 ch hi (32 B
 constexpr int kStagePerWarp = 32 * kStageRow;
 constexpr int kStageBytes = kEpiWarps * kStagePerWarp;   // 20 KB
 
-struct ConvGeom {
+// n / d for 0 <= n < 2^31 without the ~40-instruction integer division sequence (Granlund-Montgomery, the CUTLASS FastDivmod
+// construction): the per-item tile decode sits on the critical path of single warps (round-2 trace: ~1000 cycles of divisions
+// per item in the MMA and epilogue roles of the C_out <= 64 layers).
+struct FastDiv {
+    uint32_t mul, shr;
+    int d;
+};
+FastDiv make_fastdiv(int d) {
+    FastDiv f;
+    f.d = d;
+    if (d <= 1) { f.mul = 0; f.shr = 0; return f; }
+    int l = 0;
+    while ((1ll << l) < d) ++l;
+    const int p = 31 + l;
+    f.mul = (uint32_t)(((1ull << p) + (uint64_t)d - 1) / (uint64_t)d);
+    f.shr = (uint32_t)(p - 32);
+    return f;
+}
+__device__ __forceinline__ int fast_div(int n, const FastDiv& f) {
+    return f.d <= 1 ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr);
+}
+
+struct alignas(64) ConvGeom {
+    CUtensorMap tmap[4];      // [source][part]: TMA views of the conv sources (valid when use_tma)
+    int use_tma;              // A operand through the TMA engine (sources that are not zero-stuffed)
+    int scratch_warp;         // bytes of low-resolution scratch per producer warp (nearest-upsampled sources), else 0
+    int scratch_total;
     disco_conv_desc d;
     int ncb, ncb0;            // K stages total / from source 0
     int chunks, chunk_shift;  // c_blk/8
@@ -80,6 +176,7 @@ struct ConvGeom {
     int w_bytes;              // stationary: bytes of one n_tile's weights
     int tiles_h, tiles_w;
     int m_tiles, n_tiles, items;
+    FastDiv fd_m_tiles, fd_per_img, fd_tiles_w;
     long long total_pix;      // n*h_out*w_out
     int tmem_cols;
     int smem_bytes;
@@ -102,6 +199,7 @@ struct __align__(8) SmemCtl {
     uint64_t w2_full;
     uint64_t a2_full[2];
     uint64_t acc2_full[2];
+    uint64_t scr_full[4];     // low-resolution scratch box of producer warp p has landed (TMA complete_tx)
     uint32_t tmem_base;
     uint32_t pad;
 };
@@ -123,14 +221,14 @@ struct Item {
 template <int MODE>
 __device__ __forceinline__ Item decode_item(const ConvGeom& g, int item) {
     Item it;
-    it.n_tile = item / g.m_tiles;  // n-major: concurrently running CTAs stream the same weights
+    it.n_tile = fast_div(item, g.fd_m_tiles);  // n-major: concurrently running CTAs stream the same weights
     const int m_tile = item - it.n_tile * g.m_tiles;
     it.img = 0; it.h0 = 0; it.w0 = 0; it.p0 = 0;
     if (MODE != 2) {
         const int per_img = g.tiles_h * g.tiles_w;
-        it.img = m_tile / per_img;
+        it.img = fast_div(m_tile, g.fd_per_img);
         const int rem = m_tile - it.img * per_img;
-        const int th = rem / g.tiles_w;
+        const int th = fast_div(rem, g.fd_tiles_w);
         it.h0 = th * 16;
         it.w0 = (rem - th * g.tiles_w) * 8 * g.msub;
     } else {
@@ -141,12 +239,13 @@ __device__ __forceinline__ Item decode_item(const ConvGeom& g, int item) {
 
 // MODE 0: 3x3 stride 1 (patch 18x10) | MODE 1: 3x3 stride 2 (patch 33x17) | MODE 2: 1x1
 template <int MODE, int KSTEPS, int PASSES>
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) {
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvGeom g) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_raw);
     const uint32_t smem_base = smem_u32(smem_raw);
     // (chained layers never use the OUT_ACT store staging, so its 20 KB go to the A stages)
-    const uint32_t a_base = smem_base + kCtlBytes + kBiasBytes + (g.chain ? 0 : kStageBytes);
+    const uint32_t scr_base = smem_base + kCtlBytes + kBiasBytes + (g.chain ? 0 : kStageBytes);
+    const uint32_t a_base = scr_base + (uint32_t)g.scratch_total;
     const float* s_bias = reinterpret_cast<const float*>(smem_raw + kCtlBytes);
     const uint32_t b_base = a_base + g.SA * g.a_stage_bytes;
     const uint32_t w2_base = b_base + (uint32_t)g.w_bytes;          // chain only (stationary layers)
@@ -167,7 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
     // ---- one-time setup ------------------------------------------------------------------------
     if (tid == 0) {
         for (int s = 0; s < g.SA; ++s) {
-            mbar_init(smem_u32(&ctl->a_full[s]), 32);
+            mbar_init(smem_u32(&ctl->a_full[s]), 1);   // one arrival per stage: the TMA issuer's expect_tx, or lane 0 of a cp.async warp
             mbar_init(smem_u32(&ctl->a_empty[s]), 1);
         }
         for (int s = 0; s < g.SB; ++s) {
@@ -180,6 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
         }
         mbar_init(smem_u32(&ctl->w_full), 1);
         mbar_init(smem_u32(&ctl->w2_full), 1);
+        for (int s = 0; s < 4; ++s) mbar_init(smem_u32(&ctl->scr_full[s]), 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&ctl->a2_full[s]), 4 * 32);
             mbar_init(smem_u32(&ctl->acc2_full[s]), 1);
@@ -206,13 +306,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
     if (warp < kEpiWarps) {
         // =========================== epilogue =====================================================
         int iacc = 0;
+        int buf = 0;               // == iacc % nacc, acc_par == (iacc / nacc) & 1 (kept by counters: no divisions per item)
+        uint32_t acc_par = 0;
         const int egrp = warp >> 2;   // the epilogue of one item is latency-bound (~3000 cycles); two groups overlap two items
-        for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++iacc) {
+        for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++iacc, buf = (buf + 1 == g.nacc) ? 0 : buf + 1, acc_par ^= (buf == 0)) {
             if ((iacc & 1) != egrp) continue;
             const Item it = decode_item<MODE>(g, item);
-            const int buf = iacc % g.nacc;
             if (warp == 0) TRACE(0, iacc, 0);
-            mbar_wait(smem_u32(&ctl->acc_full[buf]), (uint32_t)(iacc / g.nacc) & 1u);
+            mbar_wait(smem_u32(&ctl->acc_full[buf]), acc_par);
             tc_fence_after();
             if (warp == 0) TRACE(0, iacc, 1);
             const int m = (warp & 3) * 32 + lane;   // TMEM lane == pixel row of the tile; warp w may touch lanes 32*(w%4)..+31
@@ -387,6 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
         // consumer could be a full wrap ahead and pass the parity wait on a stale phase).  Producer warp pw serves
         // ring pw % nmma and, inside it, the stages q with q % nprod == pw / nmma (nprod <= SAr, same argument).
         const int ring = pw % g.nrings, pr = pw / g.nrings;
+        uint32_t scr_phase = 0;
         int iacc_p = 0;
         for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++iacc_p) {
             if (pr >= g.nprod) break;
@@ -413,6 +515,58 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                 const uint32_t stage = a_base + sa * g.a_stage_bytes;
                 const int cofs = cbl * d.c_blk;
                 const int hi0 = it.h0 * STRIDE - 1, wi0 = (it.w0 + sub * 8) * STRIDE - 1;
+                if (g.use_tma && upm == 0) {
+                    // ---- TMA: one box per (chunk, part); out-of-image pixels arrive as zeros (= the conv padding) ----
+                    if (lane == 0) {
+                        const uint32_t bar = smem_u32(&ctl->a_full[sa]);
+                        constexpr uint32_t kBox = (MODE == 0) ? 18u * 10u * 16u : (MODE == 1) ? 2u * 33u * 9u * 16u : 128u * 16u;
+                        mbar_arrive_expect_tx(bar, (uint32_t)(g.nparts * g.chunks) * kBox);
+                        for (int part = 0; part < g.nparts; ++part) {
+                            const CUtensorMap* tm = &g.tmap[sidx * 2 + part];
+                            for (int chunk = 0; chunk < g.chunks; ++chunk) {
+                                const uint32_t dst = stage + (uint32_t)part * g.a_part_bytes + (uint32_t)chunk * g.plane;
+                                const int c0 = cofs + chunk * 8;
+                                if (MODE == 0) {
+                                    tma_load_4d(dst, tm, c0, wi0, hi0, it.img, bar);
+                                } else if (MODE == 1) {
+                                    tma_load_4d(dst, tm, c0, wi0, hi0, it.img, bar);                    // even patch columns
+                                    tma_load_4d(dst + g.parplane, tm, c0, wi0 + 1, hi0, it.img, bar);   // odd patch columns
+                                } else {
+                                    tma_load_2d(dst, tm, c0, (int)(it.p0 + sub * 128), bar);
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    continue;
+                }
+                if (g.use_tma && upm == 1 && MODE == 0) {
+                    // ---- nearest-x2 upsampled source: TMA the 10 x 6 low-resolution box, expand shared -> shared ------
+                    const uint32_t scr = scr_base + (uint32_t)pw * g.scratch_warp;
+                    const uint32_t sbar = smem_u32(&ctl->scr_full[pw]);
+                    const int nbox = g.nparts * g.chunks;
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(sbar, (uint32_t)nbox * 960u);
+                        for (int part = 0; part < g.nparts; ++part)
+                            for (int chunk = 0; chunk < g.chunks; ++chunk)
+                                tma_load_4d(scr + (uint32_t)(part * g.chunks + chunk) * kScrBox, &g.tmap[sidx * 2 + part],
+                                            cofs + chunk * 8, wi0 >> 1, hi0 >> 1, it.img, sbar);
+                    }
+                    mbar_wait(sbar, scr_phase);
+                    scr_phase ^= 1u;
+                    // patch pixel (r, c) <- low-res pixel ((r + 1) >> 1, (c + 1) >> 1) of the box (hi0, wi0 are odd)
+                    for (int idx = lane; idx < nbox * 180; idx += 32) {
+                        const int pc = idx / 180, rem = idx - pc * 180;
+                        const int r = rem / 10, c = rem - r * 10;
+                        const int part = pc >> g.chunk_shift, chunk = pc & (g.chunks - 1);
+                        const uint4 v = lds128(scr + (uint32_t)pc * kScrBox + (uint32_t)((((r + 1) >> 1) * 6 + ((c + 1) >> 1)) * 16));
+                        sts128(stage + (uint32_t)part * g.a_part_bytes + (uint32_t)chunk * g.plane + (uint32_t)(r * 160 + c * 16), v);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&ctl->a_full[sa]));
+                    continue;
+                }
                 if (MODE != 2) {
                     // Row-wise gather: the (column, chunk) a lane handles is the same for every patch row, so
                     // its shared/global offsets are computed once per stage and each row only adds its base.
@@ -470,7 +624,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                 cp_async_wait<0>();
                 fence_proxy_async_smem();
                 if (pw == 0) TRACE(1, q / g.nprod, 3);
-                mbar_arrive(smem_u32(&ctl->a_full[sa]));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&ctl->a_full[sa]));
             }
         }
     } else if (warp == kWarpB) {
@@ -549,6 +704,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
         // and the three split passes are compile-time unrolled (KSTEPS, SPLIT template parameters) and
         // every descriptor is base + precomputed offset.  The whole warp runs the warp-uniform control
         // flow; one elected lane issues.
+        // (Measured in round 2: running the whole role on ONE lane -- `if (lane == 0)` around the item loop -- is 10-30 % SLOWER
+        // than warp-uniform control flow with an elected issuing lane: divergent code loses the uniform datapath.)
         {
             const uint32_t idesc = umma_idesc_f16(d.precision == DISCO_PREC_BF16X3, 128, d.block_n);
             const uint32_t idesc2 = umma_idesc_f16(1, 128, 2 * d.block_n);   // STACKED: [W_hi; W_lo]
@@ -579,22 +736,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                 mbar_wait(smem_u32(&ctl->w_full), 0);
                 tc_fence_after();
             }
-            for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++iacc) {
-                if (mw >= g.nmma || (!g.by_sub && (iacc % g.nmma) != mw)) continue;
-                int ia = (iacc / g.nrings) * stages_per_item;  // ring-local index of this item's first A stage
-                const int ring0 = (g.nrings == 2) ? mw * g.SAr : 0;   // private ring when issuers split items
-                const int sub_lo = g.by_sub ? mw : 0, sub_hi = g.by_sub ? mw + 1 : g.msub;
-                const int buf = iacc % g.nacc;
+            // ring positions are kept by counters (no integer divisions on this warp's critical path):
+            //   buf / acc_par : accumulator buffer iacc % nacc and the parity of iacc / nacc (advance with EVERY item)
+            //   turn          : iacc % nmma (which issuer owns the item when the issuers split items)
+            //   rs / rs_par   : ring-local A slot of the next stage this issuer consumes and its wrap parity
+            int buf = 0, turn = 0, rs = 0;
+            uint32_t acc_par = 0, rs_par = 0;
+            const int ring0 = (g.nrings == 2) ? mw * g.SAr : 0;   // private ring when issuers split items
+            const int sub_lo = g.by_sub ? mw : 0, sub_hi = g.by_sub ? mw + 1 : g.msub;
+            for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++iacc, buf = (buf + 1 == g.nacc) ? 0 : buf + 1,
+                     acc_par ^= (buf == 0), turn = (turn + 1 == g.nmma) ? 0 : turn + 1) {
+                if (mw >= g.nmma || (!g.by_sub && turn != mw)) continue;
                 if (mw == 0) TRACE(2, iacc, 0);
-                mbar_wait(smem_u32(&ctl->acc_empty[buf]), ((uint32_t)(iacc / g.nacc) & 1u) ^ 1u);
+                mbar_wait(smem_u32(&ctl->acc_empty[buf]), acc_par ^ 1u);
                 tc_fence_after();
                 if (mw == 0) TRACE(2, iacc, 1);
                 const uint32_t td0 = tmem_d + (uint32_t)(buf * g.msub * g.acc_stride);
                 const uint32_t td1 = td0 + (uint32_t)g.acc_stride;
                 for (int cb = 0; cb < g.ncb; ++cb) {
                     // wait for the MSUB patches of this channel block
-                    const int slot0 = ring0 + ia % g.SAr;
-                    const uint32_t sa_phase = (uint32_t)(ia / g.SAr) & 1u;
+                    const int slot0 = ring0 + rs;
+                    const uint32_t sa_phase = rs_par;
                     if (sub_lo == 0) mbar_wait(bar_a_full + 8u * slot0, sa_phase);
                     const uint32_t a0_16 = a_base16 + (uint32_t)slot0 * a_stage16;
                     int slot1 = slot0;
@@ -609,12 +771,50 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                     tc_fence_after();
                     if (cb == 0 && mw == 0) TRACE(2, iacc, 2);
                     const uint32_t first = (cb > 0) ? 1u : 0u;   // accumulate flag of the first MMA of the item
+                    if (g.stationary) {
+                        // Resident weights: nothing to wait for between taps, so ONE elected region issues the whole channel
+                        // block as a branch-free run of tcgen05.mma with descriptor = base + precomputed offset (round-2 ncu
+                        // source view: the per-tap ring / elect / constant-bank code of the generic loop below cost ~45 scalar
+                        // instructions per 4 MMAs, i.e. ~124 cycles per MMA and issuer against a hardware floor of ~50).
+                        const uint32_t b_cb16 = b_base16 + (uint32_t)(cb * TAPS) * b_stage16;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int sub = 0; sub < 2; ++sub) {
+                                if (sub >= sub_lo && sub < sub_hi) {
+                                    const uint32_t td = sub ? td1 : td0;
+                                    const uint32_t a16s = sub ? a1_16 : a0_16;
+#pragma unroll
+                                    for (int tap = 0; tap < TAPS; ++tap) {
+                                        const int kh = tap / 3, kw = tap - kh * 3;
+                                        const uint32_t toff = (MODE == 0) ? (uint32_t)(kh * 10 + kw)
+                                                            : (MODE == 1) ? (uint32_t)(kw & 1) * par16 + (uint32_t)(kh * 9 + (kw >> 1))
+                                                                          : 0u;
+                                        const uint32_t a16 = a16s + toff, b16 = b_cb16 + (uint32_t)tap * b_stage16;
+#pragma unroll
+                                        for (int ks = 0; ks < KSTEPS; ++ks) {
+                                            const uint32_t alo = a16 + a_ks[ks], blo = b16 + b_ks[ks];
+                                            const uint32_t accf = (tap == 0 && ks == 0) ? first : 1u;
+                                            if (STACKED) {
+                                                umma_f16_parts(td, alo, a_hi, blo, b_hi, idesc2, accf);            // hi*[hi|lo]
+                                                umma_f16_parts(td, alo + a_part16, a_hi, blo, b_hi, idesc, 1u);   // lo*hi
+                                            } else {
+                                                umma_f16_parts(td, alo, a_hi, blo, b_hi, idesc, accf);
+                                                if (SPLIT) {
+                                                    umma_f16_parts(td, alo + a_part16, a_hi, blo, b_hi, idesc, 1u);
+                                                    umma_f16_parts(td, alo, a_hi, blo + b_part16, b_hi, idesc, 1u);
+                                                }
+                                            }
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    } else {
 #pragma unroll
                     for (int tap = 0; tap < TAPS; ++tap) {
                         uint32_t b16;
-                        if (g.stationary) {
-                            b16 = b_base16 + (uint32_t)(cb * TAPS + tap) * b_stage16;
-                        } else {
+                        {
                             mbar_wait(bar_b_full + 8u * sb_slot, sb_phase);
                             tc_fence_after();
                             b16 = b_base16 + (uint32_t)sb_slot * b_stage16;
@@ -646,19 +846,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvGeom g) 
                                     }
                                 }
                             }
-                            if (!g.stationary) umma_commit(bar_b_empty + 8u * sb_slot);
+                            umma_commit(bar_b_empty + 8u * sb_slot);
                         }
                         __syncwarp();
-                        if (!g.stationary) {
-                            if (++sb_slot == g.SB) { sb_slot = 0; sb_phase ^= 1u; }
-                        }
+                        if (++sb_slot == g.SB) { sb_slot = 0; sb_phase ^= 1u; }
+                    }
                     }
                     if (elect_one()) {
                         if (sub_lo == 0) umma_commit(bar_a_empty + 8u * slot0);
                         if (sub_hi == 2) umma_commit(bar_a_empty + 8u * slot1);
                     }
                     __syncwarp();
-                    ia += g.msub;
+                    rs += g.msub;
+                    if (rs >= g.SAr) { rs -= g.SAr; rs_par ^= 1u; }
                 }
                 if (elect_one()) umma_commit(smem_u32(&ctl->acc_full[buf]));
                 __syncwarp();
@@ -720,6 +920,7 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     g->chunks = d->c_blk / 8;
     g->chunk_shift = (g->chunks == 2) ? 1 : (g->chunks == 4) ? 2 : 3;
     g->nparts = (d->precision == DISCO_PREC_BF16X3) ? 2 : 1;
+    g->total_pix = (long long)d->n * d->h_out * d->w_out;
     if (d->taps == 1) {
         g->PIX = 128; g->parplane = 0; g->sbo_a = 128;
     } else if (d->stride == 1) {
@@ -727,20 +928,39 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     } else {
         g->PIX = 33 * 17; g->parplane = 33 * 9 * 16; g->sbo_a = 2 * 9 * 16;
     }
+    // TMA for the A operand: every source that is not zero-stuffed (src_up == 2 is the transposed-conv trick of the
+    // training data gradient and keeps the cp.async gather).  DISCO_CONV_NO_TMA=1 forces the cp.async gather (A/B tests).
+    g->use_tma = 0; g->scratch_warp = 0; g->scratch_total = 0;
+    {
+        static int no_tma = -1;
+        if (no_tma < 0) { const char* e = getenv("DISCO_CONV_NO_TMA"); no_tma = (e && e[0] == '1') ? 1 : 0; }
+        const bool any_plain = (d->src_up[0] != 2) || (d->src_c[1] && d->src_up[1] != 2);
+        const bool up_in_s2 = d->stride == 2 && (d->src_up[0] == 1 || (d->src_c[1] && d->src_up[1] == 1));
+        if (!no_tma && any_plain && !up_in_s2 && g->total_pix < (1ll << 31) && get_encode_tiled()) g->use_tma = 1;
+    }
     int plane = (d->taps == 9 && d->stride == 2) ? 2 * g->parplane : g->PIX * 16;
-    // pad so that the `chunks` 16-byte writes of one pixel land in distinct bank groups
-    const int want = (128 / (g->chunks > 8 ? 8 : g->chunks)) % 128;
-    while ((plane % 128) != want) plane += 16;
+    if (g->use_tma) {
+        // TMA destinations are 128-byte aligned: round the per-chunk planes up (the async proxy has no bank conflicts to dodge)
+        if (d->taps == 9 && d->stride == 2) { g->parplane = (g->parplane + 127) / 128 * 128; plane = 2 * g->parplane; }
+        else plane = (plane + 127) / 128 * 128;
+        if (d->taps == 9 && (d->src_up[0] == 1 || (d->src_c[1] && d->src_up[1] == 1))) {
+            g->scratch_warp = g->nparts * g->chunks * kScrBox;
+            g->scratch_total = kProdWarps * g->scratch_warp;
+        }
+    } else {
+        // pad so that the `chunks` 16-byte writes of one pixel land in distinct bank groups
+        const int want = (128 / (g->chunks > 8 ? 8 : g->chunks)) % 128;
+        while ((plane % 128) != want) plane += 16;
+    }
     g->plane = plane;
     g->a_part_bytes = g->chunks * plane;
     g->a_stage_bytes = ((g->nparts * g->a_part_bytes + 127) / 128) * 128;
     g->b_part_bytes = d->c_blk * d->block_n * 2;
     g->b_stage_bytes = g->nparts * g->b_part_bytes;
     g->n_tiles = (d->c_out + d->block_n - 1) / d->block_n;
-    g->total_pix = (long long)d->n * d->h_out * d->w_out;
 
     const int stage_region = d->chain_c_out > 0 ? 0 : kStageBytes;
-    const int budget = 224 * 1024 - kCtlBytes - kBiasBytes - stage_region;
+    const int budget = 224 * 1024 - kCtlBytes - kBiasBytes - stage_region - g->scratch_total;
     g->w_bytes = g->ncb * d->taps * g->b_stage_bytes;
     // MSUB = 2 (256-pixel items) when the N tile leaves room for double-buffered accumulators and the
     // image is wide enough; it halves the weight stream per MAC.
@@ -802,7 +1022,7 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
         if (sa > kMaxStages) sa = kMaxStages;
         g->SA = sa;
         g->SB = 1;
-        g->smem_bytes = kCtlBytes + kBiasBytes + stage_region + g->SA * g->a_stage_bytes + g->w_bytes + chain_smem;
+        g->smem_bytes = kCtlBytes + kBiasBytes + stage_region + g->scratch_total + g->SA * g->a_stage_bytes + g->w_bytes + chain_smem;
     } else {
         int sa = 2 * g->msub;  // current + next channel block
         if (sa < 4 && 4 * g->a_stage_bytes <= budget / 3) sa = 4;
@@ -816,7 +1036,7 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
                       g->a_stage_bytes, g->b_stage_bytes);
         g->SA = sa;
         g->SB = sb;
-        g->smem_bytes = kCtlBytes + kBiasBytes + stage_region + g->SA * g->a_stage_bytes + g->SB * g->b_stage_bytes;
+        g->smem_bytes = kCtlBytes + kBiasBytes + stage_region + g->scratch_total + g->SA * g->a_stage_bytes + g->SB * g->b_stage_bytes;
     }
     DISCO_REQUIRE(g->SA >= g->msub && g->SA >= 1, "conv: not enough A stages");
     g->by_sub = 0;
@@ -840,8 +1060,28 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     DISCO_REQUIRE(m_tiles > 0 && m_tiles * g->n_tiles < (1ll << 30), "conv: bad tile count");
     g->m_tiles = (int)m_tiles;
     g->items = g->m_tiles * g->n_tiles;
+    g->fd_m_tiles = make_fastdiv(g->m_tiles);
+    g->fd_per_img = make_fastdiv(g->tiles_h * g->tiles_w);
+    g->fd_tiles_w = make_fastdiv(g->tiles_w);
     g->grid = g->items < ctas_per_sm * g_num_sms ? g->items : ctas_per_sm * g_num_sms;
     DISCO_REQUIRE((g->plane >> 4) < 16384 && g->smem_bytes <= 227 * 1024, "conv: descriptor / smem range");
+    if (g->use_tma) {
+        for (int s = 0; s < 2; ++s) {
+            if (!d->src_c[s] || d->src_up[s] == 2) continue;
+            const int up = d->src_up[s] ? 1 : 0;
+            const int Hs = d->h_in >> up, Ws = d->w_in >> up;
+            for (int part = 0; part < g->nparts; ++part) {
+                const uint16_t* base = reinterpret_cast<const uint16_t*>(d->src[s]) + (part ? d->src_lo_off[s] : 0);
+                DISCO_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "conv: source %d is not 16-byte aligned", s);
+                bool ok;
+                if (d->taps == 1) ok = make_tmap2(&g->tmap[s * 2 + part], base, d->src_c[s], g->total_pix);
+                else if (up) ok = make_tmap4(&g->tmap[s * 2 + part], base, d->src_c[s], Ws, Hs, d->n, 6, 10, 1);
+                else if (d->stride == 1) ok = make_tmap4(&g->tmap[s * 2 + part], base, d->src_c[s], Ws, Hs, d->n, 10, 18, 1);
+                else ok = make_tmap4(&g->tmap[s * 2 + part], base, d->src_c[s], Ws, Hs, d->n, 18, 33, 2);
+                DISCO_REQUIRE(ok, "conv: cuTensorMapEncodeTiled failed (source %d: C %d, %dx%d, n %d)", s, d->src_c[s], Hs, Ws, d->n);
+            }
+        }
+    }
     return DISCO_OK;
 }
 

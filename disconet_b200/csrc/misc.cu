@@ -161,7 +161,40 @@ __global__ void bev_scatter_kernel(const int* __restrict__ idx, int n, int dx, i
     if (act) act[pix * act_c + z] = one_bits;
 }
 
+// Batched dataset scatter straight into the encoder's input activation: indices [n, m_max, 3] (x, y, z; rows >= count[a] are
+// ignored) -> act[a, y, X-1-x, z] = 1 in the 16-channel NHWC input buffer (hi plane; the lo plane of an exact 0/1 tensor is 0).
+__global__ void bev_scatter_batched_kernel(const int* __restrict__ idx, const int* __restrict__ count, int m_max, int dx, int dy,
+                                           int dz, uint16_t* __restrict__ act, int act_c, uint16_t one_bits) {
+    const int a = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m_max || i >= count[a]) return;
+    const int* p = idx + ((long long)a * m_max + i) * 3;
+    const int x = p[0], y = p[1], z = p[2];
+    if (x < 0 || x >= dx || y < 0 || y >= dy || z < 0 || z >= dz) return;
+    const long long pix = ((long long)a * dy + y) * dx + (dx - 1 - x);
+    act[pix * act_c + z] = one_bits;
+}
+
 }  // namespace
+
+int disco_bev_scatter_batched_launch(const int* voxel_indices, const int* counts, int n, int m_max, const int* dims, void* act_hi,
+                                     long long act_lo_off, int act_c, int precision, void* stream) {
+    DISCO_REQUIRE(dims && act_hi && counts, "bev_scatter_batched: null argument");
+    DISCO_REQUIRE(n > 0 && m_max >= 0 && (m_max == 0 || voxel_indices), "bev_scatter_batched: bad indices");
+    DISCO_REQUIRE(act_c >= dims[2], "bev_scatter_batched: act_c %d < z dim %d", act_c, dims[2]);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t plane = (size_t)n * dims[0] * dims[1] * act_c * 2;
+    DISCO_CHECK_CUDA(cudaMemsetAsync(act_hi, 0, plane, s));
+    if (precision == DISCO_PREC_BF16X3) DISCO_CHECK_CUDA(cudaMemsetAsync((uint16_t*)act_hi + act_lo_off, 0, plane, s));
+    if (m_max > 0) {
+        const uint16_t one = (precision == DISCO_PREC_BF16X3) ? 0x3F80 : 0x3C00;
+        dim3 grid((m_max + 255) / 256, n);
+        bev_scatter_batched_kernel<<<grid, 256, 0, s>>>(voxel_indices, counts, m_max, dims[0], dims[1], dims[2], (uint16_t*)act_hi,
+                                                        act_c, one);
+        DISCO_CHECK_CUDA(cudaGetLastError());
+    }
+    return DISCO_OK;
+}
 
 int disco_bev_pack_launch(const float* bev, long long n_pix, int z, void* out_hi, long long out_lo_off, int precision,
                           void* stream) {

@@ -47,6 +47,9 @@ int disco_voxelize_launch(const float* points, int n_points, int point_stride, c
 int disco_bev_scatter_launch(const int* voxel_indices, int n_voxels, const int* dims, float* bev_f32, void* act_hi,
                              int act_c, int precision, void* stream);
 
+int disco_bev_scatter_batched_launch(const int* voxel_indices, const int* counts, int n, int m_max, const int* dims, void* act_hi,
+                                     long long act_lo_off, int act_c, int precision, void* stream);
+
 // BEV-segmentation U-Net data movement (seg.cu)
 int disco_maxpool2_launch(const void* src_hi, long long src_lo_off, void* dst_hi, long long dst_lo_off, int precision, int n,
                           int h, int w, int c, void* stream);
@@ -61,3 +64,12 @@ int disco_det_candidates_launch(const float* loc, const float* cls, const float*
 int disco_maxpool2_backward_launch(const void* x_hi, long long x_lo_off, int precision, const float* g, float* gx, int n, int h, int w,
                                    int c, void* stream);
 int disco_upsample_bilinear2x_backward_launch(const float* g_up, float* gs, int n, int h, int w, int c, void* stream);
+
+// Detection post-processing + regression loss (post.cu)
+#include <stddef.h>
+size_t disco_nms_workspace_bytes_impl(int n, int kmax);
+int disco_nms_rotated_launch(const void* corners, int corners_f64, const float* scores, const int* ids, const int* count, int n,
+                             int cap, int kmax, float score_thresh, double iou_thresh, void* workspace, size_t workspace_bytes,
+                             int* keep, int* n_keep, int* n_valid, void* stream);
+int disco_corner_loss_launch(const float* pred, const float* target, const float* anchors, const unsigned char* mask,
+                             long long n_entries, int t_len, float inv_n, double* loss_sum, float* grad, void* stream);

@@ -1,0 +1,361 @@
+// Detection post-processing and regression loss on the device.
+//
+//   nms_rotated  : the reference's `non_max_suppression` (utils/postprocess.py:72-115) -- keep `scores > 0.7`, order by
+//                  descending score, then greedily pick the best box and drop every remaining box whose rotated-polygon
+//                  IoU with it exceeds the threshold (0.01 at both call sites: detection_util.py:349-351 `apply_nms_det`
+//                  and :962-964 `late_fusion`).  The reference builds shapely polygons on the host and runs an O(n^2)
+//                  Python loop per agent; here: one block sorts the candidates of an agent (bitonic, 64-bit keys), a
+//                  grid computes the upper-triangular "IoU > thr" bit matrix with an exact float64 convex-quad clip
+//                  (Sutherland-Hodgman + shoelace; same operation order as oracle/post_oracle.py, no FMA contraction),
+//                  and one warp per agent replays the greedy scan over the bit rows.
+//   corner_loss  : `FaFModule.corner_loss` (utils/CoDetModule.py:80-105): decode prediction and target of every
+//                  assigned anchor (bev_box_decode_torch, detection_util.py:376-400), four rotated corners each
+//                  (center_to_corner_box2d_torch :403-479), sum of corner distances / N -- value and gradient wrt the
+//                  regression map in ONE launch (the reference gathers, decodes and back-propagates through ~40 torch ops).
+#include "common.cuh"
+#include "conv.h"
+#include "ops.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------
+// exact-order float64 helpers (no FMA contraction: every product and sum is rounded like numpy does it)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+// cross(b - a, p - a)
+__device__ __forceinline__ double cross3(double ax, double ay, double bx, double by, double px, double py) {
+    return dsub(dmul(dsub(bx, ax), dsub(py, ay)), dmul(dsub(by, ay), dsub(px, ax)));
+}
+
+// shoelace: 0.5 * sum(x_i * y_{i+1} - x_{i+1} * y_i), summed in index order
+__device__ __forceinline__ double poly_area_signed(const double* x, const double* y, int n) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const int j = (i + 1 == n) ? 0 : i + 1;
+        s = dadd(s, dsub(dmul(x[i], y[j]), dmul(x[j], y[i])));
+    }
+    return dmul(0.5, s);
+}
+
+// Intersection area of two convex quads (vertices in either orientation).  Sutherland-Hodgman: clip P by the four edges
+// of Q (both made counter-clockwise first).  Inside test `cross >= 0`; an edge crossing is s + t (e - s) with
+// t = ds / (ds - de).  Must stay in lock-step with oracle/post_oracle.py::quad_intersection_area.
+__device__ double quad_intersection_area(const double* P, const double* Q) {
+    double px[4], py[4], qx[4], qy[4];
+    for (int i = 0; i < 4; ++i) { px[i] = P[2 * i]; py[i] = P[2 * i + 1]; qx[i] = Q[2 * i]; qy[i] = Q[2 * i + 1]; }
+    if (poly_area_signed(px, py, 4) < 0.0) {
+        double t;
+        t = px[1]; px[1] = px[3]; px[3] = t; t = py[1]; py[1] = py[3]; py[3] = t;
+    }
+    if (poly_area_signed(qx, qy, 4) < 0.0) {
+        double t;
+        t = qx[1]; qx[1] = qx[3]; qx[3] = t; t = qy[1]; qy[1] = qy[3]; qy[3] = t;
+    }
+    double sx[8], sy[8], ox[8], oy[8];
+    int n = 4;
+    for (int i = 0; i < 4; ++i) { sx[i] = px[i]; sy[i] = py[i]; }
+    for (int e = 0; e < 4 && n > 0; ++e) {
+        const double ax = qx[e], ay = qy[e], bx = qx[(e + 1) & 3], by = qy[(e + 1) & 3];
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            const int j = (i + 1 == n) ? 0 : i + 1;
+            const double ds = cross3(ax, ay, bx, by, sx[i], sy[i]);
+            const double de = cross3(ax, ay, bx, by, sx[j], sy[j]);
+            const bool in_s = ds >= 0.0, in_e = de >= 0.0;
+            if (in_s && m < 8) { ox[m] = sx[i]; oy[m] = sy[i]; ++m; }
+            if (in_s != in_e && m < 8) {
+                const double t = ds / dsub(ds, de);
+                ox[m] = dadd(sx[i], dmul(t, dsub(sx[j], sx[i])));
+                oy[m] = dadd(sy[i], dmul(t, dsub(sy[j], sy[i])));
+                ++m;
+            }
+        }
+        n = m;
+        for (int i = 0; i < n; ++i) { sx[i] = ox[i]; sy[i] = oy[i]; }
+    }
+    if (n < 3) return 0.0;
+    return fabs(poly_area_signed(sx, sy, n));
+}
+
+__device__ __forceinline__ double quad_area(const double* P) {
+    double x[4], y[4];
+    for (int i = 0; i < 4; ++i) { x[i] = P[2 * i]; y[i] = P[2 * i + 1]; }
+    return fabs(poly_area_signed(x, y, 4));
+}
+
+// iou > thr, with the decision the oracle makes: inter / (area_p + area_q - inter); a zero union gives NaN -> false.
+__device__ __forceinline__ bool quad_iou_above(const double* P, const double* Q, double thr) {
+    // axis-aligned bounding boxes that do not touch cannot intersect: exact-zero intersection, IoU 0 (or 0/0), never > thr
+    double pl = P[0], ph = P[0], pb = P[1], pt = P[1], ql = Q[0], qh = Q[0], qb = Q[1], qt = Q[1];
+    for (int i = 1; i < 4; ++i) {
+        pl = fmin(pl, P[2 * i]); ph = fmax(ph, P[2 * i]); pb = fmin(pb, P[2 * i + 1]); pt = fmax(pt, P[2 * i + 1]);
+        ql = fmin(ql, Q[2 * i]); qh = fmax(qh, Q[2 * i]); qb = fmin(qb, Q[2 * i + 1]); qt = fmax(qt, Q[2 * i + 1]);
+    }
+    if (ph < ql || qh < pl || pt < qb || qt < pb) return false;
+    const double inter = quad_intersection_area(P, Q);
+    const double uni = dsub(dadd(quad_area(P), quad_area(Q)), inter);
+    const double iou = inter / uni;
+    return iou > thr;   // NaN compares false
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// 1. per-agent candidate sort: key = score bits | anchor id | slot, descending (score desc, ties: larger id first, which is
+//    what `scores.argsort()[::-1]` yields for a stable argsort)
+// ------------------------------------------------------------------------------------------------------------
+template <typename CT>
+__global__ void __launch_bounds__(1024) nms_sort_kernel(const CT* __restrict__ corners, const float* __restrict__ scores,
+                                                        const int* __restrict__ ids, const int* __restrict__ count, int cap,
+                                                        int kmax, float score_thresh, double* __restrict__ s_corners,
+                                                        float* __restrict__ s_scores, int* __restrict__ s_ids,
+                                                        int* __restrict__ s_slot, int* __restrict__ s_count) {
+    extern __shared__ unsigned long long keys[];
+    const int a = blockIdx.x, tid = threadIdx.x;
+    int k_in = count ? count[a] : cap;
+    if (k_in > cap) k_in = cap;
+    int P = 32;
+    while (P < k_in) P <<= 1;
+    for (int i = tid; i < P; i += blockDim.x) {
+        unsigned long long key = 0ull;
+        if (i < k_in) {
+            const float sc = scores[(long long)a * cap + i];
+            if (sc > score_thresh) {
+                const unsigned id = ids ? (unsigned)ids[(long long)a * cap + i] : (unsigned)i;
+                key = ((unsigned long long)__float_as_uint(sc) << 32) | ((unsigned long long)(id & 0x7FFFFu) << 13) |
+                      (unsigned long long)(i & 0x1FFF);
+            }
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < P / 2; i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride - 1));   // index with bit `stride` clear
+                const int hi = lo + stride;
+                const bool desc = ((lo & size) == 0);
+                const unsigned long long x = keys[lo], y = keys[hi];
+                if ((x < y) == desc) { keys[lo] = y; keys[hi] = x; }
+            }
+            __syncthreads();
+        }
+    }
+    // number of valid (score > thresh) candidates = non-zero keys (scores > 0 have non-zero bit patterns)
+    __shared__ int n_valid;
+    if (tid == 0) n_valid = 0;
+    __syncthreads();
+    int local = 0;
+    for (int i = tid; i < P; i += blockDim.x) local += keys[i] != 0ull;
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((tid & 31) == 0 && local) atomicAdd(&n_valid, local);
+    __syncthreads();
+    int K = n_valid;
+    if (K > kmax) K = kmax;
+    if (tid == 0) s_count[a] = n_valid;   // (> kmax reports the overflow to the host)
+    for (int r = tid; r < K; r += blockDim.x) {
+        const unsigned long long key = keys[r];
+        const int slot = (int)(key & 0x1FFF);
+        const long long src = (long long)a * cap + slot, dst = (long long)a * kmax + r;
+        s_scores[dst] = __uint_as_float((unsigned)(key >> 32));
+        s_ids[dst] = ids ? ids[src] : slot;
+        s_slot[dst] = slot;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s_corners[dst * 8 + q] = (double)corners[src * 8 + q];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// 2. upper-triangular "IoU > thr" bit matrix: mask[a][i][j / 64] bit (j % 64), j > i
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) nms_mask_kernel(const double* __restrict__ s_corners, const int* __restrict__ s_count,
+                                                      int kmax, int words, double thr,
+                                                      unsigned long long* __restrict__ mask) {
+    const int a = blockIdx.z, rb = blockIdx.y, cb = blockIdx.x, t = threadIdx.x;
+    int K = s_count[a];
+    if (K > kmax) K = kmax;
+    if (cb < rb || rb * 64 >= K || cb * 64 >= K) return;
+    __shared__ double cq[64][8];
+    const int j0 = cb * 64;
+    if (j0 + t < K) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) cq[t][q] = s_corners[((long long)a * kmax + j0 + t) * 8 + q];
+    }
+    __syncthreads();
+    const int i = rb * 64 + t;
+    if (i >= K) return;
+    double P[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) P[q] = s_corners[((long long)a * kmax + i) * 8 + q];
+    unsigned long long bits = 0ull;
+    const int jn = min(64, K - j0);
+    for (int jj = 0; jj < jn; ++jj) {
+        if (j0 + jj <= i) continue;
+        if (quad_iou_above(P, cq[jj], thr)) bits |= 1ull << jj;
+    }
+    mask[((long long)a * kmax + i) * words + cb] = bits;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// 3. greedy scan (postprocess.py:97-112), one warp per agent: rows of removed boxes are skipped
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ s_count,
+                                                      const int* __restrict__ s_slot, int kmax, int words, int* __restrict__ keep,
+                                                      int* __restrict__ n_keep) {
+    extern __shared__ unsigned long long removed[];
+    const int a = blockIdx.x, lane = threadIdx.x;
+    int K = s_count[a];
+    if (K > kmax) K = kmax;
+    const int kw = (K + 63) / 64;
+    for (int w = lane; w < kw; w += 32) removed[w] = 0ull;
+    __syncwarp();
+    int nk = 0;
+    for (int i = 0; i < K; ++i) {
+        const bool gone = (removed[i >> 6] >> (i & 63)) & 1ull;   // warp-uniform (shared memory broadcast)
+        if (gone) continue;
+        if (lane == 0) keep[(long long)a * kmax + nk] = s_slot[(long long)a * kmax + i];
+        ++nk;
+        const unsigned long long* row = mask + ((long long)a * kmax + i) * words;
+        for (int w = (i >> 6) + lane; w < kw; w += 32) removed[w] |= row[w];
+        __syncwarp();
+    }
+    if (lane == 0) n_keep[a] = nk;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// corner loss: value + gradient, one thread per (anchor, time step)
+// ------------------------------------------------------------------------------------------------------------
+struct Box6 { float x, y, w, h, s, c; };
+
+__device__ __forceinline__ Box6 decode6(const float* p, const float* q) {
+    Box6 b;
+    b.h = q[3] / expf(p[3]);
+    b.w = q[2] / expf(p[2]);
+    b.x = q[0] - b.w * p[0];
+    b.y = q[1] - b.h * p[1];
+    b.s = q[4] * p[5] + q[5] * p[4];
+    b.c = q[5] * p[5] - q[4] * p[4];
+    return b;
+}
+
+__global__ void __launch_bounds__(256) corner_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                          const float* __restrict__ anchors, const unsigned char* __restrict__ mask,
+                                                          long long n_entries, int t_len, float inv_n, double* __restrict__ loss_sum,
+                                                          float* __restrict__ grad) {
+    __shared__ double warp_sum[8];
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double mine = 0.0;
+    if (e < n_entries) {
+        float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (mask[e]) {
+            const float* p = pred + e * 6;
+            const float* q = anchors + (e / t_len) * 6;
+            const Box6 bp = decode6(p, q), bt = decode6(target + e * 6, q);
+            const float nx[4] = {-0.5f, 0.5f, 0.5f, -0.5f}, ny[4] = {0.5f, 0.5f, -0.5f, -0.5f};
+            float Gx = 0.f, Gy = 0.f, Gw = 0.f, Gh = 0.f, Gs = 0.f, Gc = 0.f, l = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float px = bp.w * nx[k], py = bp.h * ny[k];
+                const float cx = px * bp.c + py * bp.s + bp.x, cy = -px * bp.s + py * bp.c + bp.y;
+                const float qx = bt.w * nx[k], qy = bt.h * ny[k];
+                const float tx = qx * bt.c + qy * bt.s + bt.x, ty = -qx * bt.s + qy * bt.c + bt.y;
+                const float dx = cx - tx, dy = cy - ty;
+                const float d = sqrtf(dx * dx + dy * dy);
+                l += d;
+                const float gx = d > 0.f ? dx / d : 0.f, gy = d > 0.f ? dy / d : 0.f;   // torch.norm's subgradient at 0
+                Gx += gx; Gy += gy;
+                Gw += nx[k] * (gx * bp.c - gy * bp.s);
+                Gh += ny[k] * (gx * bp.s + gy * bp.c);
+                Gc += gx * px + gy * py;
+                Gs += gx * py - gy * px;
+            }
+            mine = (double)l;
+            g[0] = -bp.w * Gx;
+            g[1] = -bp.h * Gy;
+            g[2] = -bp.w * (Gw - p[0] * Gx);
+            g[3] = -bp.h * (Gh - p[1] * Gy);
+            g[4] = Gs * q[5] - Gc * q[4];
+            g[5] = Gs * q[4] + Gc * q[5];
+        }
+        if (grad) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) grad[e * 6 + i] = g[i] * inv_n;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += warp_sum[w];
+        if (s != 0.0) atomicAdd(loss_sum, s);
+    }
+}
+
+}  // namespace
+
+size_t disco_nms_workspace_bytes_impl(int n, int kmax) {
+    const size_t words = (size_t)(kmax + 63) / 64;
+    size_t b = 0;
+    b += (size_t)n * kmax * 8 * sizeof(double);   // sorted corners
+    b += (size_t)n * kmax * sizeof(float);        // sorted scores
+    b += (size_t)n * kmax * sizeof(int) * 2;      // sorted ids, slots
+    b += (size_t)n * sizeof(int) * 2;             // valid count (+pad)
+    b += (size_t)n * kmax * words * 8;            // bit matrix
+    return b + 256;
+}
+
+int disco_nms_rotated_launch(const void* corners, int corners_f64, const float* scores, const int* ids, const int* count, int n,
+                             int cap, int kmax, float score_thresh, double iou_thresh, void* workspace, size_t workspace_bytes,
+                             int* keep, int* n_keep, int* n_valid, void* stream) {
+    DISCO_REQUIRE(corners && scores && workspace && keep && n_keep, "nms: null tensor");
+    DISCO_REQUIRE(n > 0 && cap > 0 && cap <= 8192 && kmax > 0 && kmax <= cap, "nms: need 0 < kmax <= cap <= 8192 (got %d, %d)", kmax, cap);
+    DISCO_REQUIRE(workspace_bytes >= disco_nms_workspace_bytes_impl(n, kmax), "nms: workspace too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int words = (kmax + 63) / 64;
+    uint8_t* w = reinterpret_cast<uint8_t*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    double* s_corners = reinterpret_cast<double*>(w); w += (size_t)n * kmax * 8 * sizeof(double);
+    unsigned long long* mask = reinterpret_cast<unsigned long long*>(w); w += (size_t)n * kmax * words * 8;
+    float* s_scores = reinterpret_cast<float*>(w); w += (size_t)n * kmax * sizeof(float);
+    int* s_ids = reinterpret_cast<int*>(w); w += (size_t)n * kmax * sizeof(int);
+    int* s_slot = reinterpret_cast<int*>(w); w += (size_t)n * kmax * sizeof(int);
+    int* s_count = reinterpret_cast<int*>(w);
+    int P = 32;
+    while (P < cap) P <<= 1;
+    const size_t sort_smem = (size_t)P * 8;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    DISCO_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !attr_set[dev]) {
+        DISCO_CHECK_CUDA(cudaFuncSetAttribute(nms_sort_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        DISCO_CHECK_CUDA(cudaFuncSetAttribute(nms_sort_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_set[dev] = true;
+    }
+    if (corners_f64)
+        nms_sort_kernel<double><<<n, 1024, sort_smem, s>>>((const double*)corners, scores, ids, count, cap, kmax, score_thresh,
+                                                           s_corners, s_scores, s_ids, s_slot, s_count);
+    else
+        nms_sort_kernel<float><<<n, 1024, sort_smem, s>>>((const float*)corners, scores, ids, count, cap, kmax, score_thresh,
+                                                          s_corners, s_scores, s_ids, s_slot, s_count);
+    DISCO_CHECK_CUDA(cudaGetLastError());
+    dim3 grid(words, words, n);
+    nms_mask_kernel<<<grid, 64, 0, s>>>(s_corners, s_count, kmax, words, iou_thresh, mask);
+    DISCO_CHECK_CUDA(cudaGetLastError());
+    nms_scan_kernel<<<n, 32, (size_t)words * 8, s>>>(mask, s_count, s_slot, kmax, words, keep, n_keep);
+    DISCO_CHECK_CUDA(cudaGetLastError());
+    if (n_valid) DISCO_CHECK_CUDA(cudaMemcpyAsync(n_valid, s_count, sizeof(int) * n, cudaMemcpyDeviceToDevice, s));
+    return DISCO_OK;
+}
+
+int disco_corner_loss_launch(const float* pred, const float* target, const float* anchors, const unsigned char* mask,
+                             long long n_entries, int t_len, float inv_n, double* loss_sum, float* grad, void* stream) {
+    DISCO_REQUIRE(pred && target && anchors && mask && loss_sum, "corner_loss: null tensor");
+    DISCO_REQUIRE(n_entries > 0 && t_len > 0, "corner_loss: bad sizes");
+    cudaStream_t s = (cudaStream_t)stream;
+    DISCO_CHECK_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(double), s));
+    const long long blocks = (n_entries + 255) / 256;
+    DISCO_REQUIRE(blocks < (1ll << 31), "corner_loss: too many anchors");
+    corner_loss_kernel<<<(unsigned)blocks, 256, 0, s>>>(pred, target, anchors, mask, n_entries, t_len, inv_n, loss_sum, grad);
+    DISCO_CHECK_CUDA(cudaGetLastError());
+    return DISCO_OK;
+}

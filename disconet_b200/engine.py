@@ -8,6 +8,7 @@ i.e. 26 launches instead of the reference's ~700 ATen kernels per 5-agent scene.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, List, Optional
 
 import torch
@@ -78,6 +79,7 @@ def build_decoder_plans(get: Getter, p: str, precision: int) -> Dict[str, ConvPl
     P: Dict[str, ConvPlan] = {}
 
     def add(name, conv, bn, srcs, c_blk=None):
+        c_blk = int(os.environ.get("DISCO_CBLK_" + name.upper(), "0")) or c_blk     # tuning hook (K-stage width of one layer)
         w, b = _conv_bn(get, p + conv, p + bn)
         P[name] = pack_conv(w, b, src_channels=srcs, relu=True, precision=precision, name=p + conv, c_blk=c_blk)
 

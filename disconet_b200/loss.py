@@ -66,3 +66,44 @@ class SoftmaxFocalClassificationLoss:
             raise NotImplementedError("class_indices is not used on the DiscoNet path")
         loss = _Focal.apply(prediction_tensor, target_tensor, self._gamma, self._alpha)
         return loss * weights if weights is not None else loss
+
+
+class _CornerLoss(torch.autograd.Function):
+    """`FaFModule.corner_loss` (utils/CoDetModule.py:80-105) as one kernel: value and the gradient wrt the regression map."""
+
+    @staticmethod
+    def forward(ctx, pred, anchors, mask, targets):
+        if not (pred.is_cuda and anchors.is_cuda and mask.is_cuda and targets.is_cuda):
+            raise ValueError("disconet_b200.loss runs on CUDA tensors only (no CPU fallback)")
+        if pred.shape != targets.shape or pred.shape[-1] != 6 or tuple(mask.shape) != tuple(pred.shape[:-1]):
+            raise ValueError(f"pred {tuple(pred.shape)} / targets {tuple(targets.shape)} / mask {tuple(mask.shape)} do not match")
+        t_len = pred.shape[-2]
+        if anchors.numel() * t_len != pred.numel():
+            raise ValueError(f"anchors {tuple(anchors.shape)} do not match pred {tuple(pred.shape)}")
+        p = pred.detach().float().contiguous()
+        t = targets.detach().float().contiguous()
+        a = anchors.detach().float().contiguous()
+        m = mask.detach().to(torch.uint8).contiguous()
+        n = pred.shape[0]
+        acc = torch.empty((), dtype=torch.float64, device=p.device)
+        grad = torch.empty_like(p) if pred.requires_grad else None
+        check(load().disco_corner_loss(p.data_ptr(), t.data_ptr(), a.data_ptr(), m.data_ptr(), p.numel() // 6, t_len, 1.0 / n,
+                                       acc.data_ptr(), grad.data_ptr() if grad is not None else None,
+                                       torch.cuda.current_stream(p.device).cuda_stream), "corner_loss")
+        ctx.grad = grad
+        return (acc / n).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return (ctx.grad * g if ctx.grad is not None else None), None, None, None
+
+
+def corner_loss(anchors, reg_loss_mask, reg_targets, pred_result):
+    """Same arguments and result as `FaFModule.corner_loss(self, anchors, reg_loss_mask, reg_targets, pred_result)`:
+    anchors [N,H,W,A,6], reg_loss_mask [N,H,W,A,T] bool, reg_targets / pred_result [N,H,W,A,T,6] -> scalar
+    sum over assigned anchors and corners of ||pred corner - target corner|| / N; differentiable wrt pred_result."""
+    return _CornerLoss.apply(pred_result, anchors, reg_loss_mask, reg_targets)
+
+
+def _corner_loss_method(self, anchors, reg_loss_mask, reg_targets, pred_result):
+    return corner_loss(anchors, reg_loss_mask, reg_targets, pred_result)

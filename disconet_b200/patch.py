@@ -22,11 +22,20 @@ def patch_coperception(classes=("DiscoNet", "FaFNet", "TeacherNet")) -> None:
         sub = sys.modules.get(f"coperception.models.det.{name}")
         if sub is not None:
             setattr(sub, name, getattr(ours, name))
-    # KD loss of the training step (FaFModule.get_kd_loss) on the fused kernel
+    # KD loss (FaFModule.get_kd_loss), corner loss (FaFModule.corner_loss) and the detection post-processing of
+    # predict_all (apply_nms_det -> polygon NMS) on the fused kernels
     try:
         mod = importlib.import_module("coperception.utils.CoDetModule")
-        from . import kd
+        from . import kd, loss as ours_loss, post
         mod.FaFModule.get_kd_loss = kd.get_kd_loss
+        mod.FaFModule.corner_loss = ours_loss._corner_loss_method
+        mod.apply_nms_det = post.apply_nms_det          # CoDetModule does `from ...detection_util import *`
+        du = importlib.import_module("coperception.utils.detection_util")
+        du.apply_nms_det = post.apply_nms_det
+        du.late_fusion = post.late_fusion
+        du.non_max_suppression = post.non_max_suppression
+        pp = importlib.import_module("coperception.utils.postprocess")
+        pp.non_max_suppression = post.non_max_suppression
     except Exception:
         pass
     # focal classification loss (train_codet.py:173-176 builds it from coperception.utils.loss)

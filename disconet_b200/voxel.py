@@ -79,3 +79,38 @@ def bev_scatter(voxel_indices: torch.Tensor, dims, *, packed: bool = False, prec
                                    act.data_ptr() if act is not None else None, 16, precision,
                                    _stream_ptr(dev)), "bev_scatter")
     return (bev, act) if packed else bev
+
+
+def bev_scatter_batched(voxel_indices: torch.Tensor, counts: torch.Tensor, dims, act: torch.Tensor, precision: int = PREC_BF16X3):
+    """Dataset scatter of a whole batch (V2XSimDet.py:293-302 per agent) straight into the encoder's input activation:
+    voxel_indices [N, M_max, 3] int32 (x, y, z), counts [N] int32 -> act [parts, N, Y, X, 16] (zeroed, then act[a, y, X-1-x, z] = 1)."""
+    _require_cuda(voxel_indices, counts, act)
+    if voxel_indices.dtype != torch.int32 or counts.dtype != torch.int32:
+        raise ValueError("voxel indices / counts must be int32")
+    voxel_indices, counts = voxel_indices.contiguous(), counts.contiguous()
+    dx, dy, dz = (int(d) for d in dims)
+    n, m_max = voxel_indices.shape[0], voxel_indices.shape[1]
+    if tuple(act.shape[1:]) != (n, dy, dx, 16):
+        raise ValueError(f"activation buffer {tuple(act.shape)} does not match {n} agents of {dy}x{dx}x16")
+    cd = (C.c_int * 3)(dx, dy, dz)
+    lo_off = act.stride(0) if act.shape[0] == 2 else 0
+    check(load().disco_bev_scatter_batched(voxel_indices.data_ptr(), counts.data_ptr(), n, m_max, cd, act.data_ptr(), lo_off, 16,
+                                           precision, _stream_ptr(act.device)), "bev_scatter_batched")
+    return act
+
+
+def bev_to_voxel_indices(bev: torch.Tensor):
+    """Inverse of the dataset scatter for host-side synthetic data: dense BEV [N, 1, Y, X, Z] (0/1) -> (indices [N, M_max, 3]
+    int32 padded with -1, counts [N] int32) with (x, y, z) such that bev[a, 0, y, X-1-x, z] = 1 (V2XSimDet.py:293-302)."""
+    b = bev[:, 0] if bev.dim() == 5 else bev
+    n, Y, X, Z = b.shape
+    nz = torch.nonzero(b > 0)                      # [K, 4] = (a, r, c, z) sorted by a
+    counts = torch.bincount(nz[:, 0], minlength=n).to(torch.int32)
+    m_max = int(counts.max()) if nz.numel() else 0
+    idx = torch.full((n, max(m_max, 1), 3), -1, dtype=torch.int32)
+    start = torch.cumsum(counts, 0) - counts
+    pos = torch.arange(nz.shape[0]) - start[nz[:, 0]].long()
+    idx[nz[:, 0], pos, 0] = (X - 1 - nz[:, 2]).to(torch.int32)
+    idx[nz[:, 0], pos, 1] = nz[:, 1].to(torch.int32)
+    idx[nz[:, 0], pos, 2] = nz[:, 3].to(torch.int32)
+    return idx, counts

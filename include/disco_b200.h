@@ -101,6 +101,12 @@ int disco_voxelize_occupy(const float* points, int n_points, int point_stride, c
 int disco_bev_scatter(const int* voxel_indices, int n_voxels, const int* dims /* host */, float* bev_f32,
                       void* act_hi, int act_c, int precision, void* stream);
 
+/* The same scatter for a whole batch of agents, straight into the encoder's input activation (skips the dense fp32 BEV of
+ * V2XSimDet.py:293-302 and its 3.4 MB/agent host->device copy): voxel_indices [n, m_max, 3] int32 (device), counts [n]
+ * (device; rows >= counts[a] ignored), act = activation buffer [parts, n, Y, X, act_c] (zeroed by the call). */
+int disco_bev_scatter_batched(const int* voxel_indices, const int* counts, int n, int m_max, const int* dims /* host */,
+                              void* act_hi, long long act_lo_off, int act_c, int precision, void* stream);
+
 /* DiscoGraph fusion block: per-ego affine warp of every neighbour map (DetModelBase.py:139-209),
  * PixelWeightedFusionSoftmax tail (DiscoNet.py:150-153), agent-axis softmax and weighted sum
  * (DiscoNet.py:83-111) in one launch. */
@@ -136,6 +142,28 @@ int disco_fusion_forward(const disco_fusion_desc* d /* host */, void* stream);
 int disco_det_candidates(const float* loc, const float* cls, const float* anchors, long long anchors_per_agent,
                          long long anchor_agent_stride, int n_agents, float thresh, int max_cand, int* count, float* corners,
                          float* scores, int* index, void* stream);
+
+/* Rotated-box NMS: `non_max_suppression` of utils/postprocess.py:72-115 (called with threshold 0.01 by apply_nms_det,
+ * detection_util.py:349-351, and late_fusion, :962-964) for n_sets independent candidate sets in one go.
+ * corners [n_sets, cap, 4, 2] (float32, or float64 when corners_f64), scores [n_sets, cap], ids [n_sets, cap] or NULL
+ * (tie-break key: the anchor number; NULL = the position), count [n_sets] (device; NULL = every set holds `cap` boxes).
+ * Keeps scores > score_thresh, orders by descending score (ties: larger id first = `scores.argsort()[::-1]` of a
+ * stable argsort), then greedily drops every box whose polygon IoU (float64 convex clip) with a picked one is > iou_thresh.
+ * keep [n_sets, kmax] receives the picked POSITIONS (into corners/scores) in pick order, n_keep [n_sets] their number,
+ * n_valid [n_sets] (optional) the number of boxes above score_thresh (> kmax means the set was truncated to the kmax best).
+ * cap <= 8192, ids < 2^19.  workspace: disco_nms_workspace_bytes(n_sets, kmax) bytes of device memory. */
+long long disco_nms_workspace_bytes(int n_sets, int kmax);
+int disco_nms_rotated(const void* corners, int corners_f64, const float* scores, const int* ids, const int* count, int n_sets,
+                      int cap, int kmax, float score_thresh, double iou_thresh, void* workspace, long long workspace_bytes,
+                      int* keep, int* n_keep, int* n_valid, void* stream);
+
+/* `FaFModule.corner_loss` (utils/CoDetModule.py:80-105), value and gradient in one launch: for every entry e of
+ * pred / target [n_entries, 6] with mask[e] != 0 (reg_loss_mask, one byte per entry; t_len consecutive entries share an
+ * anchor of anchors [n_entries / t_len, 6]): decode both boxes (bev_box_decode_torch), four rotated corners each
+ * (center_to_corner_box2d_torch), sum of the corner distances.  *loss_sum (float64, zeroed by the call) receives the
+ * UNSCALED sum; grad (optional, [n_entries, 6]) receives inv_n * d(sum)/d(pred), zeros where the mask is 0. */
+int disco_corner_loss(const float* pred, const float* target, const float* anchors, const unsigned char* mask, long long n_entries,
+                      int t_len, float inv_n, double* loss_sum, float* grad, void* stream);
 
 /* ---- BEV segmentation U-Net (models/seg/SegModelBase.py) around disco_conv_forward ------------------------
  * nn.MaxPool2d(2) of the Down blocks (:113-123): activation buffer [n,h,w,c] -> [n,h/2,w/2,c]. */

@@ -5,7 +5,7 @@ import torch
 from bench import Cfg, AGENTS, synth_inputs
 from disconet_b200 import DiscoNet, synth
 dev = torch.device("cuda:0")
-B = 8
+B = int(os.environ.get("TRACE_B", "16"))
 m = DiscoNet(Cfg(), kd_flag=0, num_agent=AGENTS, precision=os.environ.get("PRECISION", "bf16x3"))
 m.load_state_dict(synth.synth_state_dict(m.state_dict(), seed=0)); m = m.to(dev).eval()
 bev, T, na = synth_inputs(B, 100)
