@@ -35,6 +35,7 @@ class ConvDesc(C.Structure):
         ("out_lo_off", C.c_longlong),
         ("out_split", C.c_int),
         ("chain_wpack", C.c_void_p), ("chain_bias", C.c_void_p), ("chain_c_out", C.c_int), ("chain_relu", C.c_int),
+        ("src_lo_nonzero", C.c_void_p),
     ]
 
 
@@ -125,7 +126,7 @@ EXPORTS = {
     "disco_conv_forward": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "disco_conv_reference": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "disco_conv_smem_bytes": (C.c_int, [C.POINTER(ConvDesc)]),
-    "disco_bev_pack": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
+    "disco_bev_pack": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
     "disco_act_unpack_nchw": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p, C.c_void_p]),
     "disco_voxelize_occupy": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -134,7 +135,7 @@ EXPORTS = {
     "disco_bev_scatter": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_int,
                                     C.c_int, C.c_void_p]),
     "disco_bev_scatter_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_longlong,
-                                            C.c_int, C.c_int, C.c_void_p]),
+                                            C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "disco_fusion_forward": (C.c_int, [C.POINTER(FusionDesc), C.c_void_p]),
     "disco_det_candidates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_float, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

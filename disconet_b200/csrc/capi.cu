@@ -55,8 +55,8 @@ int disco_conv_smem_bytes(const disco_conv_desc* d) {
 }
 
 int disco_bev_pack(const float* bev, long long n_pix, int z, void* out_hi, long long out_lo_off, int precision,
-                   void* stream) {
-    return disco_bev_pack_launch(bev, n_pix, z, out_hi, out_lo_off, precision, stream);
+                   int* lo_nonzero, void* stream) {
+    return disco_bev_pack_launch(bev, n_pix, z, out_hi, out_lo_off, precision, lo_nonzero, stream);
 }
 
 int disco_act_unpack_nchw(const void* act_hi, long long lo_off, int precision, int n, int h, int w, int c,
@@ -77,8 +77,8 @@ int disco_bev_scatter(const int* voxel_indices, int n_voxels, const int* dims, f
 }
 
 int disco_bev_scatter_batched(const int* voxel_indices, const int* counts, int n, int m_max, const int* dims, void* act_hi,
-                              long long act_lo_off, int act_c, int precision, void* stream) {
-    return disco_bev_scatter_batched_launch(voxel_indices, counts, n, m_max, dims, act_hi, act_lo_off, act_c, precision, stream);
+                              long long act_lo_off, int act_c, int precision, int* lo_nonzero, void* stream) {
+    return disco_bev_scatter_batched_launch(voxel_indices, counts, n, m_max, dims, act_hi, act_lo_off, act_c, precision, lo_nonzero, stream);
 }
 
 int disco_fusion_forward(const disco_fusion_desc* d, void* stream) {

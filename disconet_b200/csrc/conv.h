@@ -48,6 +48,9 @@ struct disco_conv_desc {
     const float* chain_bias; // [chain_block_n]
     int chain_c_out;         // 0 = no chain
     int chain_relu;
+    /* optional device flag (int): when it reads 0 every lo element of the sources is zero (exact 0/1 occupancy input written by
+     * disco_bev_pack / disco_bev_scatter_batched), so the kernel skips the lo-plane loads and the A_lo*W_hi pass; NULL = use lo */
+    const int* src_lo_nonzero;
 };
 
 int disco_conv_tc_launch(const disco_conv_desc* d, void* stream);

@@ -300,6 +300,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     tc_fence_after();
     const uint32_t tmem_d = ctl->tmem_base;
     const int stages_per_item = g.ncb * g.msub;
+    // exact 0/1 occupancy input (first encoder conv): the lo plane is identically zero -> neither fetched nor multiplied
+    const bool skip_lo = SPLIT && g.d.src_lo_nonzero != nullptr && *g.d.src_lo_nonzero == 0;
+    const int a_parts = skip_lo ? 1 : g.nparts;
     // trace layout: [role 0..3][item 0..63][4 stamps]; roles: 0 epilogue, 1 producer warp 0, 2 MMA, 3 B loader
 #define TRACE(role, it_, k) do { if (g.trace && blockIdx.x == 0 && (it_) < 64 && lane == 0) g.trace[((role) * 64 + (it_)) * 4 + (k)] = clock64(); } while (0)
 
@@ -520,8 +523,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     if (lane == 0) {
                         const uint32_t bar = smem_u32(&ctl->a_full[sa]);
                         constexpr uint32_t kBox = (MODE == 0) ? 18u * 10u * 16u : (MODE == 1) ? 2u * 33u * 9u * 16u : 128u * 16u;
-                        mbar_arrive_expect_tx(bar, (uint32_t)(g.nparts * g.chunks) * kBox);
-                        for (int part = 0; part < g.nparts; ++part) {
+                        mbar_arrive_expect_tx(bar, (uint32_t)(a_parts * g.chunks) * kBox);
+                        for (int part = 0; part < a_parts; ++part) {
                             const CUtensorMap* tm = &g.tmap[sidx * 2 + part];
                             for (int chunk = 0; chunk < g.chunks; ++chunk) {
                                 const uint32_t dst = stage + (uint32_t)part * g.a_part_bytes + (uint32_t)chunk * g.plane;
@@ -796,11 +799,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                                             const uint32_t accf = (tap == 0 && ks == 0) ? first : 1u;
                                             if (STACKED) {
                                                 umma_f16_parts(td, alo, a_hi, blo, b_hi, idesc2, accf);            // hi*[hi|lo]
-                                                umma_f16_parts(td, alo + a_part16, a_hi, blo, b_hi, idesc, 1u);   // lo*hi
+                                                if (!skip_lo) umma_f16_parts(td, alo + a_part16, a_hi, blo, b_hi, idesc, 1u);   // lo*hi
                                             } else {
                                                 umma_f16_parts(td, alo, a_hi, blo, b_hi, idesc, accf);
                                                 if (SPLIT) {
-                                                    umma_f16_parts(td, alo + a_part16, a_hi, blo, b_hi, idesc, 1u);
+                                                    if (!skip_lo) umma_f16_parts(td, alo + a_part16, a_hi, blo, b_hi, idesc, 1u);
                                                     umma_f16_parts(td, alo, a_hi, blo + b_part16, b_hi, idesc, 1u);
                                                 }
                                             }
@@ -835,11 +838,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                                         const uint32_t accf = (tap == 0 && ks == 0) ? first : 1u;
                                         if (STACKED) {
                                             umma_f16_parts(td, alo, a_hi, blo, b_hi, idesc2, accf);            // hi*[hi|lo]
-                                            umma_f16_parts(td, alo + a_part16, a_hi, blo, b_hi, idesc, 1u);   // lo*hi
+                                            if (!skip_lo) umma_f16_parts(td, alo + a_part16, a_hi, blo, b_hi, idesc, 1u);   // lo*hi
                                         } else {
                                             umma_f16_parts(td, alo, a_hi, blo, b_hi, idesc, accf);
                                             if (SPLIT) {
-                                                umma_f16_parts(td, alo + a_part16, a_hi, blo, b_hi, idesc, 1u);
+                                                if (!skip_lo) umma_f16_parts(td, alo + a_part16, a_hi, blo, b_hi, idesc, 1u);
                                                 umma_f16_parts(td, alo, a_hi, blo + b_part16, b_hi, idesc, 1u);
                                             }
                                         }

@@ -12,7 +12,7 @@
 namespace {
 
 __global__ void bev_pack_kernel(const float* __restrict__ bev, long long n_pix, int z, uint16_t* __restrict__ out_hi,
-                                long long lo_off, int precision) {
+                                long long lo_off, int precision, int* __restrict__ lo_nonzero) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pix) return;
     const float* src = bev + p * z;
@@ -40,6 +40,8 @@ __global__ void bev_pack_kernel(const float* __restrict__ bev, long long n_pix, 
         uint4* ol = reinterpret_cast<uint4*>(out_hi + lo_off + p * 16);
         ol[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         ol[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        // occupancy inputs are exact in bf16 (0/1): tell the first conv when it may skip the lo plane altogether
+        if (lo_nonzero && ((lo[0] | lo[1] | lo[2] | lo[3] | lo[4] | lo[5] | lo[6] | lo[7]) & 0x7FFF7FFFu)) atomicOr(lo_nonzero, 1);
     }
 }
 
@@ -178,12 +180,13 @@ __global__ void bev_scatter_batched_kernel(const int* __restrict__ idx, const in
 }  // namespace
 
 int disco_bev_scatter_batched_launch(const int* voxel_indices, const int* counts, int n, int m_max, const int* dims, void* act_hi,
-                                     long long act_lo_off, int act_c, int precision, void* stream) {
+                                     long long act_lo_off, int act_c, int precision, int* lo_nonzero, void* stream) {
     DISCO_REQUIRE(dims && act_hi && counts, "bev_scatter_batched: null argument");
     DISCO_REQUIRE(n > 0 && m_max >= 0 && (m_max == 0 || voxel_indices), "bev_scatter_batched: bad indices");
     DISCO_REQUIRE(act_c >= dims[2], "bev_scatter_batched: act_c %d < z dim %d", act_c, dims[2]);
     cudaStream_t s = (cudaStream_t)stream;
     const size_t plane = (size_t)n * dims[0] * dims[1] * act_c * 2;
+    if (lo_nonzero) DISCO_CHECK_CUDA(cudaMemsetAsync(lo_nonzero, 0, sizeof(int), s));   // the lo plane of a 0/1 tensor is all zero
     DISCO_CHECK_CUDA(cudaMemsetAsync(act_hi, 0, plane, s));
     if (precision == DISCO_PREC_BF16X3) DISCO_CHECK_CUDA(cudaMemsetAsync((uint16_t*)act_hi + act_lo_off, 0, plane, s));
     if (m_max > 0) {
@@ -197,12 +200,13 @@ int disco_bev_scatter_batched_launch(const int* voxel_indices, const int* counts
 }
 
 int disco_bev_pack_launch(const float* bev, long long n_pix, int z, void* out_hi, long long out_lo_off, int precision,
-                          void* stream) {
+                          int* lo_nonzero, void* stream) {
     DISCO_REQUIRE(bev && out_hi && n_pix > 0 && z > 0 && z <= 16, "bev_pack: bad arguments (z=%d)", z);
     const int threads = 256;
     const long long blocks = (n_pix + threads - 1) / threads;
+    if (lo_nonzero) DISCO_CHECK_CUDA(cudaMemsetAsync(lo_nonzero, 0, sizeof(int), (cudaStream_t)stream));
     bev_pack_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(bev, n_pix, z, (uint16_t*)out_hi, out_lo_off,
-                                                                             precision);
+                                                                             precision, lo_nonzero);
     DISCO_CHECK_CUDA(cudaGetLastError());
     return DISCO_OK;
 }

@@ -38,7 +38,7 @@ struct disco_fusion_desc {
 
 int disco_fusion_launch(const disco_fusion_desc* d, void* stream);
 int disco_bev_pack_launch(const float* bev, long long n_pix, int z, void* out_hi, long long out_lo_off, int precision,
-                          void* stream);
+                          int* lo_nonzero, void* stream);
 int disco_act_unpack_nchw_launch(const void* act_hi, long long lo_off, int precision, int n, int h, int w, int c,
                                  float* out_nchw, void* stream);
 int disco_voxelize_launch(const float* points, int n_points, int point_stride, const double* extents,
@@ -48,7 +48,7 @@ int disco_bev_scatter_launch(const int* voxel_indices, int n_voxels, const int* 
                              int act_c, int precision, void* stream);
 
 int disco_bev_scatter_batched_launch(const int* voxel_indices, const int* counts, int n, int m_max, const int* dims, void* act_hi,
-                                     long long act_lo_off, int act_c, int precision, void* stream);
+                                     long long act_lo_off, int act_c, int precision, int* lo_nonzero, void* stream);
 
 // BEV-segmentation U-Net data movement (seg.cu)
 int disco_maxpool2_launch(const void* src_hi, long long src_lo_off, void* dst_hi, long long dst_lo_off, int precision, int n,

@@ -129,7 +129,10 @@ class _DetBase(nn.Module):
 
     def _param_key(self):
         ts = list(self.parameters()) + list(self.buffers())
-        return (self.precision_name, ts[0].device, tuple(t._version for t in ts), tuple(t.data_ptr() for t in ts[:4]))
+        # `_train_epoch`: the training kernels update BatchNorm running statistics through raw pointers, which does not
+        # bump tensor._version -- every training-mode forward therefore invalidates the folded eval plans explicitly
+        return (self.precision_name, ts[0].device, tuple(t._version for t in ts), tuple(t.data_ptr() for t in ts[:4]),
+                getattr(self, "_train_epoch", 0))
 
     def _getter(self):
         sd = dict(self.named_parameters())
@@ -166,7 +169,7 @@ class _DetBase(nn.Module):
         bev = bevs.detach()
         if bev.dtype != torch.float32:
             bev = bev.float()
-        ops.bev_pack(bev.contiguous(), ws.buf["a0"], self.precision)
+        ops.bev_pack(bev.contiguous(), ws.buf["a0"], self.precision, ws.lo_nonzero)
 
     def _run_heads(self, ws: engine.Workspace, stream):
         n, h, w = ws.n, ws.h, ws.w
@@ -187,6 +190,7 @@ class _DetBase(nn.Module):
     # ---- training mode (a12) ------------------------------------------------------------------------------
     def _train_step(self, runner, bevs, trans, num_agent, outage_host, kd_keys):
         """Run the training forward through one autograd node; returns (result dict | None, [kd maps])."""
+        self._train_epoch = getattr(self, "_train_epoch", 0) + 1
         live = runner_param_names(runner)
         named = dict(self.named_parameters())
         names = tuple(k for k in named if k in live)
@@ -266,18 +270,49 @@ class DiscoNet(_DetBase):
                                   batch_size=B, agents=A, shard=(r0, A * B), fusion_level=self.layer)
             self._ws[key] = ws
         stream = torch.cuda.current_stream(dev).cuda_stream
-        trans = trans_matrices.detach().to(device=dev, dtype=torch.float64, non_blocking=True).contiguous()
-        num_agent = num_agent_tensor.detach().to(device=dev, non_blocking=True)[:, 0].to(torch.int32).contiguous()
+        if getattr(ws, "static", None) is None:
+            # static device-side arguments: the two launch runs either side of the collective replay as CUDA graphs
+            ws.static = {"trans": torch.empty((B, A, A, 4, 4), dtype=torch.float64, device=dev),
+                         "na": torch.empty((B,), dtype=torch.int32, device=dev)}
+            f = ws.fusion
+            f.trans, f.num_agent, f.weights = ws.static["trans"].data_ptr(), ws.static["na"].data_ptr(), None
+            ws.graphs, ws.calls_done = None, 0
+        ws.static["trans"].copy_(trans_matrices.detach(), non_blocking=True)
+        ws.static["na"].copy_(num_agent_tensor.detach()[:, 0], non_blocking=True)
+        ws.fusion.only_v2i = int(bool(self.only_v2i))
         self._pack_input(bevs_local, ws)
-        for c in ws.enc_calls:
-            c.launch(stream)
+
+        def run_enc(sp):
+            for c in ws.enc_calls:
+                c.launch(sp)
+
+        def run_rest(sp):
+            ws.en_call.launch(sp)
+            ops.fusion_forward(ws.fusion, sp)
+            for c in ws.dec_calls:
+                c.launch(sp)
+
+        if USE_GRAPH and ws.graphs is None and ws.calls_done >= 1 and not torch.cuda.is_current_stream_capturing():
+            try:
+                g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1):
+                    run_enc(torch.cuda.current_stream(dev).cuda_stream)
+                with torch.cuda.graph(g2):
+                    run_rest(torch.cuda.current_stream(dev).cuda_stream)
+                ws.graphs = (g1, g2, ws.fusion.only_v2i)
+            except Exception:
+                ws.graphs = False
+        use = bool(ws.graphs) and ws.graphs[2] == ws.fusion.only_v2i
+        if use:
+            ws.graphs[0].replay()
+        else:
+            run_enc(stream)
         parallel.all_gather_rows(ws.buf[ws.feat_key], ws.buf["x3g"], group)     # the path's one exchange step
-        ws.en_call.launch(stream)
-        f = ws.fusion
-        f.trans, f.num_agent, f.only_v2i, f.weights = trans.data_ptr(), num_agent.data_ptr(), int(bool(self.only_v2i)), None
-        ops.fusion_forward(f, stream)
-        for c in ws.dec_calls:
-            c.launch(stream)
+        if use:
+            ws.graphs[1].replay()
+        else:
+            run_rest(stream)
+        ws.calls_done += 1
         return self._run_heads(ws, stream)
 
     def outage(self) -> bool:
@@ -323,7 +358,7 @@ class DiscoNet(_DetBase):
             raise ValueError(f"{N} agent rows / {Z} height bins do not match agent_num*batch_size = {A}*{B}, in_channels = {self.in_channels}")
         if tuple(trans_matrices.shape) != (B, A, A, 4, 4):
             raise ValueError(f"trans_matrices must be [{B},{A},{A},4,4] (got {tuple(trans_matrices.shape)})")
-        pack = lambda ws: voxel.bev_scatter_batched(voxel_indices, counts, (X, Y, Z), ws.buf["a0"], self.precision)
+        pack = lambda ws: voxel.bev_scatter_batched(voxel_indices, counts, (X, Y, Z), ws.buf["a0"], self.precision, ws.lo_nonzero)
         return self._forward_eval(pack, N, Y, X, B, dev, trans_matrices, num_agent_tensor)
 
     def _forward_eval(self, pack_input, N, H, W, B, dev, trans_matrices, num_agent_tensor):
@@ -414,6 +449,7 @@ class DiscoNet(_DetBase):
                                            compress_level=self.compress_level)
             self._runners[key] = runner
         runner.get = self._getter()
+        runner.grad_group = getattr(self, "_grad_group", None)
         outage_host = None
         if self.p_com_outage != 0.0:
             na_host = num_agent_tensor.detach()[:, 0].tolist()
@@ -462,10 +498,10 @@ class _StpnModel(_DetBase):
                 "heads": engine.build_head_plans(get, p)}
 
     def _workspace(self, n, h, w, device):
+        P = self.plans()    # ALWAYS: compares parameter versions and drops stale workspaces (eval after an optimizer step)
         key = (n, h, w, str(device))
         ws = self._ws.get(key)
         if ws is None:
-            P = self.plans()
             ws = engine.Workspace(n, h, w, self.precision, device, P["enc"], P["dec"], P["heads"], None)
             self._ws[key] = ws
         return ws
@@ -479,6 +515,7 @@ class _StpnModel(_DetBase):
                                            compress_level=self.compress_level)
             self._runners[key] = runner
         runner.get = self._getter()
+        runner.grad_group = getattr(self, "_grad_group", None)
         return runner
 
     def _backbone(self, bevs):

@@ -46,15 +46,16 @@ def conv_forward(plan: ConvPlan, srcs: Sequence[torch.Tensor], ups: Sequence[int
     call.launch(_stream_ptr(srcs[0].device), reference=reference)
 
 
-def bev_pack(bev: torch.Tensor, out: torch.Tensor, precision: int):
-    """bev fp32 [..., Z] contiguous -> out activation buffer [parts, n, h, w, 16]."""
+def bev_pack(bev: torch.Tensor, out: torch.Tensor, precision: int, lo_nonzero: Optional[torch.Tensor] = None):
+    """bev fp32 [..., Z] contiguous -> out activation buffer [parts, n, h, w, 16].  `lo_nonzero` (int32 [1], optional)
+    receives 1 if any value needed a lo part (0/1 occupancy never does: the first conv then skips the lo plane)."""
     _require_cuda(bev, out)
     assert bev.dtype == torch.float32 and bev.is_contiguous()
     z = bev.shape[-1]
     n_pix = bev.numel() // z
     assert out.shape[-1] == 16 and out[0].numel() == n_pix * 16
     check(load().disco_bev_pack(bev.data_ptr(), n_pix, z, out.data_ptr(), _lo_off(out), precision,
-                                _stream_ptr(bev.device)), "bev_pack")
+                                lo_nonzero.data_ptr() if lo_nonzero is not None else None, _stream_ptr(bev.device)), "bev_pack")
 
 
 def act_to_nchw_f32(act: torch.Tensor, precision: int) -> torch.Tensor:
@@ -70,9 +71,9 @@ def act_to_nchw_f32(act: torch.Tensor, precision: int) -> torch.Tensor:
 class ConvCall:
     """A prebuilt conv launch (descriptor filled once; only output pointers may be re-pointed)."""
 
-    def __init__(self, plan: ConvPlan, srcs, ups, out, *, n, h_in, w_in, out_split=None):
+    def __init__(self, plan: ConvPlan, srcs, ups, out, *, n, h_in, w_in, out_split=None, lo_nonzero: Optional[torch.Tensor] = None):
         self.plan = plan
-        self.keep = (plan, list(srcs), out)   # keep tensors alive as long as the descriptor exists
+        self.keep = (plan, list(srcs), out, lo_nonzero)   # keep tensors alive as long as the descriptor exists
         d = ConvDesc()
         _require_cuda(*srcs)
         for i in range(2):
@@ -102,6 +103,7 @@ class ConvCall:
             d.chain_c_out = plan.chain["c_out"]
             d.chain_relu = int(plan.chain["relu"])
             fpp += plan.chain["flops_per_pixel"]
+        d.src_lo_nonzero = lo_nonzero.data_ptr() if lo_nonzero is not None else None
         self.desc = d
         self.flops = fpp * n * d.h_out * d.w_out
         self.set_output(out, out_split)

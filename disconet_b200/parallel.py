@@ -33,9 +33,9 @@ def row_counts(n_rows: int, world: int) -> List[int]:
 def all_gather_rows(local: torch.Tensor, out: torch.Tensor, group=None) -> torch.Tensor:
     """local [parts, n_local, ...] -> out [parts, n_total, ...], ranks concatenated along dim 1 in rank order.
 
-    One collective when every rank holds the same number of rows (all_gather_into_tensor over a
-    [world, parts, n_local, ...] staging view); padded list all_gather otherwise (works on gloo and nccl).
-    """
+    Equal row counts (the normal case: A*B divisible by the world size): one `all_gather_into_tensor` per precision part
+    straight into its final place -- out[p] is the rank-order concatenation of the ranks' local[p] -- with no staging
+    copies.  Ragged counts: padded list all_gather + slice copies (works on gloo and nccl)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     parts, n_total = out.shape[0], out.shape[1]
@@ -44,6 +44,10 @@ def all_gather_rows(local: torch.Tensor, out: torch.Tensor, group=None) -> torch
         raise ValueError(f"rank {rank} holds {local.shape[1]} rows, expected {counts[rank]}")
     nmax = max(counts)
     if nmax == 0:
+        return out
+    if min(counts) == nmax and local.is_contiguous() and out.is_contiguous():
+        for p in range(parts):
+            dist.all_gather_into_tensor(out[p], local[p], group=group)
         return out
     pad = local
     if local.shape[1] != nmax:
@@ -57,3 +61,27 @@ def all_gather_rows(local: torch.Tensor, out: torch.Tensor, group=None) -> torch
         out[:, off:off + c] = pieces[r][:, :c]
         off += c
     return out
+
+
+def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place mean over the ranks of one flat buffer (the training runner's gradient buffer: every live parameter
+    gradient of a step in ONE ~32 MB message instead of DistributedDataParallel's per-bucket copies and hooks)."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return flat
+    if flat.is_cuda:
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+    else:   # gloo has no AVG
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+    return flat
+
+
+def enable_grad_allreduce(model, group=None) -> None:
+    """Scene-sharded data-parallel training (BASELINE config 3) without DistributedDataParallel: every rank trains on its
+    own scenes and `TrainRunner.backward` averages its flat gradient buffer over `group` before handing the gradients to
+    autograd.  Call once after construction; parameters must start identical on all ranks (same checkpoint / seed).
+    BatchNorm statistics stay per rank, exactly as the reference's nn.DataParallel replicas keep them."""
+    model._grad_group = group if group is not None else dist.group.WORLD
+    for r in getattr(model, "_runners", {}).values():
+        r.grad_group = model._grad_group

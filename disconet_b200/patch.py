@@ -14,47 +14,66 @@ import runpy
 import sys
 
 
+_originals = []   # (object, attribute name, original value) of everything patch_coperception() replaced
+
+
+def _swap(obj, name, value) -> None:
+    _originals.append((obj, name, getattr(obj, name)))
+    setattr(obj, name, value)
+
+
+def unpatch_coperception() -> None:
+    """Undo patch_coperception(): put the reference's own classes / functions back (used by the tests that run the stock
+    reference and the drop-in side by side in one process)."""
+    while _originals:
+        obj, name, value = _originals.pop()
+        setattr(obj, name, value)
+
+
 def patch_coperception(classes=("DiscoNet", "FaFNet", "TeacherNet")) -> None:
     from . import det as ours
     pkg = importlib.import_module("coperception.models.det")
     for name in classes:
-        setattr(pkg, name, getattr(ours, name))
+        _swap(pkg, name, getattr(ours, name))
         sub = sys.modules.get(f"coperception.models.det.{name}")
         if sub is not None:
-            setattr(sub, name, getattr(ours, name))
+            _swap(sub, name, getattr(ours, name))
     # KD loss (FaFModule.get_kd_loss), corner loss (FaFModule.corner_loss) and the detection post-processing of
-    # predict_all (apply_nms_det -> polygon NMS) on the fused kernels
+    # predict_all (apply_nms_det -> polygon NMS) on the fused kernels.  Optional: the utils modules pull heavy third-party
+    # imports (shapely, matplotlib, nuscenes ...) that a model-only user may not have.
     try:
         mod = importlib.import_module("coperception.utils.CoDetModule")
-        from . import kd, loss as ours_loss, post
-        mod.FaFModule.get_kd_loss = kd.get_kd_loss
-        mod.FaFModule.corner_loss = ours_loss._corner_loss_method
-        mod.apply_nms_det = post.apply_nms_det          # CoDetModule does `from ...detection_util import *`
         du = importlib.import_module("coperception.utils.detection_util")
-        du.apply_nms_det = post.apply_nms_det
-        du.late_fusion = post.late_fusion
-        du.non_max_suppression = post.non_max_suppression
         pp = importlib.import_module("coperception.utils.postprocess")
-        pp.non_max_suppression = post.non_max_suppression
-    except Exception:
-        pass
+    except ImportError:
+        mod = None
+    if mod is not None:
+        from . import kd, loss as ours_loss, post
+        _swap(mod.FaFModule, "get_kd_loss", kd.get_kd_loss)
+        _swap(mod.FaFModule, "corner_loss", ours_loss._corner_loss_method)
+        _swap(mod, "apply_nms_det", post.apply_nms_det)          # CoDetModule does `from ...detection_util import *`
+        _swap(du, "apply_nms_det", post.apply_nms_det)
+        _swap(du, "late_fusion", post.late_fusion)
+        _swap(du, "non_max_suppression", post.non_max_suppression)
+        _swap(pp, "non_max_suppression", post.non_max_suppression)
     # focal classification loss (train_codet.py:173-176 builds it from coperception.utils.loss)
     try:
         lmod = importlib.import_module("coperception.utils.loss")
+    except ImportError:
+        lmod = None
+    if lmod is not None:
         from . import loss as ours_loss
-        lmod.SoftmaxFocalClassificationLoss = ours_loss.SoftmaxFocalClassificationLoss
-    except Exception:
-        pass
+        _swap(lmod, "SoftmaxFocalClassificationLoss", ours_loss.SoftmaxFocalClassificationLoss)
     # BEV segmentation (tools/seg/*.py do `from coperception.models.seg import *`)
     try:
         seg_pkg = importlib.import_module("coperception.models.seg")
     except Exception:   # the seg package pulls optional dependencies; the detection tools do not need it
         return
     from .seg import SegDiscoNet
-    setattr(seg_pkg, "DiscoNet", SegDiscoNet)
+    _swap(seg_pkg, "DiscoNet", SegDiscoNet)
     sub = sys.modules.get("coperception.models.seg.DiscoNet")
     if sub is not None:
-        setattr(sub, "DiscoNet", SegDiscoNet)
+        _swap(sub, "DiscoNet", SegDiscoNet)
 
 
 if __name__ == "__main__":

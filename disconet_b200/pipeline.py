@@ -1,36 +1,60 @@
-"""Host <-> device pipelining for the eval path: overlaps the pinned-host -> HBM copy of step i+1 and the
-logits -> pinned-host copy of step i-1 with the kernels of step i (PCIe gen5 is full duplex and the copy
-engines run beside the SMs).  The reference's eval loop (tools/det/test_codet.py:215-280) does
-`.to(device)` -> forward -> CPU post-processing strictly in sequence."""
+"""Host <-> device pipelining for the eval path: overlaps the pinned-host -> HBM copy of step i+1 and the result ->
+pinned-host copy of step i-1 with the kernels of step i (PCIe gen5 is full duplex and the copy engines run beside the
+SMs).  The reference's eval loop (tools/det/test_codet.py:215-280) does `.to(device)` -> forward -> CPU post-processing
+strictly in sequence, ships a dense fp32 BEV per agent to the device (3.4 MB) and ALL class scores + decoded boxes back
+(`apply_nms_det`, detection_util.py:276-343).
+
+Two input formats and two result formats (any combination):
+  input  "bev"        dense fp32 BEV [A*B, 1, H, W, 13], what the reference DataLoader collates (V2XSimDet.py:293-302)
+         "voxels"     the dataset's sparse sample format: padded voxel indices [A*B, M_max, 3] int32 + counts [A*B]
+                      (`voxel_indices_0`, create_data_det.py:497); the scatter + rot90 run on the device
+                      (disco_bev_scatter_batched) -> ~12 bytes per occupied voxel over PCIe instead of 3.4 MB per agent
+  output "logits"     cls [A*B, H*W*6, 2] + loc [A*B, H, W, 6, 1, 6] fp32 (63 MB per 5-agent scene)
+         "detections" what `predict_all` finally keeps (CoDetModule.py:484-511): per agent the NMS survivors -- corners
+                      [max_keep, 4, 2], score, anchor index, count -- computed on the device (post.detect: score / decode /
+                      corners -> sort -> rotated-polygon NMS), a few hundred KB per step
+"""
 from __future__ import annotations
 
-from typing import Callable, Optional
+from typing import Optional
 
 import torch
+
+from . import post
 
 
 class HostPipeline:
     """Double-buffered eval runner around a `disconet_b200.DiscoNet`.
 
-        pipe = HostPipeline(model, batch_size=B)
-        for bev_host, trans, num_agent in loader:           # pinned host tensors
-            done = pipe.submit(bev_host, trans, num_agent)    # returns the slot whose results are now on the host
+        pipe = HostPipeline(model, batch_size=B, input="voxels", output="detections", anchors=anchors)
+        for idx, counts, trans, num_agent in loader:          # pinned host tensors
+            slot = pipe.submit((idx, counts), trans, num_agent)   # results of the step that used this slot before are final
         pipe.flush()
 
-    Results of step i land in `pipe.cls_host[i % 2]`, `pipe.loc_host[i % 2]` (pinned) and are valid once
-    `pipe.d2h_done[i % 2]` has completed (`submit`/`flush` synchronise on it before reusing the slot).
+    Results of step i land in slot i % 2: `cls_host / loc_host` (logits) or `det_host` (dict of pinned tensors: n_keep [N],
+    corners [N, max_keep, 4, 2], score [N, max_keep], index [N, max_keep], n_candidates [N]) and are valid once
+    `d2h_done[slot]` has completed (`submit` / `flush` synchronise on it before the slot is reused).
     """
 
-    def __init__(self, model, batch_size: int, device: Optional[torch.device] = None):
+    def __init__(self, model, batch_size: int, device: Optional[torch.device] = None, input: str = "bev", output: str = "logits",
+                 anchors: Optional[torch.Tensor] = None, max_keep: int = 1024, max_candidates: int = 2048):
+        if input not in ("bev", "voxels") or output not in ("logits", "detections"):
+            raise ValueError("input must be 'bev' | 'voxels', output 'logits' | 'detections'")
+        if output == "detections" and anchors is None:
+            raise ValueError("output='detections' needs the anchor map [H, W, 6, 6] (obj_util.init_anchors_no_check)")
         self.model = model
         self.B = int(batch_size)
         self.device = device or next(model.parameters()).device
+        self.input, self.output = input, output
+        self.anchors = anchors.to(self.device).float().contiguous() if anchors is not None else None
+        self.max_keep, self.max_candidates = int(max_keep), int(max_candidates)
         self.compute = torch.cuda.current_stream(self.device)
         self.h2d = torch.cuda.Stream(self.device)
         self.d2h = torch.cuda.Stream(self.device)
         self.x = [None, None]
         self.cls_host = [None, None]
         self.loc_host = [None, None]
+        self.det_host = [None, None]
         self.h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
         self.comp_done = [torch.cuda.Event(), torch.cuda.Event()]
         self.d2h_done = [torch.cuda.Event(), torch.cuda.Event()]
@@ -38,35 +62,59 @@ class HostPipeline:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
+    @staticmethod
+    def _nbytes(*ts):
+        return sum(t.numel() * t.element_size() for t in ts)
+
     @torch.no_grad()
-    def submit(self, bev_host: torch.Tensor, trans: torch.Tensor, num_agent: torch.Tensor) -> int:
+    def submit(self, inp, trans: torch.Tensor, num_agent: torch.Tensor) -> int:
         s = self.step % 2
-        if self.x[s] is None:
-            self.x[s] = torch.empty(bev_host.shape, dtype=bev_host.dtype, device=self.device)
-        # slot reuse: the forward of step-2 must have consumed x[s]; its results must have left cls/loc_host[s]
+        host = (inp,) if isinstance(inp, torch.Tensor) else tuple(inp)
+        if self.x[s] is None or any(d.shape != h.shape for d, h in zip(self.x[s], host)):
+            self.x[s] = tuple(torch.empty(h.shape, dtype=h.dtype, device=self.device) for h in host)
+        # slot reuse: the forward of step-2 must have consumed x[s]; its results must have left the host buffers of slot s
         if self.step >= 2:
             self.h2d.wait_event(self.comp_done[s])
             self.d2h_done[s].synchronize()
         with torch.cuda.stream(self.h2d):
-            self.x[s].copy_(bev_host, non_blocking=True)
+            for d, h in zip(self.x[s], host):
+                d.copy_(h, non_blocking=True)
             self.h2d_done[s].record(self.h2d)
         self.compute.wait_event(self.h2d_done[s])
-        res, _ = self.model(self.x[s], trans, num_agent, batch_size=self.B)
-        self.comp_done[s].record(self.compute)
+        if self.input == "bev":
+            res, _ = self.model(self.x[s][0], trans, num_agent, batch_size=self.B)
+        else:
+            res, _ = self.model.forward_voxels(self.x[s][0], self.x[s][1], trans, num_agent, batch_size=self.B)
         cls, loc = res["cls"], res["loc"]
-        if self.cls_host[s] is None:
-            self.cls_host[s] = torch.empty(cls.shape, dtype=cls.dtype).pin_memory()
-            self.loc_host[s] = torch.empty(loc.shape, dtype=loc.dtype).pin_memory()
+        if self.output == "logits":
+            outs = {"cls": cls, "loc": loc}
+        else:
+            corners, scores, index, keep, n_keep, n_valid, count = post.detect(loc, cls, self.anchors, device_only=True,
+                                                                               max_candidates=self.max_candidates)
+            n, cap = scores.shape
+            kk = keep[:, :self.max_keep].clamp(0, cap - 1).long()      # entries past n_keep are don't-cares
+            outs = {"n_keep": n_keep, "n_candidates": count,
+                    "corners": torch.gather(corners.view(n, cap, 8), 1, kk.unsqueeze(-1).expand(-1, -1, 8)).view(n, -1, 4, 2),
+                    "score": torch.gather(scores, 1, kk), "index": torch.gather(index, 1, kk)}
+        self.comp_done[s].record(self.compute)
+        if self.output == "logits":
+            if self.cls_host[s] is None:
+                self.cls_host[s] = torch.empty(cls.shape, dtype=cls.dtype).pin_memory()
+                self.loc_host[s] = torch.empty(loc.shape, dtype=loc.dtype).pin_memory()
+            dst = {"cls": self.cls_host[s], "loc": self.loc_host[s]}
+        else:
+            if self.det_host[s] is None:
+                self.det_host[s] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in outs.items()}
+            dst = self.det_host[s]
         self.d2h.wait_event(self.comp_done[s])
         with torch.cuda.stream(self.d2h):
-            self.cls_host[s].copy_(cls, non_blocking=True)
-            self.loc_host[s].copy_(loc, non_blocking=True)
+            for k, v in outs.items():
+                dst[k].copy_(v, non_blocking=True)
             self.d2h_done[s].record(self.d2h)
-        cls.record_stream(self.d2h)
-        loc.record_stream(self.d2h)
-        self.h2d_bytes = bev_host.numel() * bev_host.element_size() + trans.numel() * trans.element_size() + \
-            num_agent.numel() * num_agent.element_size()
-        self.d2h_bytes = cls.numel() * 4 + loc.numel() * 4
+        for v in outs.values():
+            v.record_stream(self.d2h)
+        self.h2d_bytes = self._nbytes(*host, trans, num_agent)
+        self.d2h_bytes = self._nbytes(*outs.values())
         self.step += 1
         return s
 

@@ -99,7 +99,8 @@ class SegDiscoNet(nn.Module):
 
     def plans(self):
         ts = list(self.parameters()) + list(self.buffers())
-        key = (self.precision_name, ts[0].device, tuple(t._version for t in ts), tuple(t.data_ptr() for t in ts[:4]))
+        key = (self.precision_name, ts[0].device, tuple(t._version for t in ts), tuple(t.data_ptr() for t in ts[:4]),
+               getattr(self, "_train_epoch", 0))   # training kernels write BN running stats through raw pointers
         if self._plans is None or key != self._plans_key:
             with torch.no_grad():
                 self._plans = build_seg_plans(self._getter(), self.precision, self.n_channels, self.n_classes)
@@ -166,6 +167,7 @@ class SegDiscoNet(nn.Module):
         named = dict(self.named_parameters())
         names = tuple(k for k in named if k in live)
         bev = x.detach().permute(0, 2, 3, 1).unsqueeze(1)          # [N, 1, H, W, 13], the layout the pack kernel reads
+        self._train_epoch = getattr(self, "_train_epoch", 0) + 1
         outs = list(_TrainFn.apply(runner, bev, trans_matrices, num_agent_tensor, None, tuple(kd_keys), names,
                                    *[named[k] for k in names]))
         return (outs[0], *outs[1:]) if self.kd_flag else outs[0]

@@ -62,3 +62,22 @@ def synth_bev(N, H=256, W=256, Z=13, occupancy=0.03, seed=0):
     import numpy as np
     rng = np.random.default_rng(seed)
     return torch.from_numpy((rng.random((N, 1, H, W, Z)) < occupancy).astype(np.float32))
+
+
+# binary detection config of the reference (configs/Config.py:154-163): (w, l, yaw) of the 6 anchors per BEV cell
+ANCHOR_SIZE = ((2.0, 4.0, 0.0), (2.0, 4.0, 1.5707963267948966), (2.0, 4.0, -0.7853981633974483),
+               (3.0, 12.0, 0.0), (3.0, 12.0, 1.5707963267948966), (3.0, 12.0, -0.7853981633974483))
+
+
+def synth_anchors(H=256, W=256, extent=32.0, voxel=0.25, anchor_size=ANCHOR_SIZE):
+    """Anchor map [H, W, A, 6] float32 = (x, y, w, h, sin, cos) laid out like obj_util.init_anchors_no_check (:611-633):
+    cell (i, j) is centred at (j*voxel - extent + voxel/2, i*voxel - extent + voxel/2)."""
+    import numpy as np
+    a = np.asarray(anchor_size, dtype=np.float64)
+    m = np.zeros((H, W, len(a), 6))
+    m[..., 2:4] = a[:, :2]
+    m[..., 4] = np.sin(a[:, 2])
+    m[..., 5] = np.cos(a[:, 2])
+    m[..., 0] = (np.arange(W) * voxel - extent + voxel / 2.0)[None, :, None]
+    m[..., 1] = (np.arange(H) * voxel - extent + voxel / 2.0)[:, None, None]
+    return torch.from_numpy(m.astype(np.float32))

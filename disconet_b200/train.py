@@ -741,13 +741,28 @@ class TrainRunner:
         self._run("bwd", self.bwd_ops, stream)
         self._steps += 1
         self._bwd_keep = keep
-        return self._collect(self.G.clone())
+        G = self.G.clone()
+        if getattr(self, "grad_group", None) is not None:
+            from . import parallel
+            self.last_local_grad = G.clone() if getattr(self, "keep_local_grad", False) else None
+            parallel.allreduce_mean_(G, self.grad_group)     # scene-sharded data parallelism: ONE flat all-reduce per step
+        return self._collect(G)
 
     def _collect(self, G: torch.Tensor) -> Dict[str, torch.Tensor]:
         """Views of the (cloned) flat gradient buffer under the reference's parameter names."""
         out: Dict[str, torch.Tensor] = {}
         v = lambda name: self._gview(G, name)
-        zero = v("_zero")
+
+        class _Zeros:   # DISJOINT zero slices, one per bias (AccumulateGrad may steal the tensor: no two .grad may alias)
+            def __init__(self_):
+                self_.buf, self_.pos = torch.zeros(16384, dtype=G.dtype, device=G.device), 0
+
+            def __getitem__(self_, sl):
+                a = self_.pos
+                self_.pos += sl.stop
+                assert self_.pos <= self_.buf.numel()
+                return self_.buf[a:self_.pos]
+        zero = _Zeros()
         for L in self.enc + self.dec:
             if L.kind != "conv":
                 continue

@@ -81,7 +81,8 @@ def bev_scatter(voxel_indices: torch.Tensor, dims, *, packed: bool = False, prec
     return (bev, act) if packed else bev
 
 
-def bev_scatter_batched(voxel_indices: torch.Tensor, counts: torch.Tensor, dims, act: torch.Tensor, precision: int = PREC_BF16X3):
+def bev_scatter_batched(voxel_indices: torch.Tensor, counts: torch.Tensor, dims, act: torch.Tensor, precision: int = PREC_BF16X3,
+                        lo_nonzero: Optional[torch.Tensor] = None):
     """Dataset scatter of a whole batch (V2XSimDet.py:293-302 per agent) straight into the encoder's input activation:
     voxel_indices [N, M_max, 3] int32 (x, y, z), counts [N] int32 -> act [parts, N, Y, X, 16] (zeroed, then act[a, y, X-1-x, z] = 1)."""
     _require_cuda(voxel_indices, counts, act)
@@ -95,7 +96,8 @@ def bev_scatter_batched(voxel_indices: torch.Tensor, counts: torch.Tensor, dims,
     cd = (C.c_int * 3)(dx, dy, dz)
     lo_off = act.stride(0) if act.shape[0] == 2 else 0
     check(load().disco_bev_scatter_batched(voxel_indices.data_ptr(), counts.data_ptr(), n, m_max, cd, act.data_ptr(), lo_off, 16,
-                                           precision, _stream_ptr(act.device)), "bev_scatter_batched")
+                                           precision, lo_nonzero.data_ptr() if lo_nonzero is not None else None,
+                                           _stream_ptr(act.device)), "bev_scatter_batched")
     return act
 
 

@@ -69,6 +69,9 @@ typedef struct disco_conv_desc {
     const float* chain_bias; /* [chain_block_n]                                                          */
     int chain_c_out;         /* 0 = no chain                                                             */
     int chain_relu;
+    /* optional device flag (int): when it reads 0 every lo element of the sources is zero (exact 0/1 occupancy input written by
+     * disco_bev_pack / disco_bev_scatter_batched), so the kernel skips the lo-plane loads and the A_lo*W_hi pass; NULL = use lo */
+    const int* src_lo_nonzero;
 } disco_conv_desc;
 
 int disco_conv_forward(const disco_conv_desc* d /* host */, void* stream);
@@ -78,9 +81,11 @@ int disco_conv_reference(const disco_conv_desc* d /* host */, void* stream);
 int disco_conv_smem_bytes(const disco_conv_desc* d /* host */);
 
 /* Dense BEV fp32 [n_pix, z] (the DataLoader's padded_voxel_points, V2XSimDet.py:293-302, in the layout
- * DiscoNet.forward receives it, DiscoNet.py:42) -> 16-channel NHWC activation buffer (z <= 16). */
+ * DiscoNet.forward receives it, DiscoNet.py:42) -> 16-channel NHWC activation buffer (z <= 16).
+ * lo_nonzero (optional device int): set to 0, then to 1 if any element needs a non-zero lo part (i.e. is not exactly
+ * representable in bf16; 0/1 occupancy is) -- feeds disco_conv_desc.src_lo_nonzero of the first conv. */
 int disco_bev_pack(const float* bev, long long n_pix, int z, void* out_hi, long long out_lo_off, int precision,
-                   void* stream);
+                   int* lo_nonzero, void* stream);
 
 /* NHWC activation buffer -> fp32 NCHW (layout of the tensors DiscoNet.forward returns when kd_flag == 1). */
 int disco_act_unpack_nchw(const void* act_hi, long long lo_off, int precision, int n, int h, int w, int c,
@@ -105,7 +110,8 @@ int disco_bev_scatter(const int* voxel_indices, int n_voxels, const int* dims /*
  * V2XSimDet.py:293-302 and its 3.4 MB/agent host->device copy): voxel_indices [n, m_max, 3] int32 (device), counts [n]
  * (device; rows >= counts[a] ignored), act = activation buffer [parts, n, Y, X, act_c] (zeroed by the call). */
 int disco_bev_scatter_batched(const int* voxel_indices, const int* counts, int n, int m_max, const int* dims /* host */,
-                              void* act_hi, long long act_lo_off, int act_c, int precision, void* stream);
+                              void* act_hi, long long act_lo_off, int act_c, int precision, int* lo_nonzero /* optional: set to 0 */,
+                              void* stream);
 
 /* DiscoGraph fusion block: per-ego affine warp of every neighbour map (DetModelBase.py:139-209),
  * PixelWeightedFusionSoftmax tail (DiscoNet.py:150-153), agent-axis softmax and weighted sum

@@ -25,6 +25,9 @@ DISCO_CASES = {
     "disco_a3_b2_absent": dict(A=3, B=2, num_agent=[3, 2], kd_flag=0, only_v2i=False, compress_level=0, seed=12),
     "disco_a3_b1_v2i_comp": dict(A=3, B=1, num_agent=[3], kd_flag=1, only_v2i=True, compress_level=2, seed=13),
     "disco_a2_b1_layer2": dict(A=2, B=1, num_agent=[2], kd_flag=1, only_v2i=False, compress_level=0, seed=14, layer=2),
+    # the headline shape (BASELINE configs[1]: 5 agents) from the live reference: one scene, and two scenes with an absent agent
+    "disco_a5_b1": dict(A=5, B=1, num_agent=[5], kd_flag=0, only_v2i=False, compress_level=0, seed=15),
+    "disco_a5_b2": dict(A=5, B=2, num_agent=[5, 4], kd_flag=1, only_v2i=False, compress_level=0, seed=16),
 }
 
 
@@ -85,12 +88,19 @@ def _sub(t: torch.Tensor, stride: int):
     return f[::stride].float().numpy(), np.array([f.sum().item(), f.abs().sum().item(), f.abs().max().item()])
 
 
-def main():
+def main(only=None):
+    """`only`: iterable of DISCO_CASES names -> (re)generate just those eval fixtures (python -m oracle.make_golden name ...)."""
     os.makedirs(OUT, exist_ok=True)
     RDisco, RFaF, RTeach, Config = ref_import.reference_classes()
     cfg = Config("train", binary=True, only_det=True)
     keys = {}
+    kpath = os.path.join(OUT, "state_dict_keys.json")
+    if only and os.path.exists(kpath):
+        with open(kpath) as f:
+            keys = json.load(f)
     for name, case in DISCO_CASES.items():
+        if only and name not in only:
+            continue
         m = RDisco(cfg, layer=case.get("layer", 3), kd_flag=case["kd_flag"], num_agent=case["A"], compress_level=case["compress_level"],
                    only_v2i=case["only_v2i"]).eval()
         keys[name] = [[k, list(v.shape)] for k, v in m.state_dict().items()]
@@ -112,6 +122,10 @@ def main():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
         print(name, {k: v.shape for k, v in rec.items()})
 
+    if only:
+        with open(kpath, "w") as f:
+            json.dump(keys, f)
+        return
     for name, case in TRAIN_CASES.items():
         m = RDisco(cfg, layer=3, kd_flag=1, num_agent=case["A"], compress_level=0, only_v2i=case["only_v2i"]).train()
         keys[name] = [[k, list(v.shape)] for k, v in m.state_dict().items()]
@@ -220,4 +234,5 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+    main(only=sys.argv[1:] or None)

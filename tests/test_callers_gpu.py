@@ -103,11 +103,8 @@ def test_unmodified_fafmodule_step_on_b200(cuda_dev):
         got = fm2.step(d2, B, A)
         torch.cuda.synchronize()
     finally:
-        det.DiscoNet, det.TeacherNet = RefDisco, RefTeacher
-        sys.modules["coperception.models.det.DiscoNet"].DiscoNet = RefDisco
-        sys.modules["coperception.models.det.TeacherNet"].TeacherNet = RefTeacher
-        loss_mod.SoftmaxFocalClassificationLoss = RefFocal
-        mod.FaFModule.corner_loss, mod.FaFModule.get_kd_loss = ref_corner, ref_kd
+        patch.unpatch_coperception()
+        assert det.DiscoNet is RefDisco and mod.FaFModule.corner_loss is ref_corner and mod.FaFModule.get_kd_loss is ref_kd
     print("FaFModule.step  reference (CPU):", want, " drop-in (B200):", got)
     for w_, g_ in zip(want, got):            # loss, loss_cls, loss_loc
         assert abs(w_ - g_) <= 2e-3 * abs(w_), (want, got)
@@ -160,12 +157,9 @@ def test_unmodified_predict_all_on_b200(cuda_dev):
             got = fm2.predict_all(_to(data, cuda_dev), B, num_agent=A)      # trans_matrices on the device (test_codet.py:266)
         torch.cuda.synchronize()
     finally:
-        det.DiscoNet, det.TeacherNet = RefDisco, RefTeacher
-        sys.modules["coperception.models.det.DiscoNet"].DiscoNet = RefDisco
-        sys.modules["coperception.models.det.TeacherNet"].TeacherNet = RefTeacher
-        loss_mod.SoftmaxFocalClassificationLoss = RefFocal
-        (mod.FaFModule.corner_loss, mod.FaFModule.get_kd_loss, mod.apply_nms_det, du.apply_nms_det, du.late_fusion,
-         du.non_max_suppression, pp.non_max_suppression) = saved
+        patch.unpatch_coperception()
+        assert (mod.FaFModule.corner_loss, mod.FaFModule.get_kd_loss, mod.apply_nms_det, du.apply_nms_det, du.late_fusion,
+                du.non_max_suppression, pp.non_max_suppression) == saved and det.DiscoNet is RefDisco
     # (loss, loss_cls, loss_loc, seq_results, save_agent_weight_list)
     print("predict_all losses  reference (CPU):", want[:3], " drop-in (B200):", got[:3])
     for w_, g_ in zip(want[:3], got[:3]):

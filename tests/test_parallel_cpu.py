@@ -47,6 +47,10 @@ def _worker(rank, world, port, n_total, q):
             rejected = False
         except ValueError:
             rejected = True
+        # flat gradient all-reduce of the scene-sharded training path: mean over ranks, in place
+        flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+        parallel.allreduce_mean_(flat, None)
+        ok = ok and torch.allclose(flat, torch.arange(1000, dtype=torch.float32) * (sum(range(1, world + 1)) / world))
         q.put((rank, ok, rejected))
     finally:
         dist.destroy_process_group()
