@@ -262,6 +262,8 @@ def train_leg(dev, dist, world, steps: int, warmup: int, scenes: int = 4):
         "loss": float(loss.detach()), "wall_ms_per_step_plus_extra_teacher_pass": wall / steps,
         "data_parallel": ("one flat NCCL all-reduce (mean) of the %.1f MB gradient buffer per step" % (next(iter(m._runners.values())).G.numel() * 4 / 1e6)) if dist else None,
         "parity": parity,
+        "cuda_graphs": {k: bool(v) for k, v in next(iter(m._runners.values()))._graphs.items()},
+        "cuda_graph_error": getattr(next(iter(m._runners.values())), "graph_error", None),
     }
 
 

@@ -36,6 +36,7 @@ class ConvDesc(C.Structure):
         ("out_split", C.c_int),
         ("chain_wpack", C.c_void_p), ("chain_bias", C.c_void_p), ("chain_c_out", C.c_int), ("chain_relu", C.c_int),
         ("src_lo_nonzero", C.c_void_p),
+        ("subpix", C.c_int), ("sub_py", C.c_int), ("sub_px", C.c_int),
     ]
 
 

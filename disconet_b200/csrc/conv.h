@@ -51,6 +51,12 @@ struct disco_conv_desc {
     /* optional device flag (int): when it reads 0 every lo element of the sources is zero (exact 0/1 occupancy input written by
      * disco_bev_pack / disco_bev_scatter_batched), so the kernel skips the lo-plane loads and the A_lo*W_hi pass; NULL = use lo */
     const int* src_lo_nonzero;
+    /* output-parity ("sub-pixel") class of conv(cat(nearest_up2(src[0]), src[1])): subpix = 1 computes ONLY the output pixels
+     * (2a + sub_py, 2b + sub_px); wpack then holds, per 16-channel block, the 4 pre-summed taps of that class for source 0
+     * (ascending tap index inside the 3x3 window: rows sub_py..sub_py+1, columns sub_px..sub_px+1) and all 9 taps for source 1
+     * (see disconet_b200/plan.py::pack_conv_subpix).  Needs taps 9, stride 1, src_up = {1, 0}, c_blk 16, bf16x3.  Four launches
+     * (one per class) replace one launch with src_up[0] = 1 and execute 4/9 of its source-0 MMAs. */
+    int subpix, sub_py, sub_px;
 };
 
 int disco_conv_tc_launch(const disco_conv_desc* d, void* stream);

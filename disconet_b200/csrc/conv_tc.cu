@@ -177,6 +177,8 @@ struct alignas(64) ConvGeom {
     int tiles_h, tiles_w;
     int m_tiles, n_tiles, items;
     FastDiv fd_m_tiles, fd_per_img, fd_tiles_w;
+    int w_iters;              // weight blocks per N tile (= K stages x taps; sub-pixel mode: 4 per source-0 stage, 9 per source-1 stage)
+    int plane0, a_part0;      // sub-pixel mode: chunk / part strides of a SOURCE-0 stage (18 x 10 low-res patch)
     long long total_pix;      // n*h_out*w_out
     int tmem_cols;
     int smem_bytes;
@@ -218,6 +220,14 @@ struct Item {
     long long p0;
 };
 
+// output pixel of tile row m (0..127) of sub-tile `sub`
+template <int MODE>
+__device__ __forceinline__ void out_coords(const ConvGeom& g, const Item& it, int sub, int m, int& oh, int& ow) {
+    oh = it.h0 + (m >> 3);
+    ow = it.w0 + sub * 8 + (m & 7);
+    if (MODE == 3) { oh = 2 * oh + g.d.sub_py; ow = 2 * ow + g.d.sub_px; }
+}
+
 template <int MODE>
 __device__ __forceinline__ Item decode_item(const ConvGeom& g, int item) {
     Item it;
@@ -238,6 +248,10 @@ __device__ __forceinline__ Item decode_item(const ConvGeom& g, int item) {
 }
 
 // MODE 0: 3x3 stride 1 (patch 18x10) | MODE 1: 3x3 stride 2 (patch 33x17) | MODE 2: 1x1
+// MODE 3: one output-parity class (sub_py, sub_px) of a 3x3 conv over cat(nearest_up2(src0), src1) ("sub-pixel" decomposition):
+//         tiles of 16 x 8 class pixels (output (2a + py, 2b + px)); source 0 is read at its native half resolution as an
+//         18 x 10 patch with only the 2 x 2 taps the class touches (weights pre-summed on the host), source 1 exactly like a
+//         stride-2 conv whose input origin is shifted by (py, px)
 template <int MODE, int KSTEPS, int PASSES>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvGeom g) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -255,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int warp = tid >> 5;
     const int lane = tid & 31;
     const disco_conv_desc& d = g.d;
-    constexpr int PW = (MODE == 0) ? 10 : (MODE == 1) ? 17 : 128;
+    constexpr int PW = (MODE == 0 || MODE == 3) ? 10 : (MODE == 1) ? 17 : 128;
     constexpr int TAPS = (MODE == 2) ? 1 : 9;
     constexpr int STRIDE = (MODE == 1) ? 2 : 1;
     constexpr bool SPLIT = PASSES != 1;     // bf16 hi+lo operands
@@ -324,7 +338,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 bool valid;
                 long long pixel;
                 if (MODE != 2) {
-                    const int oh = it.h0 + (m >> 3), ow = it.w0 + sub * 8 + (m & 7);
+                    int oh, ow;
+                    out_coords<MODE>(g, it, sub, m, oh, ow);
                     valid = (oh < d.h_out) && (ow < d.w_out);
                     pixel = ((long long)it.img * d.h_out + oh) * d.w_out + ow;
                 } else {
@@ -407,7 +422,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                                 bool ok;
                                 long long pix2;
                                 if (MODE != 2) {
-                                    const int oh = it.h0 + (m2 >> 3), ow = it.w0 + sub * 8 + (m2 & 7);
+                                    int oh, ow;
+                                    out_coords<MODE>(g, it, sub, m2, oh, ow);
                                     ok = (oh < d.h_out) && (ow < d.w_out);
                                     pix2 = ((long long)it.img * d.h_out + oh) * d.w_out + ow;
                                 } else {
@@ -447,7 +463,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 mbar_wait(smem_u32(&ctl->acc2_full[egrp]), (uint32_t)(iacc >> 1) & 1u);
                 tc_fence_after();
                 const int mrow = (warp & 3) * 32 + lane;
-                const int oh = it.h0 + (mrow >> 3), ow = it.w0 + (mrow & 7);
+                int oh, ow;
+                out_coords<MODE>(g, it, 0, mrow, oh, ow);
                 const bool ok = (MODE != 2) ? ((oh < d.h_out) && (ow < d.w_out)) : (it.p0 + mrow < g.total_pix);
                 const long long px = (MODE != 2) ? ((long long)it.img * d.h_out + oh) * d.w_out + ow : it.p0 + mrow;
                 const uint32_t t2 = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) +
@@ -518,6 +535,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 const uint32_t stage = a_base + sa * g.a_stage_bytes;
                 const int cofs = cbl * d.c_blk;
                 const int hi0 = it.h0 * STRIDE - 1, wi0 = (it.w0 + sub * 8) * STRIDE - 1;
+                if (MODE == 3) {
+                    // ---- sub-pixel class: source 0 at native half resolution (18 x 10 box), source 1 as the two stride-2
+                    //      column-parity planes of a 33 x 17 window whose origin is shifted by (py, px) ----
+                    if (lane == 0) {
+                        const uint32_t bar = smem_u32(&ctl->a_full[sa]);
+                        const int a0 = it.h0, b0 = it.w0 + sub * 8;
+                        if (sidx == 0) {
+                            mbar_arrive_expect_tx(bar, (uint32_t)(a_parts * g.chunks) * 2880u);
+                            for (int part = 0; part < a_parts; ++part)
+                                for (int chunk = 0; chunk < g.chunks; ++chunk)
+                                    tma_load_4d(stage + (uint32_t)part * g.a_part0 + (uint32_t)chunk * g.plane0, &g.tmap[part],
+                                                cofs + chunk * 8, b0 - 1, a0 - 1, it.img, bar);
+                        } else {
+                            mbar_arrive_expect_tx(bar, (uint32_t)(a_parts * g.chunks) * 9504u);
+                            const int hs = 2 * a0 - 1 + d.sub_py, wsx = 2 * b0 - 1 + d.sub_px;
+                            for (int part = 0; part < a_parts; ++part)
+                                for (int chunk = 0; chunk < g.chunks; ++chunk) {
+                                    const uint32_t dst = stage + (uint32_t)part * g.a_part_bytes + (uint32_t)chunk * g.plane;
+                                    tma_load_4d(dst, &g.tmap[2 + part], cofs + chunk * 8, wsx, hs, it.img, bar);
+                                    tma_load_4d(dst + g.parplane, &g.tmap[2 + part], cofs + chunk * 8, wsx + 1, hs, it.img, bar);
+                                }
+                        }
+                    }
+                    __syncwarp();
+                    continue;
+                }
                 if (g.use_tma && upm == 0) {
                     // ---- TMA: one box per (chunk, part); out-of-image pixels arrive as zeros (= the conv padding) ----
                     if (lane == 0) {
@@ -570,7 +613,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     if (lane == 0) mbar_arrive(smem_u32(&ctl->a_full[sa]));
                     continue;
                 }
-                if (MODE != 2) {
+                if (MODE != 2 && MODE != 3) {
                     // Row-wise gather: the (column, chunk) a lane handles is the same for every patch row, so
                     // its shared/global offsets are computed once per stage and each row only adds its base.
                     constexpr int PH = (MODE == 0) ? 18 : 33;
@@ -609,7 +652,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                             if (SPLIT) cp_async16(drow + soff[j] + g.a_part_bytes, valid ? gp + lo_off : src, valid ? 16u : 0u);
                         }
                     }
-                } else {
+                } else if (MODE == 2) {
                     const long long pbase = it.p0 + sub * 128;
                     for (int e = lane; e < per_part; e += 32) {
                         const int chunk = e & (g.chunks - 1);
@@ -634,7 +677,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     } else if (warp == kWarpB) {
         // =========================== B loader (bulk copy engine) ===================================
         if (lane == 0) {
-            const int iters_per_tile = g.ncb * TAPS;
+            const int iters_per_tile = g.w_iters;
             if (g.chain) {
                 const uint32_t bar2 = smem_u32(&ctl->w2_full);
                 mbar_arrive_expect_tx(bar2, (uint32_t)g.w2_bytes);
@@ -731,6 +774,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 b_ks[ks] = (uint32_t)(2 * ks) * lbo_b16;
             }
             const uint32_t par16 = (uint32_t)g.parplane >> 4;
+            // sub-pixel mode: the 2 x 2 low-res taps (of the 3 x 3 window) class (py, px) touches -- rows {py, py+1} x cols {px, px+1}
+            const uint32_t sub_mask0 = (MODE == 3) ? ((3u << d.sub_px) | ((3u << d.sub_px) << 3)) << (3 * d.sub_py) : 0u;
+            (void)sub_mask0;
             const int mw = warp - kWarpMma;              // issuing warp index; owns items with iacc % nmma == mw
             int iacc = 0;
             int sb_slot = 0;                             // B ring position (streamed weights: single issuer)
@@ -751,6 +797,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                      acc_par ^= (buf == 0), turn = (turn + 1 == g.nmma) ? 0 : turn + 1) {
                 if (mw >= g.nmma || (!g.by_sub && turn != mw)) continue;
                 if (mw == 0) TRACE(2, iacc, 0);
+                uint32_t wblk = 0;   // sub-pixel mode, resident weights: running weight-block index inside the N tile
+                (void)wblk;
                 mbar_wait(smem_u32(&ctl->acc_empty[buf]), acc_par ^ 1u);
                 tc_fence_after();
                 if (mw == 0) TRACE(2, iacc, 1);
@@ -774,7 +822,58 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     tc_fence_after();
                     if (cb == 0 && mw == 0) TRACE(2, iacc, 2);
                     const uint32_t first = (cb > 0) ? 1u : 0u;   // accumulate flag of the first MMA of the item
-                    if (g.stationary) {
+                    if (MODE == 3) {
+                        // ---- sub-pixel class: 4 pre-summed taps on a source-0 stage (18 x 10 low-res patch), all 9 taps on a
+                        //      source-1 stage (stride-2 parity planes); weight blocks are consumed in packed order ----
+                        const bool s1 = cb >= g.ncb0;
+                        const uint32_t ahi = s1 ? a_hi : ((160u >> 4) | (1u << 14));
+                        const uint32_t lbo16 = s1 ? a_lo_c : (((uint32_t)g.plane0 >> 4) << 16);
+                        const uint32_t part16 = s1 ? a_part16 : ((uint32_t)g.a_part0 >> 4);
+                        const uint32_t sa0 = (a_base >> 4) + (uint32_t)slot0 * a_stage16 + lbo16;
+                        const uint32_t sa1 = (a_base >> 4) + (uint32_t)slot1 * a_stage16 + lbo16;
+                        const uint32_t mask = s1 ? 0x1FFu : sub_mask0;
+                        uint32_t acc = first;
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            if (!((mask >> tap) & 1u)) continue;
+                            uint32_t b16;
+                            if (g.stationary) {
+                                b16 = b_base16 + wblk * b_stage16;
+                            } else {
+                                mbar_wait(bar_b_full + 8u * sb_slot, sb_phase);
+                                tc_fence_after();
+                                b16 = b_base16 + (uint32_t)sb_slot * b_stage16;
+                            }
+                            const int kh = tap / 3, kw = tap - kh * 3;
+                            const uint32_t toff = s1 ? ((uint32_t)(kw & 1) * par16 + (uint32_t)(kh * 9 + (kw >> 1))) : (uint32_t)(kh * 10 + kw);
+                            if (elect_one()) {
+#pragma unroll
+                                for (int sub = 0; sub < 2; ++sub) {
+                                    if (sub >= sub_lo && sub < sub_hi) {
+                                        const uint32_t td = sub ? td1 : td0;
+                                        const uint32_t a16 = (sub ? sa1 : sa0) + toff;
+                                        if (STACKED) {
+                                            umma_f16_parts(td, a16, ahi, b16, b_hi, idesc2, acc);
+                                            if (!skip_lo) umma_f16_parts(td, a16 + part16, ahi, b16, b_hi, idesc, 1u);
+                                        } else {
+                                            umma_f16_parts(td, a16, ahi, b16, b_hi, idesc, acc);
+                                            if (SPLIT) {
+                                                if (!skip_lo) umma_f16_parts(td, a16 + part16, ahi, b16, b_hi, idesc, 1u);
+                                                umma_f16_parts(td, a16, ahi, b16 + b_part16, b_hi, idesc, 1u);
+                                            }
+                                        }
+                                    }
+                                }
+                                if (!g.stationary) umma_commit(bar_b_empty + 8u * sb_slot);
+                            }
+                            __syncwarp();
+                            acc = 1u;
+                            ++wblk;
+                            if (!g.stationary) {
+                                if (++sb_slot == g.SB) { sb_slot = 0; sb_phase ^= 1u; }
+                            }
+                        }
+                    } else if (g.stationary) {
                         // Resident weights: nothing to wait for between taps, so ONE elected region issues the whole channel
                         // block as a branch-free run of tcgen05.mma with descriptor = base + precomputed offset (round-2 ncu
                         // source view: the per-tap ring / elect / constant-bank code of the generic loop below cost ~45 scalar
@@ -889,6 +988,11 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
                   "conv: stacked weight images need bf16x3 and block_n <= 128");
     DISCO_REQUIRE(d->taps == 9 || (d->src_up[0] == 0 && d->src_up[1] == 0), "conv: 1x1 cannot upsample");
     DISCO_REQUIRE(d->n > 0 && d->h_in > 0 && d->w_in > 0, "conv: empty input");
+    if (d->subpix)
+        DISCO_REQUIRE(d->taps == 9 && d->stride == 1 && d->src_up[0] == 1 && d->src_up[1] == 0 && d->src_c[1] > 0 && d->c_blk == 16 &&
+                          d->precision == DISCO_PREC_BF16X3 && d->chain_c_out == 0 && (d->sub_py | d->sub_px) >= 0 && d->sub_py <= 1 &&
+                          d->sub_px <= 1 && d->h_in % 2 == 0 && d->w_in % 2 == 0 && get_encode_tiled() != nullptr,
+                      "conv: sub-pixel class needs a 3x3 stride-1 conv over (upsampled, plain) sources, c_blk 16, bf16x3 and TMA");
     DISCO_REQUIRE(((d->c_out + d->block_n - 1) / d->block_n) * d->block_n * 4 <= kBiasBytes, "conv: c_out %d too large", d->c_out);
     if (d->taps == 9) {
         DISCO_REQUIRE(d->h_out == (d->h_in - 1) / d->stride + 1 && d->w_out == (d->w_in - 1) / d->stride + 1,
@@ -924,8 +1028,11 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     g->chunk_shift = (g->chunks == 2) ? 1 : (g->chunks == 4) ? 2 : 3;
     g->nparts = (d->precision == DISCO_PREC_BF16X3) ? 2 : 1;
     g->total_pix = (long long)d->n * d->h_out * d->w_out;
+    g->plane0 = 0; g->a_part0 = 0;
     if (d->taps == 1) {
         g->PIX = 128; g->parplane = 0; g->sbo_a = 128;
+    } else if (d->subpix) {
+        g->PIX = 33 * 17; g->parplane = 33 * 9 * 16; g->sbo_a = 2 * 9 * 16;   // source-1 stages: stride-2 geometry
     } else if (d->stride == 1) {
         g->PIX = 180; g->parplane = 0; g->sbo_a = 160;
     } else {
@@ -941,8 +1048,14 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
         const bool up_in_s2 = d->stride == 2 && (d->src_up[0] == 1 || (d->src_c[1] && d->src_up[1] == 1));
         if (!no_tma && any_plain && !up_in_s2 && g->total_pix < (1ll << 31) && get_encode_tiled()) g->use_tma = 1;
     }
-    int plane = (d->taps == 9 && d->stride == 2) ? 2 * g->parplane : g->PIX * 16;
-    if (g->use_tma) {
+    int plane = (d->taps == 9 && (d->stride == 2 || d->subpix)) ? 2 * g->parplane : g->PIX * 16;
+    if (d->subpix) {
+        g->use_tma = 1;
+        g->parplane = (g->parplane + 127) / 128 * 128;
+        plane = 2 * g->parplane;
+        g->plane0 = (18 * 10 * 16 + 127) / 128 * 128;
+        g->a_part0 = g->chunks * g->plane0;
+    } else if (g->use_tma) {
         // TMA destinations are 128-byte aligned: round the per-chunk planes up (the async proxy has no bank conflicts to dodge)
         if (d->taps == 9 && d->stride == 2) { g->parplane = (g->parplane + 127) / 128 * 128; plane = 2 * g->parplane; }
         else plane = (plane + 127) / 128 * 128;
@@ -964,10 +1077,12 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
 
     const int stage_region = d->chain_c_out > 0 ? 0 : kStageBytes;
     const int budget = 224 * 1024 - kCtlBytes - kBiasBytes - stage_region - g->scratch_total;
-    g->w_bytes = g->ncb * d->taps * g->b_stage_bytes;
+    g->w_iters = d->subpix ? g->ncb0 * 4 + (g->ncb - g->ncb0) * 9 : g->ncb * d->taps;
+    g->w_bytes = g->w_iters * g->b_stage_bytes;
     // MSUB = 2 (256-pixel items) when the N tile leaves room for double-buffered accumulators and the
     // image is wide enough; it halves the weight stream per MAC.
-    const bool wide = (d->taps == 1) ? (g->total_pix >= 256) : (d->w_out >= 16);
+    const int h_grid = d->subpix ? d->h_out / 2 : d->h_out, w_grid = d->subpix ? d->w_out / 2 : d->w_out;   // tiled pixel grid
+    const bool wide = (d->taps == 1) ? (g->total_pix >= 256) : (w_grid >= 16);
     const int acc_cols = (d->wpack_stacked ? 2 : 1) * d->block_n;   // TMEM columns one accumulator writes
     g->msub = (wide && 4 * acc_cols <= 512) ? 2 : 1;
     g->stationary = (g->n_tiles == 1 && g->w_bytes + 3 * g->a_stage_bytes <= budget) ? 1 : 0;
@@ -1056,8 +1171,8 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     g->nprod = kProdWarps / g->nrings;
     if (g->nprod > g->SAr) g->nprod = g->SAr;
     DISCO_REQUIRE(g->SAr >= g->msub && g->nprod >= 1, "conv: A ring too small");
-    g->tiles_h = (d->h_out + 15) / 16;
-    g->tiles_w = (d->w_out + 8 * g->msub - 1) / (8 * g->msub);
+    g->tiles_h = (h_grid + 15) / 16;
+    g->tiles_w = (w_grid + 8 * g->msub - 1) / (8 * g->msub);
     const long long m_tiles = (d->taps == 9) ? (long long)d->n * g->tiles_h * g->tiles_w
                                              : (g->total_pix + 128 * g->msub - 1) / (128 * g->msub);
     DISCO_REQUIRE(m_tiles > 0 && m_tiles * g->n_tiles < (1ll << 30), "conv: bad tile count");
@@ -1068,7 +1183,16 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     g->fd_tiles_w = make_fastdiv(g->tiles_w);
     g->grid = g->items < ctas_per_sm * g_num_sms ? g->items : ctas_per_sm * g_num_sms;
     DISCO_REQUIRE((g->plane >> 4) < 16384 && g->smem_bytes <= 227 * 1024, "conv: descriptor / smem range");
-    if (g->use_tma) {
+    if (d->subpix) {
+        for (int part = 0; part < g->nparts; ++part) {
+            const uint16_t* b0 = reinterpret_cast<const uint16_t*>(d->src[0]) + (part ? d->src_lo_off[0] : 0);
+            const uint16_t* b1 = reinterpret_cast<const uint16_t*>(d->src[1]) + (part ? d->src_lo_off[1] : 0);
+            DISCO_REQUIRE(((reinterpret_cast<uintptr_t>(b0) | reinterpret_cast<uintptr_t>(b1)) & 15) == 0, "conv: sources not 16-byte aligned");
+            const bool ok = make_tmap4(&g->tmap[part], b0, d->src_c[0], d->w_in / 2, d->h_in / 2, d->n, 10, 18, 1) &&
+                            make_tmap4(&g->tmap[2 + part], b1, d->src_c[1], d->w_in, d->h_in, d->n, 18, 33, 2);
+            DISCO_REQUIRE(ok, "conv: cuTensorMapEncodeTiled failed (sub-pixel class)");
+        }
+    } else if (g->use_tma) {
         for (int s = 0; s < 2; ++s) {
             if (!d->src_c[s] || d->src_up[s] == 2) continue;
             const int up = d->src_up[s] ? 1 : 0;
@@ -1131,5 +1255,6 @@ int disco_conv_tc_launch(const disco_conv_desc* d, void* stream) {
     if (rc < 0) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     if (d->taps == 1) return launch_mode<2>(g, s);
+    if (d->subpix) return g.d.wpack_stacked ? launch_inst<3, 1, 2>(g, s) : launch_inst<3, 1, 3>(g, s);
     return d->stride == 1 ? launch_mode<0>(g, s) : launch_mode<1>(g, s);
 }

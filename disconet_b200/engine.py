@@ -15,7 +15,16 @@ import torch
 
 from . import ops
 from ._lib import PREC_BF16X3, PREC_FP16, FusionDesc
-from .plan import ConvPlan, fold_bn, pack_chain, pack_conv
+from .plan import ConvPlan, fold_bn, pack_chain, pack_conv, pack_conv_subpix
+
+# Output-parity ("sub-pixel") decomposition of the four upsample-concat convs (conv5_1 .. conv8_1): 4 launches, one per parity
+# class, with 4 instead of 9 taps on the upsampled channels (-37 % MMAs on those layers).  Parity-green (tests/test_conv_gpu.py)
+# but OFF by default: measured on B200 (round 2, B = 16, profiles/r02_layers_subpix_B16.csv) the per-class launches are slower
+# than the single launch -- conv5_1 0.85 vs 0.56 ms, conv6_1 0.79 vs 0.52, conv7_1 1.05 vs 0.69, conv8_1 2.50 vs 1.08 -- because
+# every class re-stages the whole full-resolution skip window (stride-2 parity planes: 4.8x the pixels it uses) and the small
+# per-class grids quantise badly over 148 SMs.  The profitable form keeps the four class accumulators of one tile in TMEM and
+# shares one staged window.  DISCO_B200_SUBPIX=1 enables it.
+USE_SUBPIX = os.environ.get("DISCO_B200_SUBPIX", "0") == "1"
 
 PRECISIONS = {"bf16x3": PREC_BF16X3, "fp16": PREC_FP16}
 
@@ -78,10 +87,15 @@ def build_decoder_plans(get: Getter, p: str, precision: int) -> Dict[str, ConvPl
     """Backbone.decode (Backbone.py:145-242); concat order = (upsampled, skip) (:176,195,214,233)."""
     P: Dict[str, ConvPlan] = {}
 
+    subpix = set(x for x in os.environ.get("DISCO_B200_SUBPIX_LAYERS", "c5_1,c6_1,c7_1,c8_1").split(",") if x)
+
     def add(name, conv, bn, srcs, c_blk=None):
         c_blk = int(os.environ.get("DISCO_CBLK_" + name.upper(), "0")) or c_blk     # tuning hook (K-stage width of one layer)
         w, b = _conv_bn(get, p + conv, p + bn)
         P[name] = pack_conv(w, b, src_channels=srcs, relu=True, precision=precision, name=p + conv, c_blk=c_blk)
+        if USE_SUBPIX and len(srcs) == 2 and precision == PREC_BF16X3 and name in subpix:
+            P[name + "/sub"] = [pack_conv_subpix(w, b, src_channels=srcs, py=py, px=px, relu=True, precision=precision, name=p + conv)
+                                for py in (0, 1) for px in (0, 1)]
 
     add("c5_1", "conv5_1", "bn5_1", [512, 256]); add("c5_2", "conv5_2", "bn5_2", [256])
     add("c6_1", "conv6_1", "bn6_1", [256, 128]); add("c6_2", "conv6_2", "bn6_2", [128])
@@ -229,16 +243,17 @@ class Workspace:
                 x3_dec = b["x3f"]
             else:
                 x2_dec = b["x2f"]
-        self.dec_calls: List[ops.ConvCall] = [
-            mk(dec["c5_1"], [b["x4"], x3_dec], [1, 0], b["t5"], h3, w3),
-            mk(dec["c5_2"], [b["t5"]], [0], b["x5"], h3, w3),
-            mk(dec["c6_1"], [b["x5"], x2_dec], [1, 0], b["t6"], h2, w2),
-            mk(dec["c6_2"], [b["t6"]], [0], b["x6"], h2, w2),
-            mk(dec["c7_1"], [b["x6"], b["x1"]], [1, 0], b["t7"], h1, w1),
-            mk(dec["c7_2"], [b["t7"]], [0], b["x7"], h1, w1),
-            mk(dec["c8_1"], [b["x7"], b["x"]], [1, 0], b["t8"], h, w),
-            mk(dec["c8_2"], [b["t8"]], [0], b["x8"], h, w),
-        ]
+        def up(name, srcs, out, hh, ww):
+            """conv(cat(nearest_up2(srcs[0]), srcs[1])): one launch, or one per output-parity class (engine.USE_SUBPIX)."""
+            if name + "/sub" in dec and hh % 2 == 0 and ww % 2 == 0:
+                return [mk(pl, srcs, [1, 0], out, hh, ww) for pl in dec[name + "/sub"]]
+            return [mk(dec[name], srcs, [1, 0], out, hh, ww)]
+
+        self.dec_calls: List[ops.ConvCall] = (
+            up("c5_1", [b["x4"], x3_dec], b["t5"], h3, w3) + [mk(dec["c5_2"], [b["t5"]], [0], b["x5"], h3, w3)] +
+            up("c6_1", [b["x5"], x2_dec], b["t6"], h2, w2) + [mk(dec["c6_2"], [b["t6"]], [0], b["x6"], h2, w2)] +
+            up("c7_1", [b["x6"], b["x1"]], b["t7"], h1, w1) + [mk(dec["c7_2"], [b["t7"]], [0], b["x7"], h1, w1)] +
+            up("c8_1", [b["x7"], b["x"]], b["t8"], h, w) + [mk(dec["c8_2"], [b["t8"]], [0], b["x8"], h, w)])
         self.head_calls: List[ops.ConvCall] = []
         if heads is not None:
             self.n_cls, self.n_reg = heads["n_cls"], heads["n_reg"]

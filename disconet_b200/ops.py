@@ -104,8 +104,12 @@ class ConvCall:
             d.chain_relu = int(plan.chain["relu"])
             fpp += plan.chain["flops_per_pixel"]
         d.src_lo_nonzero = lo_nonzero.data_ptr() if lo_nonzero is not None else None
+        if plan.subpix is not None:       # one output-parity class of an upsample-concat conv (a quarter of the output pixels)
+            if list(ups) != [1, 0] or len(srcs) != 2:
+                raise ValueError(f"conv[{plan.name}]: a sub-pixel class plan needs (upsampled, plain) sources")
+            d.subpix, d.sub_py, d.sub_px = 1, int(plan.subpix[0]), int(plan.subpix[1])
         self.desc = d
-        self.flops = fpp * n * d.h_out * d.w_out
+        self.flops = fpp * n * d.h_out * d.w_out // (4 if plan.subpix is not None else 1)
         self.set_output(out, out_split)
         self._fn = load().disco_conv_forward
         self._ref = load().disco_conv_reference

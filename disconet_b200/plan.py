@@ -67,6 +67,7 @@ class ConvPlan:
     chain: Optional[dict] = None   # chained 1x1: {wpack, bias, c_out, relu} (see conv.h chain_*)
     name: str = ""
     flops_per_pixel: int = field(default=0)
+    subpix: Optional[tuple] = None   # (py, px): this plan computes ONE output-parity class of an upsample-concat conv (conv.h subpix)
 
 
 def pack_conv(wf: torch.Tensor, bf: torch.Tensor, *, src_channels, stride: int = 1, relu: bool = True,
@@ -127,3 +128,59 @@ def pack_chain(w2: torch.Tensor, b2: torch.Tensor, k2: int, relu: bool = False) 
     bias = torch.zeros(bn, dtype=torch.float32, device=w2.device)
     bias[:n2] = b2
     return {"wpack": img, "bias": bias, "c_out": n2, "relu": bool(relu), "flops_per_pixel": 2 * k2 * n2}
+
+
+# ---- output-parity ("sub-pixel") decomposition of conv(cat(nearest_up2(a), b)) ------------------------------------------
+# For the output pixels of one parity class (oy % 2, ox % 2) = (py, px) the nine taps of the UPSAMPLED source touch only
+# 2 x 2 distinct low-resolution pixels, so their weights can be pre-summed: 4 taps instead of 9 on those channels
+# (Backbone.py:176,195,214,233 feed 2/3 of the input channels of conv5_1..conv8_1 through F.interpolate(scale_factor=2)).
+# Tap kh of the 3x3 kernel reads up-res row oy + kh - 1 = low-res row a + {-1, 0, +1}[kh'] with (oy = 2a + py):
+#   py = 0:  kh 0 -> kh' 0 ;  kh 1, 2 -> kh' 1          py = 1:  kh 0, 1 -> kh' 1 ;  kh 2 -> kh' 2      (same for columns)
+_SUBPIX_MAP = {0: (0, 1, 1), 1: (1, 1, 2)}
+
+
+def subpix_active_taps(py: int, px: int):
+    """Tap positions (kh' * 3 + kw') of the low-res 3x3 window that class (py, px) uses, ascending."""
+    rows, cols = sorted(set(_SUBPIX_MAP[py])), sorted(set(_SUBPIX_MAP[px]))
+    return [r * 3 + c for r in rows for c in cols]
+
+
+def pack_conv_subpix(wf: torch.Tensor, bf: torch.Tensor, *, src_channels, py: int, px: int, relu: bool = True,
+                     precision: int = PREC_BF16X3, name: str = "") -> ConvPlan:
+    """Weights of output-parity class (py, px) of a 3x3 conv over cat(nearest_up2(src0), src1): source-0 taps pre-summed into
+    the 2 x 2 low-res taps the class touches (packed as 4 blocks per channel block), source-1 taps unchanged (9 blocks).
+    Block order = [n_tile][channel block][active tap]; 16-channel K stages (the stride-2 parity planes of source 1 are large)."""
+    assert precision == PREC_BF16X3 and wf.shape[2:] == (3, 3) and len(src_channels) == 2
+    c_out, c_in_real = wf.shape[0], wf.shape[1]
+    c0, c1 = int(src_channels[0]), int(src_channels[1])
+    assert c0 + c1 == c_in_real and c0 % 16 == 0 and c1 % 16 == 0
+    c_blk = 16
+    c_out_pad16 = (c_out + 15) // 16 * 16
+    block_n = 256 if c_out_pad16 >= 256 else min(c_out_pad16, 128)
+    n_tiles = (c_out + block_n - 1) // block_n
+    n_rows = n_tiles * block_n
+    dev = wf.device
+    w = torch.zeros(n_rows, c_in_real, 3, 3, dtype=torch.float32, device=dev)
+    w[:c_out] = wf.detach().float()
+    w0 = torch.zeros(n_rows, c0, 3, 3, dtype=torch.float32, device=dev)
+    for kh in range(3):
+        for kw in range(3):
+            w0[:, :, _SUBPIX_MAP[py][kh], _SUBPIX_MAP[px][kw]] += w[:, :c0, kh, kw]
+    w = torch.cat((w0, w[:, c0:]), 1).reshape(n_rows, c_in_real, 9)
+    bias = torch.zeros(n_rows, dtype=torch.float32, device=dev)
+    bias[:c_out] = bf
+    ncb = c_in_real // c_blk
+    w6 = w.view(n_tiles, block_n, ncb, c_blk // 8, 8, 9).permute(0, 2, 5, 3, 1, 4).contiguous()   # [n_tile, cb, tap, chunk, n, 8]
+    stacked = block_n <= 64
+    hi, lo = split_bf16(w6)
+    parts = torch.stack((hi, lo), dim=4 if stacked else 3).contiguous()      # [.., tap, chunk, part, n, 8] | [.., tap, part, chunk, n, 8]
+    act = subpix_active_taps(py, px)
+    blocks = []
+    for t in range(n_tiles):
+        for cb in range(ncb):
+            taps = act if cb < c0 // c_blk else range(9)
+            blocks += [parts[t, cb, tap].reshape(-1) for tap in taps]
+    wpack = torch.cat(blocks).view(torch.int16)
+    return ConvPlan(taps=9, stride=1, c_in=c_in_real, c_out=c_out, c_blk=c_blk, block_n=block_n, relu=relu, precision=precision,
+                    wpack=wpack.reshape(-1), bias=bias, wref=None, name=name + f"[py{py}px{px}]", stacked=stacked,
+                    flops_per_pixel=2 * 9 * c_in_real * c_out, subpix=(py, px))

@@ -661,8 +661,9 @@ class TrainRunner:
                 with torch.cuda.graph(graph):
                     self.run_ops(op_list, torch.cuda.current_stream(self.dev).cuda_stream)
                 g = self._graphs[which] = graph
-            except Exception:           # capture unsupported in this context: stay eager
+            except Exception as e:      # capture unsupported in this context: stay eager (the reason is kept for diagnosis)
                 g = self._graphs[which] = False
+                self.graph_error = f"{which}: {type(e).__name__}: {e}"[:400]
                 torch.cuda.synchronize()
         if g:
             g.replay()

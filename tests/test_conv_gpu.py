@@ -175,3 +175,45 @@ def test_conv_fuzz_against_validator(cuda_dev):
             assert torch.isfinite(got).all(), (case, which)
             err = rel_max(got, ref)
             assert err < tol, f"{case} {which}: {err:.3e}"
+
+
+# ---- output-parity ("sub-pixel") decomposition of the upsample-concat convs (conv.h `subpix`, plan.pack_conv_subpix) ----------
+SUBPIX_CASES = [
+    # (name, n, h, w, c_up, c_skip, c_out)   -- conv8_1 / conv7_1 / conv6_1 / conv5_1 shape classes + ragged / tiny grids
+    ("c8_1_like", 2, 64, 64, 64, 32, 32),
+    ("c7_1_like", 2, 32, 32, 128, 64, 64),
+    ("c6_1_like_many_items", 5, 64, 64, 256, 128, 128),
+    ("c5_1_like", 2, 32, 32, 512, 256, 256),
+    ("ragged_class_grid_24x20", 1, 24, 20, 64, 32, 32),
+    ("tiny_8x8", 3, 8, 8, 128, 64, 64),
+]
+
+
+@pytest.mark.parametrize("case", SUBPIX_CASES, ids=[c[0] for c in SUBPIX_CASES])
+def test_subpix_classes_match_torch_conv(cuda_dev, case):
+    """Four class launches == F.conv2d(cat(interpolate(a, 2), b)) (Backbone.py:176-178,195-197,214-216,233-235)."""
+    from disconet_b200.ops import ConvCall
+    from disconet_b200.plan import pack_conv_subpix
+    name, n, h, w, c_up, c_skip, c_out = case
+    dev = cuda_dev
+    g = torch.Generator(device="cpu").manual_seed(5)
+    a = to_act(torch.randn(n, c_up, h // 2, w // 2, generator=g).to(dev), PREC_BF16X3)
+    b = to_act(torch.randn(n, c_skip, h, w, generator=g).to(dev), PREC_BF16X3)
+    c_in = c_up + c_skip
+    wgt = (torch.randn(c_out, c_in, 3, 3, generator=g) / (c_in * 9) ** 0.5).to(dev)
+    bias = (torch.randn(c_out, generator=g) * 0.1).to(dev)
+    x_cat = torch.cat((F.interpolate(act_value(a).permute(0, 3, 1, 2), scale_factor=2), act_value(b).permute(0, 3, 1, 2)), 1)
+    ref = F.relu(F.conv2d(x_cat.double(), wgt.double(), bias.double(), padding=1)).permute(0, 2, 3, 1).float()
+    out = alloc_act(n, h, w, c_out, PREC_BF16X3, dev)
+    out.fill_(float("nan"))
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    for py in (0, 1):
+        for px in (0, 1):
+            plan = pack_conv_subpix(wgt, bias, src_channels=[c_up, c_skip], py=py, px=px, relu=True, name=name)
+            ConvCall(plan, [a, b], [1, 0], out, n=n, h_in=h, w_in=w).launch(stream)
+    torch.cuda.synchronize()
+    got = act_value(out)
+    assert torch.isfinite(got).all(), "a class launch left output pixels unwritten"
+    err = rel_max(got, ref)
+    print(name, "sub-pixel rel-max error vs fp64 torch conv", err)
+    assert err < 3e-5          # bf16x3 operands (~16 mantissa bits), fp32 accumulation
