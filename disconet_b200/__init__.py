@@ -4,8 +4,9 @@ Public surface = the reference's model classes for this path (`DiscoNet`, `FaFNe
 the BEV-segmentation variant) plus the data-format entry points (`voxelize_occupy`, `bev_scatter`).  Everything computes in libdisco_b200.so.
 """
 from .det import DiscoNet, FaFNet, TeacherNet, AgentWeightList  # noqa: F401
-from .voxel import voxelize_occupy, bev_scatter  # noqa: F401
+from .voxel import voxelize_occupy, voxelize_occupy_batched, bev_scatter, bev_scatter_batched  # noqa: F401
 from .pipeline import HostPipeline  # noqa: F401
 from . import seg  # noqa: F401  (disconet_b200.seg.SegDiscoNet == coperception.models.seg.DiscoNet)
 
-__all__ = ["DiscoNet", "FaFNet", "TeacherNet", "voxelize_occupy", "bev_scatter", "HostPipeline"]
+__all__ = ["DiscoNet", "FaFNet", "TeacherNet", "voxelize_occupy", "voxelize_occupy_batched", "bev_scatter", "bev_scatter_batched",
+           "HostPipeline"]

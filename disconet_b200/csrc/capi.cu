@@ -71,6 +71,13 @@ int disco_voxelize_occupy(const float* points, int n_points, int point_stride, c
                                  n_voxels, dense, stream);
 }
 
+int disco_voxelize_occupy_batched(const float* points, const int* n_points, int n_sweeps, int p_max, int point_stride,
+                                  const double* extents, const double* voxel_size, const int* dims, unsigned int* bitmap,
+                                  int* block_count, int* voxel_indices, int m_max, int* n_voxels, void* stream) {
+    return disco_voxelize_batched_launch(points, n_points, n_sweeps, p_max, point_stride, extents, voxel_size, dims, bitmap, block_count,
+                                         voxel_indices, m_max, n_voxels, stream);
+}
+
 int disco_bev_scatter(const int* voxel_indices, int n_voxels, const int* dims, float* bev_f32, void* act_hi,
                       int act_c, int precision, void* stream) {
     return disco_bev_scatter_launch(voxel_indices, n_voxels, dims, bev_f32, act_hi, act_c, precision, stream);

@@ -62,7 +62,7 @@ __device__ __forceinline__ void load_feat(const uint16_t* p, long long lo_off, i
 
 template <int CPL>
 __global__ void __launch_bounds__(kWarps * 32, 3) fusion_kernel(const disco_fusion_desc d) {
-    __shared__ float s_w2[kH2][kHid + 1];
+    __shared__ __align__(16) float s_w2[kH2][kHid + 4];   // row pitch 132 floats: 16-byte aligned rows, LDS.128 by 8 lanes hits 32 banks
     __shared__ float s_b2[kH2];
     __shared__ float s_w3[kH3][kH2];
     __shared__ float s_b3[kH3];
@@ -174,23 +174,44 @@ __global__ void __launch_bounds__(kWarps * 32, 3) fusion_kernel(const disco_fusi
 #pragma unroll 8
                     for (int c = 0; c < kHid; c += 4) {
                         const float4 hv = *reinterpret_cast<const float4*>(&s_h1[warp][c]);
-                        q0 = fmaf(s_w2[lane][c], hv.x, q0);
-                        q1 = fmaf(s_w2[lane][c + 1], hv.y, q1);
-                        q2 = fmaf(s_w2[lane][c + 2], hv.z, q2);
-                        q3 = fmaf(s_w2[lane][c + 3], hv.w, q3);
+                        const float4 wv = *reinterpret_cast<const float4*>(&s_w2[lane][c]);   // one LDS.128 instead of four LDS.32
+                        q0 = fmaf(wv.x, hv.x, q0);
+                        q1 = fmaf(wv.y, hv.y, q1);
+                        q2 = fmaf(wv.z, hv.z, q2);
+                        q3 = fmaf(wv.w, hv.w, q3);
                     }
                     h2 = (q0 + q1) + (q2 + q3);
                 }
                 h2 = fmaxf(h2, 0.f);
-                wk = s_b4;
+                {
+                    // 32 -> 8: eight dot products over the lanes as a reduce-scatter (8 -> 4 -> 2 -> 1 values per lane, then two
+                    // plain butterfly steps): 9 shuffles instead of 8 x 5; lane bits 4,3,2 then select the output unit q.
+                    float v[kH3];
 #pragma unroll
-                for (int q = 0; q < kH3; ++q) {
-                    float part = s_w3[q][lane] * h2;
+                    for (int q = 0; q < kH3; ++q) v[q] = s_w3[q][lane] * h2;
+                    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+                    float u[4], t[2];
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-                    wk = fmaf(s_w4[q], fmaxf(part + s_b3[q], 0.f), wk);
+                    for (int i = 0; i < 4; ++i) {
+                        const float send = b4 ? v[i] : v[i + 4], keep = b4 ? v[i + 4] : v[i];
+                        u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const float send = b3 ? u[i] : u[i + 2], keep = b3 ? u[i + 2] : u[i];
+                        t[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    }
+                    float r = (b2 ? t[1] : t[0]) + __shfl_xor_sync(0xffffffffu, b2 ? t[0] : t[1], 4);
+                    r += __shfl_xor_sync(0xffffffffu, r, 2);
+                    r += __shfl_xor_sync(0xffffffffu, r, 1);
+                    const int q = (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0);
+                    // 8 -> 1: sum over q = sum over lane bits 4,3,2 (every q is replicated on the 4 lanes of its group)
+                    float o = s_w4[q] * fmaxf(r + s_b3[q], 0.f);
+                    o += __shfl_xor_sync(0xffffffffu, o, 4);
+                    o += __shfl_xor_sync(0xffffffffu, o, 8);
+                    o += __shfl_xor_sync(0xffffffffu, o, 16);
+                    wk = fmaxf(o + s_b4, 0.f);
                 }
-                wk = fmaxf(wk, 0.f);
                 }
                 const float ek = expf(wk);
                 esum += ek;

@@ -146,6 +146,92 @@ __global__ void __launch_bounds__(1024) voxel_compact_kernel(const unsigned int*
     if (tid == 0) *n_out = carry;
 }
 
+// ---- batched form: S sweeps in three launches (mark, per-block bit counts, ordered multi-block compaction) ----------------
+__global__ void voxel_mark_batched_kernel(const float* __restrict__ pts, const int* __restrict__ n_points, int p_max, int stride,
+                                          double x0, double x1, double y0, double y1, double z0, double z1, double vx, double vy,
+                                          double vz, int dx, int dy, int dz, int n_words, unsigned int* __restrict__ bitmap) {
+    const int s = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p_max || i >= n_points[s]) return;
+    const float* p = pts + ((long long)s * p_max + i) * stride;
+    const double x = (double)p[0], y = (double)p[1], z = (double)p[2];
+    if (!(x0 < x && x < x1 && y0 < y && y < y1 && z0 < z && z < z1)) return;
+    const int ix = (int)floor(__ddiv_rn(x, vx)) - (int)floor(__ddiv_rn(x0, vx));
+    const int iy = (int)floor(__ddiv_rn(y, vy)) - (int)floor(__ddiv_rn(y0, vy));
+    const int iz = (int)floor(__ddiv_rn(z, vz)) - (int)floor(__ddiv_rn(z0, vz));
+    if (ix < 0 || ix >= dx || iy < 0 || iy >= dy || iz < 0 || iz >= dz) return;
+    const unsigned int key = ((unsigned)ix * dy + iy) * dz + iz;
+    atomicOr(bitmap + (long long)s * n_words + (key >> 5), 1u << (key & 31));
+}
+
+// block (b, s) counts the set bits of words [1024 b, 1024 (b+1)) of sweep s
+__global__ void __launch_bounds__(1024) voxel_count_kernel(const unsigned int* __restrict__ bitmap, int n_words, int n_blocks,
+                                                           int* __restrict__ block_count) {
+    __shared__ int warp_sums[32];
+    const int s = blockIdx.y, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int wi = b * 1024 + tid;
+    int cnt = (wi < n_words) ? __popc(bitmap[(long long)s * n_words + wi]) : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) warp_sums[wid] = cnt;
+    __syncthreads();
+    if (wid == 0) {
+        int v = warp_sums[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) block_count[s * n_blocks + b] = v;
+    }
+}
+
+// block (b, s): offset = bits in the blocks before it; ordered compaction of its 1024 words -> indices [s, offset..]; pad rows -1
+__global__ void __launch_bounds__(1024) voxel_compact_batched_kernel(const unsigned int* __restrict__ bitmap, int n_words, int n_blocks,
+                                                                     const int* __restrict__ block_count, int dy, int dz, int n_bits,
+                                                                     int m_max, int* __restrict__ out_idx, int* __restrict__ n_out) {
+    __shared__ int warp_sums[32];
+    __shared__ int base;
+    const int s = blockIdx.y, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        int off = 0;
+        for (int k = 0; k < b; ++k) off += block_count[s * n_blocks + k];
+        base = off;
+        if (b == n_blocks - 1) n_out[s] = off + block_count[s * n_blocks + b];
+    }
+    const int wi = b * 1024 + tid;
+    const unsigned int word = (wi < n_words) ? bitmap[(long long)s * n_words + wi] : 0u;
+    const int cnt = __popc(word);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int v = warp_sums[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        warp_sums[lane] = v;
+    }
+    __syncthreads();
+    int o = base + (wid ? warp_sums[wid - 1] : 0) + incl - cnt;
+    unsigned int wbits = word;
+    while (wbits) {
+        const int bit = __ffs(wbits) - 1;
+        wbits &= wbits - 1;
+        const int key = wi * 32 + bit;
+        if (key < n_bits && o < m_max) {
+            int* dst = out_idx + ((long long)s * m_max + o) * 3;
+            const int iz = key % dz, t = key / dz;
+            dst[0] = t / dy; dst[1] = t % dy; dst[2] = iz;
+        }
+        ++o;
+    }
+}
+
 __global__ void voxel_dense_kernel(const unsigned int* __restrict__ bitmap, int n_bits, float* __restrict__ dense) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_bits) dense[i] = ((bitmap[i >> 5] >> (i & 31)) & 1u) ? 1.f : 0.f;
@@ -246,6 +332,34 @@ int disco_voxelize_launch(const float* points, int n_points, int point_stride, c
         voxel_dense_kernel<<<(unsigned)((n_bits + 255) / 256), 256, 0, s>>>(bitmap, (int)n_bits, dense);
         DISCO_CHECK_CUDA(cudaGetLastError());
     }
+    return DISCO_OK;
+}
+
+int disco_voxelize_batched_launch(const float* points, const int* n_points, int n_sweeps, int p_max, int point_stride,
+                                  const double* extents, const double* voxel_size, const int* dims, unsigned int* bitmap,
+                                  int* block_count, int* voxel_indices, int m_max, int* n_voxels, void* stream) {
+    DISCO_REQUIRE(extents && voxel_size && dims && bitmap && block_count && n_voxels && n_points && voxel_indices, "voxelize_batched: null argument");
+    DISCO_REQUIRE(n_sweeps > 0 && p_max >= 0 && (p_max == 0 || points) && m_max > 0, "voxelize_batched: bad sizes");
+    DISCO_REQUIRE(point_stride >= 3, "voxelize_batched: points need >= 3 columns (got %d)", point_stride);
+    const long long n_bits = (long long)dims[0] * dims[1] * dims[2];
+    DISCO_REQUIRE(dims[0] > 0 && dims[1] > 0 && dims[2] > 0 && n_bits < (1ll << 30), "voxelize_batched: bad dims");
+    const int n_words = (int)((n_bits + 31) / 32), n_blocks = (n_words + 1023) / 1024;
+    cudaStream_t s = (cudaStream_t)stream;
+    DISCO_CHECK_CUDA(cudaMemsetAsync(bitmap, 0, (size_t)n_sweeps * n_words * 4, s));
+    DISCO_CHECK_CUDA(cudaMemsetAsync(voxel_indices, 0xFF, (size_t)n_sweeps * m_max * 3 * sizeof(int), s));   // padding rows = -1
+    if (p_max > 0) {
+        dim3 grid((p_max + 255) / 256, n_sweeps);
+        voxel_mark_batched_kernel<<<grid, 256, 0, s>>>(points, n_points, p_max, point_stride, extents[0], extents[1], extents[2],
+                                                       extents[3], extents[4], extents[5], voxel_size[0], voxel_size[1], voxel_size[2],
+                                                       dims[0], dims[1], dims[2], n_words, bitmap);
+        DISCO_CHECK_CUDA(cudaGetLastError());
+    }
+    dim3 grid2(n_blocks, n_sweeps);
+    voxel_count_kernel<<<grid2, 1024, 0, s>>>(bitmap, n_words, n_blocks, block_count);
+    DISCO_CHECK_CUDA(cudaGetLastError());
+    voxel_compact_batched_kernel<<<grid2, 1024, 0, s>>>(bitmap, n_words, n_blocks, block_count, dims[1], dims[2], (int)n_bits, m_max,
+                                                        voxel_indices, n_voxels);
+    DISCO_CHECK_CUDA(cudaGetLastError());
     return DISCO_OK;
 }
 

@@ -44,6 +44,9 @@ int disco_act_unpack_nchw_launch(const void* act_hi, long long lo_off, int preci
 int disco_voxelize_launch(const float* points, int n_points, int point_stride, const double* extents,
                           const double* voxel_size, const int* dims, unsigned int* bitmap, int* voxel_indices,
                           int* n_voxels, float* dense, void* stream);
+int disco_voxelize_batched_launch(const float* points, const int* n_points, int n_sweeps, int p_max, int point_stride,
+                                  const double* extents, const double* voxel_size, const int* dims, unsigned int* bitmap,
+                                  int* block_count, int* voxel_indices, int m_max, int* n_voxels, void* stream);
 int disco_bev_scatter_launch(const int* voxel_indices, int n_voxels, const int* dims, float* bev_f32, void* act_hi,
                              int act_c, int precision, void* stream);
 

@@ -42,8 +42,21 @@ __device__ __forceinline__ double poly_area_signed(const double* x, const double
 // Intersection area of two convex quads (vertices in either orientation).  Sutherland-Hodgman: clip P by the four edges
 // of Q (both made counter-clockwise first).  Inside test `cross >= 0`; an edge crossing is s + t (e - s) with
 // t = ds / (ds - de).  Must stay in lock-step with oracle/post_oracle.py::quad_intersection_area.
-__device__ double quad_intersection_area(const double* P, const double* Q) {
+// The two vertex lists (<= 8 vertices each) are indexed dynamically; they live in SHARED memory, interleaved over the 64
+// threads of the CTA (element k of thread t at scratch[k * 64 + t]: conflict-free) -- as per-thread stack arrays they went to
+// local memory and the kernel moved 2.5 GB through L2 per 80 agents (round-2 ncu capture).
+constexpr int kClipStride = 64;
+struct ClipScratch {
+    double* base;   // &scratch[threadIdx.x]; arrays sx, sy, ox, oy of 8 doubles each at stride kClipStride
+    __device__ __forceinline__ double& sx(int i) const { return base[(i) * kClipStride]; }
+    __device__ __forceinline__ double& sy(int i) const { return base[(8 + i) * kClipStride]; }
+    __device__ __forceinline__ double& ox(int i) const { return base[(16 + i) * kClipStride]; }
+    __device__ __forceinline__ double& oy(int i) const { return base[(24 + i) * kClipStride]; }
+};
+
+__device__ double quad_intersection_area(const double* P, const double* Q, const ClipScratch& w) {
     double px[4], py[4], qx[4], qy[4];
+#pragma unroll
     for (int i = 0; i < 4; ++i) { px[i] = P[2 * i]; py[i] = P[2 * i + 1]; qx[i] = Q[2 * i]; qy[i] = Q[2 * i + 1]; }
     if (poly_area_signed(px, py, 4) < 0.0) {
         double t;
@@ -53,30 +66,38 @@ __device__ double quad_intersection_area(const double* P, const double* Q) {
         double t;
         t = qx[1]; qx[1] = qx[3]; qx[3] = t; t = qy[1]; qy[1] = qy[3]; qy[3] = t;
     }
-    double sx[8], sy[8], ox[8], oy[8];
     int n = 4;
-    for (int i = 0; i < 4; ++i) { sx[i] = px[i]; sy[i] = py[i]; }
-    for (int e = 0; e < 4 && n > 0; ++e) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { w.sx(i) = px[i]; w.sy(i) = py[i]; }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        if (n <= 0) break;
         const double ax = qx[e], ay = qy[e], bx = qx[(e + 1) & 3], by = qy[(e + 1) & 3];
         int m = 0;
         for (int i = 0; i < n; ++i) {
             const int j = (i + 1 == n) ? 0 : i + 1;
-            const double ds = cross3(ax, ay, bx, by, sx[i], sy[i]);
-            const double de = cross3(ax, ay, bx, by, sx[j], sy[j]);
+            const double six = w.sx(i), siy = w.sy(i), sjx = w.sx(j), sjy = w.sy(j);
+            const double ds = cross3(ax, ay, bx, by, six, siy);
+            const double de = cross3(ax, ay, bx, by, sjx, sjy);
             const bool in_s = ds >= 0.0, in_e = de >= 0.0;
-            if (in_s && m < 8) { ox[m] = sx[i]; oy[m] = sy[i]; ++m; }
+            if (in_s && m < 8) { w.ox(m) = six; w.oy(m) = siy; ++m; }
             if (in_s != in_e && m < 8) {
                 const double t = ds / dsub(ds, de);
-                ox[m] = dadd(sx[i], dmul(t, dsub(sx[j], sx[i])));
-                oy[m] = dadd(sy[i], dmul(t, dsub(sy[j], sy[i])));
+                w.ox(m) = dadd(six, dmul(t, dsub(sjx, six)));
+                w.oy(m) = dadd(siy, dmul(t, dsub(sjy, siy)));
                 ++m;
             }
         }
         n = m;
-        for (int i = 0; i < n; ++i) { sx[i] = ox[i]; sy[i] = oy[i]; }
+        for (int i = 0; i < n; ++i) { w.sx(i) = w.ox(i); w.sy(i) = w.oy(i); }
     }
     if (n < 3) return 0.0;
-    return fabs(poly_area_signed(sx, sy, n));
+    double s = 0.0;   // shoelace in index order (poly_area_signed)
+    for (int i = 0; i < n; ++i) {
+        const int j = (i + 1 == n) ? 0 : i + 1;
+        s = dadd(s, dsub(dmul(w.sx(i), w.sy(j)), dmul(w.sx(j), w.sy(i))));
+    }
+    return fabs(dmul(0.5, s));
 }
 
 __device__ __forceinline__ double quad_area(const double* P) {
@@ -86,15 +107,9 @@ __device__ __forceinline__ double quad_area(const double* P) {
 }
 
 // iou > thr, with the decision the oracle makes: inter / (area_p + area_q - inter); a zero union gives NaN -> false.
-__device__ __forceinline__ bool quad_iou_above(const double* P, const double* Q, double thr) {
-    // axis-aligned bounding boxes that do not touch cannot intersect: exact-zero intersection, IoU 0 (or 0/0), never > thr
-    double pl = P[0], ph = P[0], pb = P[1], pt = P[1], ql = Q[0], qh = Q[0], qb = Q[1], qt = Q[1];
-    for (int i = 1; i < 4; ++i) {
-        pl = fmin(pl, P[2 * i]); ph = fmax(ph, P[2 * i]); pb = fmin(pb, P[2 * i + 1]); pt = fmax(pt, P[2 * i + 1]);
-        ql = fmin(ql, Q[2 * i]); qh = fmax(qh, Q[2 * i]); qb = fmin(qb, Q[2 * i + 1]); qt = fmax(qt, Q[2 * i + 1]);
-    }
-    if (ph < ql || qh < pl || pt < qb || qt < pb) return false;
-    const double inter = quad_intersection_area(P, Q);
+__device__ __forceinline__ bool quad_iou_above(const double* P, const double* Q, double thr, const ClipScratch& w) {
+    // (the caller has already rejected pairs whose axis-aligned bounds do not touch: exact-zero intersection, never > thr)
+    const double inter = quad_intersection_area(P, Q, w);
     const double uni = dsub(dadd(quad_area(P), quad_area(Q)), inter);
     const double iou = inter / uni;
     return iou > thr;   // NaN compares false
@@ -166,43 +181,76 @@ __global__ void __launch_bounds__(1024) nms_sort_kernel(const CT* __restrict__ c
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// 2. upper-triangular "IoU > thr" bit matrix: mask[a][i][j / 64] bit (j % 64), j > i
+// 2. upper-triangular "IoU > thr" bit matrix: mask[a][i][j / 64] bit (j % 64), j > i.  kMaskBlocks CTAs per agent walk the
+//    (row block, column block) pairs of the K x K upper triangle (K is only known on the device, so the grid cannot be sized to
+//    it: round 2's first version launched 32 x 32 x n mostly-empty CTAs and spent 0.8 ms per 80 agents on their launch slots).
 // ------------------------------------------------------------------------------------------------------------
+constexpr int kMaskBlocks = 32;
+
 __global__ void __launch_bounds__(64) nms_mask_kernel(const double* __restrict__ s_corners, const int* __restrict__ s_count,
                                                       int kmax, int words, double thr,
                                                       unsigned long long* __restrict__ mask) {
-    const int a = blockIdx.z, rb = blockIdx.y, cb = blockIdx.x, t = threadIdx.x;
+    const int a = blockIdx.y, t = threadIdx.x;
     int K = s_count[a];
     if (K > kmax) K = kmax;
-    if (cb < rb || rb * 64 >= K || cb * 64 >= K) return;
+    const int nb = (K + 63) / 64;                 // 64-box blocks per side
+    const int n_pairs = nb * (nb + 1) / 2;        // upper triangle incl. the diagonal blocks
     __shared__ double cq[64][8];
-    const int j0 = cb * 64;
-    if (j0 + t < K) {
+    __shared__ double qbox[64][4];                // column boxes' axis-aligned bounds (xmin, xmax, ymin, ymax)
+    __shared__ double clip[32 * kClipStride];     // Sutherland-Hodgman vertex lists of the 64 threads (16 KB)
+    const ClipScratch scratch{clip + t};
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        // pair -> (rb, cb), rb <= cb: rows of the triangle have nb, nb-1, ... entries
+        int rb = 0, rem = pair;
+        while (rem >= nb - rb) { rem -= nb - rb; ++rb; }
+        const int cb = rb + rem;
+        const int j0 = cb * 64;
+        __syncthreads();
+        if (j0 + t < K) {
+            double xl, xh, yl, yh;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) cq[t][q] = s_corners[((long long)a * kmax + j0 + t) * 8 + q];
-    }
-    __syncthreads();
-    const int i = rb * 64 + t;
-    if (i >= K) return;
-    double P[8];
+            for (int q = 0; q < 8; ++q) cq[t][q] = s_corners[((long long)a * kmax + j0 + t) * 8 + q];
+            xl = xh = cq[t][0]; yl = yh = cq[t][1];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) P[q] = s_corners[((long long)a * kmax + i) * 8 + q];
-    unsigned long long bits = 0ull;
-    const int jn = min(64, K - j0);
-    for (int jj = 0; jj < jn; ++jj) {
-        if (j0 + jj <= i) continue;
-        if (quad_iou_above(P, cq[jj], thr)) bits |= 1ull << jj;
+            for (int q = 1; q < 4; ++q) {
+                xl = fmin(xl, cq[t][2 * q]); xh = fmax(xh, cq[t][2 * q]);
+                yl = fmin(yl, cq[t][2 * q + 1]); yh = fmax(yh, cq[t][2 * q + 1]);
+            }
+            qbox[t][0] = xl; qbox[t][1] = xh; qbox[t][2] = yl; qbox[t][3] = yh;
+        }
+        __syncthreads();
+        const int i = rb * 64 + t;
+        if (i >= K) continue;
+        double P[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) P[q] = s_corners[((long long)a * kmax + i) * 8 + q];
+        double pl = P[0], ph = P[0], pb = P[1], pt = P[1];
+#pragma unroll
+        for (int q = 1; q < 4; ++q) {
+            pl = fmin(pl, P[2 * q]); ph = fmax(ph, P[2 * q]); pb = fmin(pb, P[2 * q + 1]); pt = fmax(pt, P[2 * q + 1]);
+        }
+        unsigned long long bits = 0ull;
+        const int jn = min(64, K - j0);
+        for (int jj = 0; jj < jn; ++jj) {
+            if (j0 + jj <= i) continue;
+            // boxes whose axis-aligned bounds do not touch cannot intersect: IoU 0 (or 0/0), never > thr
+            if (ph < qbox[jj][0] || qbox[jj][1] < pl || pt < qbox[jj][2] || qbox[jj][3] < pb) continue;
+            if (quad_iou_above(P, cq[jj], thr, scratch)) bits |= 1ull << jj;
+        }
+        mask[((long long)a * kmax + i) * words + cb] = bits;
     }
-    mask[((long long)a * kmax + i) * words + cb] = bits;
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// 3. greedy scan (postprocess.py:97-112), one warp per agent: rows of removed boxes are skipped
+// 3. greedy scan (postprocess.py:97-112), one warp per agent, 64 candidates at a time: the 64 x 64 diagonal block decides which
+//    of them survive (serial over bits, all in registers / shared memory), then the rows of the survivors are OR-ed into the
+//    removed set in parallel -- two dependent global-memory rounds per 64 candidates instead of one per kept box.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ s_count,
                                                       const int* __restrict__ s_slot, int kmax, int words, int* __restrict__ keep,
                                                       int* __restrict__ n_keep) {
-    extern __shared__ unsigned long long removed[];
+    extern __shared__ unsigned long long removed[];     // [words] removed set, then [64] diagonal rows
+    unsigned long long* diag = removed + words;
     const int a = blockIdx.x, lane = threadIdx.x;
     int K = s_count[a];
     if (K > kmax) K = kmax;
@@ -210,13 +258,23 @@ __global__ void __launch_bounds__(32) nms_scan_kernel(const unsigned long long* 
     for (int w = lane; w < kw; w += 32) removed[w] = 0ull;
     __syncwarp();
     int nk = 0;
-    for (int i = 0; i < K; ++i) {
-        const bool gone = (removed[i >> 6] >> (i & 63)) & 1ull;   // warp-uniform (shared memory broadcast)
-        if (gone) continue;
-        if (lane == 0) keep[(long long)a * kmax + nk] = s_slot[(long long)a * kmax + i];
-        ++nk;
-        const unsigned long long* row = mask + ((long long)a * kmax + i) * words;
-        for (int w = (i >> 6) + lane; w < kw; w += 32) removed[w] |= row[w];
+    for (int c = 0; c < kw; ++c) {
+        const int i0 = c * 64, cn = min(64, K - i0);
+        // diagonal block: row i0 + r, word c (bits j > i inside the chunk)
+        for (int r = lane; r < 64; r += 32) diag[r] = (r < cn) ? mask[((long long)a * kmax + i0 + r) * words + c] : 0ull;
+        __syncwarp();
+        unsigned long long rem = removed[c], kept = 0ull;
+        for (int r = 0; r < cn; ++r) {             // warp-uniform serial pass over the chunk
+            if (!((rem >> r) & 1ull)) { kept |= 1ull << r; rem |= diag[r]; }
+        }
+        // record the survivors in pick order and fold their rows into the removed set of the later chunks
+        for (int r = 0; r < cn; ++r) {
+            if (!((kept >> r) & 1ull)) continue;
+            if (lane == 0) keep[(long long)a * kmax + nk] = s_slot[(long long)a * kmax + i0 + r];
+            ++nk;
+            const unsigned long long* row = mask + ((long long)a * kmax + i0 + r) * words;
+            for (int w = c + 1 + lane; w < kw; w += 32) removed[w] |= row[w];
+        }
         __syncwarp();
     }
     if (lane == 0) n_keep[a] = nk;
@@ -338,10 +396,10 @@ int disco_nms_rotated_launch(const void* corners, int corners_f64, const float* 
         nms_sort_kernel<float><<<n, 1024, sort_smem, s>>>((const float*)corners, scores, ids, count, cap, kmax, score_thresh,
                                                           s_corners, s_scores, s_ids, s_slot, s_count);
     DISCO_CHECK_CUDA(cudaGetLastError());
-    dim3 grid(words, words, n);
+    dim3 grid(kMaskBlocks, n);
     nms_mask_kernel<<<grid, 64, 0, s>>>(s_corners, s_count, kmax, words, iou_thresh, mask);
     DISCO_CHECK_CUDA(cudaGetLastError());
-    nms_scan_kernel<<<n, 32, (size_t)words * 8, s>>>(mask, s_count, s_slot, kmax, words, keep, n_keep);
+    nms_scan_kernel<<<n, 32, (size_t)(words + 64) * 8, s>>>(mask, s_count, s_slot, kmax, words, keep, n_keep);
     DISCO_CHECK_CUDA(cudaGetLastError());
     if (n_valid) DISCO_CHECK_CUDA(cudaMemcpyAsync(n_valid, s_count, sizeof(int) * n, cudaMemcpyDeviceToDevice, s));
     return DISCO_OK;

@@ -123,6 +123,7 @@ def non_max_suppression(boxes, scores, threshold, device=None):
     out = keep[0, :nk].cpu()
     if base is not None:
         out = base.cpu()[out.long()]
+    print("selected: ", nk)                       # (the reference function prints this, postprocess.py:114)
     return out.numpy().astype(np.int32)
 
 
@@ -185,6 +186,8 @@ def apply_nms_det(batch_box_preds, batch_cls_preds, anchors, code_type, config, 
     n = batch_box_preds.shape[0]
     res = detect(batch_box_preds, batch_cls_preds.reshape(n, -1, 2), anchors.reshape((n,) + tuple(batch_box_preds.shape[1:4]) + (6,)))
     predictions_dicts = [[r] for r in res]
+    for r in res:
+        print("selected: ", len(r["selected_idx"]))   # (printed by the reference's non_max_suppression, postprocess.py:114)
     sel = torch.as_tensor(res[-1]["selected_idx"].astype(np.int64), device=batch_cls_preds.device)
     cls_pred_first_nms = batch_cls_preds[n - 1][sel, :]
     return predictions_dicts, cls_pred_first_nms

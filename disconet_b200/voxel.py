@@ -60,6 +60,33 @@ def voxelize_occupy(pts: torch.Tensor, voxel_size, extents=None, return_indices:
     return dense
 
 
+def voxelize_occupy_batched(pts: torch.Tensor, n_points: torch.Tensor, voxel_size, extents, max_voxels: Optional[int] = None):
+    """`voxelize_occupy` (data_util.py:625-717) for a batch of sweeps in three launches.  pts: CUDA float32 [S, P_max, 3..4]
+    (rows >= n_points[s] ignored), n_points int32 [S].  Returns (indices [S, M_max, 3] int32 -- per sweep the sorted unique voxel
+    indices, padded with -1 -- and n_voxels [S] int32), the input format of `DiscoNet.forward_voxels` / `bev_scatter_batched`."""
+    if pts.dim() != 3 or pts.shape[2] < 3 or pts.shape[2] > 4 or pts.dtype != torch.float32:
+        raise ValueError("points must be float32 [S, P_max, 3..4] (got {} {})".format(tuple(pts.shape), pts.dtype))
+    _require_cuda(pts, n_points)
+    pts, n_points = pts.contiguous(), n_points.to(torch.int32).contiguous()
+    _, dims = _grid(extents, voxel_size)
+    S, p_max = int(pts.shape[0]), int(pts.shape[1])
+    n_bits = int(dims[0]) * int(dims[1]) * int(dims[2])
+    n_words = (n_bits + 31) // 32
+    m_max = int(max_voxels) if max_voxels else min(n_bits, max(p_max, 1))
+    dev = pts.device
+    bitmap = torch.empty((S, n_words), dtype=torch.int32, device=dev)
+    block_count = torch.empty((S, (n_words + 1023) // 1024), dtype=torch.int32, device=dev)
+    idx = torch.empty((S, m_max, 3), dtype=torch.int32, device=dev)
+    n_vox = torch.empty((S,), dtype=torch.int32, device=dev)
+    ext = (C.c_double * 6)(*np.asarray(extents, dtype=np.float64).reshape(-1).tolist())
+    vs = (C.c_double * 3)(*[float(v) for v in voxel_size])
+    cd = (C.c_int * 3)(*[int(d) for d in dims])
+    check(load().disco_voxelize_occupy_batched(pts.data_ptr(), n_points.data_ptr(), S, p_max, int(pts.shape[2]), ext, vs, cd,
+                                               bitmap.data_ptr(), block_count.data_ptr(), idx.data_ptr(), m_max, n_vox.data_ptr(),
+                                               _stream_ptr(dev)), "voxelize_occupy_batched")
+    return idx, n_vox
+
+
 def bev_scatter(voxel_indices: torch.Tensor, dims, *, packed: bool = False, precision: int = PREC_BF16X3):
     """Dataset scatter: indices [M,3] -> dense BEV float32 [Y, X, Z] = np.rot90(vox, 3) with vox[idx]=1
     (V2XSimDet.py:293-302).  With `packed=True` also returns the 16-channel NHWC activation the encoder

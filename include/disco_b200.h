@@ -106,6 +106,14 @@ int disco_voxelize_occupy(const float* points, int n_points, int point_stride, c
                           const double* voxel_size /* host */, const int* dims /* host */, unsigned int* bitmap,
                           int* voxel_indices, int* n_voxels, float* dense, void* stream);
 
+/* voxelize_occupy for n_sweeps point clouds in three launches: points [n_sweeps, p_max, point_stride] fp32, n_points [n_sweeps]
+ * (device) -> voxel_indices [n_sweeps, m_max, 3] int32 (sorted unique per sweep, rows >= n_voxels[s] = -1) and n_voxels
+ * [n_sweeps] -- exactly the (indices, counts) pair disco_bev_scatter_batched consumes.  bitmap: n_sweeps * ceil(X*Y*Z/32) words,
+ * block_count: n_sweeps * ceil(words/1024) ints (scratch).  One extents / voxel_size for the whole batch (host float64). */
+int disco_voxelize_occupy_batched(const float* points, const int* n_points, int n_sweeps, int p_max, int point_stride,
+                                  const double* extents /* host */, const double* voxel_size /* host */, const int* dims /* host */,
+                                  unsigned int* bitmap, int* block_count, int* voxel_indices, int m_max, int* n_voxels, void* stream);
+
 /* Dataset scatter (datasets/V2XSimDet.py:293-302): voxel indices [n,3] int32 -> dense BEV
  * bev[y, X-1-x, z] = 1 (== np.rot90(vox, 3)), as fp32 [Y,X,Z] and/or a 16-bit NHWC activation with
  * act_c channels per cell.  Either output may be NULL. */

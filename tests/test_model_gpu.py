@@ -174,6 +174,47 @@ def test_voxelize_and_scatter_bit_exact(cuda_dev):
         voxelize_occupy(torch.zeros(4, 4), V.VOXEL_SIZE, V.EXTENTS)   # CPU tensor: no fallback
 
 
+def test_voxelize_batched_bit_exact_and_feeds_forward_voxels(cuda_dev):
+    """Batched voxelisation (three launches for S sweeps) == the per-sweep oracle incl. ragged / empty sweeps and the boundary
+    torture cloud of the live-reference golden; its (indices, counts) output drives forward_voxels to the same logits as the
+    dense-BEV forward."""
+    from disconet_b200 import DiscoNet, voxelize_occupy_batched
+    rec = np.load(os.path.join(GOLD, "voxel.npz"))
+    clouds = [V.synth_points(1, 40000), V.synth_points(3, 7), rec["edge_pts"].astype(np.float32), np.zeros((0, 4), np.float32),
+              V.synth_points(7, 100000), np.full((9, 4), 99.0, np.float32)]
+    p_max = max(len(c) for c in clouds)
+    pts = np.zeros((len(clouds), p_max, 4), np.float32)
+    for i, c in enumerate(clouds):
+        pts[i, :len(c)] = c
+    npts = torch.tensor([len(c) for c in clouds], dtype=torch.int32)
+    idx, nvox = voxelize_occupy_batched(torch.from_numpy(pts).to(cuda_dev), npts.to(cuda_dev), V.VOXEL_SIZE, V.EXTENTS)
+    idx, nvox = idx.cpu().numpy(), nvox.cpu().numpy()
+    for i, c in enumerate(clouds):
+        _, want = V.voxelize_occupy(c, V.VOXEL_SIZE, V.EXTENTS)
+        assert nvox[i] == len(want), i
+        assert np.array_equal(idx[i, :nvox[i]], want.astype(np.int32)), i
+        assert (idx[i, nvox[i]:] == -1).all()
+    assert np.array_equal(idx[2, :nvox[2]], rec["edge_idx"])          # live-reference golden (boundary torture)
+    # points -> voxels -> forward_voxels == dense forward on the oracle-scattered BEV
+    A = 2
+    m = DiscoNet(_Cfg(), kd_flag=0, num_agent=A)
+    m.load_state_dict(O.synth_state_dict(m.state_dict(), seed=71))
+    m = m.to(cuda_dev).eval()
+    two = [V.synth_points(1, 40000), V.synth_points(2, 30000)]
+    pts2 = np.zeros((A, 40000, 4), np.float32)
+    for i, c in enumerate(two):
+        pts2[i, :len(c)] = c
+    idx2, n2 = voxelize_occupy_batched(torch.from_numpy(pts2).to(cuda_dev), torch.tensor([40000, 30000], dtype=torch.int32, device=cuda_dev),
+                                       V.VOXEL_SIZE, V.EXTENTS)
+    bev = torch.from_numpy(np.stack([V.bev_scatter(V.voxelize_occupy(c, V.VOXEL_SIZE, V.EXTENTS)[1], (256, 256, 13)) for c in two]))[:, None]
+    T = O.synth_poses(1, A, seed=72)
+    na = torch.full((1, A), A)
+    with torch.no_grad():
+        r_vox, _ = m.forward_voxels(idx2, n2, T, na, batch_size=1)
+        r_dense, _ = m(bev.to(cuda_dev), T, na, batch_size=1)
+    assert torch.equal(r_vox["cls"], r_dense["cls"]) and torch.equal(r_vox["loc"], r_dense["loc"])
+
+
 def test_communication_outage_matches_reference_semantics(cuda_dev):
     """p_com_outage > 0: same numpy RNG consumption order as the reference (one draw per present ego) and
     ego features kept for the agents that drew an outage (DetModelBase.py:129-137, DiscoNet.py:68-69)."""
