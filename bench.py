@@ -631,7 +631,8 @@ def main():
     sharded = None
     if dist:
         try:
-            sharded = agent_sharded_leg(dev, world, rank, steps=max(3, min(args.steps, 10)), warmup=3)
+            sharded = agent_sharded_leg(dev, world, rank, steps=max(3, min(args.steps, 10)), warmup=3,
+                                        scenes=int(os.environ.get("DISCO_BENCH_SHARD_SCENES", "8")))
         except Exception as e:
             sharded = {"error": f"{type(e).__name__}: {e}"[:300]}
 

@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(1024) nms_sort_kernel(const CT* __restrict__ c
 //    (row block, column block) pairs of the K x K upper triangle (K is only known on the device, so the grid cannot be sized to
 //    it: round 2's first version launched 32 x 32 x n mostly-empty CTAs and spent 0.8 ms per 80 agents on their launch slots).
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kMaskBlocks = 32;
+constexpr int kMaskBlocks = 96;   // >= the 91 block pairs of ~800 candidates: one pair per CTA in the common case
 
 __global__ void __launch_bounds__(64) nms_mask_kernel(const double* __restrict__ s_corners, const int* __restrict__ s_count,
                                                       int kmax, int words, double thr,
@@ -229,12 +229,19 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const double* __restrict__
         for (int q = 1; q < 4; ++q) {
             pl = fmin(pl, P[2 * q]); ph = fmax(ph, P[2 * q]); pb = fmin(pb, P[2 * q + 1]); pt = fmax(pt, P[2 * q + 1]);
         }
-        unsigned long long bits = 0ull;
+        // phase 1: which column boxes can intersect at all (axis-aligned bounds touch; otherwise IoU is 0 or 0/0, never > thr)
+        unsigned long long hits = 0ull;
         const int jn = min(64, K - j0);
         for (int jj = 0; jj < jn; ++jj) {
             if (j0 + jj <= i) continue;
-            // boxes whose axis-aligned bounds do not touch cannot intersect: IoU 0 (or 0/0), never > thr
-            if (ph < qbox[jj][0] || qbox[jj][1] < pl || pt < qbox[jj][2] || qbox[jj][3] < pb) continue;
+            if (!(ph < qbox[jj][0] || qbox[jj][1] < pl || pt < qbox[jj][2] || qbox[jj][3] < pb)) hits |= 1ull << jj;
+        }
+        // phase 2: every lane clips ITS OWN next hit in each trip, so the warp runs max-popcount trips of the expensive float64
+        // clip instead of one (mostly idle) trip per column that any lane hits (~6 % of the pairs overlap: 8-10 trips, not ~55)
+        unsigned long long bits = 0ull;
+        while (hits) {
+            const int jj = __ffsll((long long)hits) - 1;
+            hits &= hits - 1;
             if (quad_iou_above(P, cq[jj], thr, scratch)) bits |= 1ull << jj;
         }
         mask[((long long)a * kmax + i) * words + cb] = bits;
@@ -267,13 +274,26 @@ __global__ void __launch_bounds__(32) nms_scan_kernel(const unsigned long long* 
         for (int r = 0; r < cn; ++r) {             // warp-uniform serial pass over the chunk
             if (!((rem >> r) & 1ull)) { kept |= 1ull << r; rem |= diag[r]; }
         }
-        // record the survivors in pick order and fold their rows into the removed set of the later chunks
-        for (int r = 0; r < cn; ++r) {
-            if (!((kept >> r) & 1ull)) continue;
-            if (lane == 0) keep[(long long)a * kmax + nk] = s_slot[(long long)a * kmax + i0 + r];
-            ++nk;
-            const unsigned long long* row = mask + ((long long)a * kmax + i0 + r) * words;
-            for (int w = c + 1 + lane; w < kw; w += 32) removed[w] |= row[w];
+        // record the survivors in pick order ...
+        {
+            const int nsurv = __popcll(kept);
+            for (int q = lane; q < nsurv; q += 32) {       // lane q takes the q-th set bit of `kept`
+                unsigned long long m = kept;
+                for (int z = 0; z < q; ++z) m &= m - 1;
+                const int r = __ffsll((long long)m) - 1;
+                keep[(long long)a * kmax + nk + q] = s_slot[(long long)a * kmax + i0 + r];
+            }
+            nk += nsurv;
+        }
+        // ... and fold their rows into the removed set of the later chunks: lane = word, independent loads over the survivors
+        for (int w = c + 1 + lane; w < kw; w += 32) {
+            unsigned long long acc = removed[w], m = kept;
+            while (m) {
+                const int r = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                acc |= __ldg(mask + ((long long)a * kmax + i0 + r) * words + w);
+            }
+            removed[w] = acc;
         }
         __syncwarp();
     }

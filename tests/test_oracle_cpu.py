@@ -176,7 +176,7 @@ def test_no_cpu_fallback_in_train_and_eval_mode():
 def test_c_abi_exports_every_declared_symbol():
     from disconet_b200 import _lib
     with open(os.path.join(ROOT, "include", "disco_b200.h")) as f:
-        declared = set(re.findall(r"^int\s+(disco_\w+)\s*\(", f.read(), flags=re.M))
+        declared = set(re.findall(r"^(?:int|long long)\s+(disco_\w+)\s*\(", f.read(), flags=re.M))
     assert declared and declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:

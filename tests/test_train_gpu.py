@@ -218,6 +218,40 @@ def test_dgrad_stride2_zero_stuffed_matches_autograd(shape, cuda_dev):
         assert e < 1e-4, e
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 32, 64, 32, 32), (1, 32, 48, 128, 64, 64), (1, 16, 16, 512, 256, 256)])
+def test_dgrad_stride1_and_upsample_concat_matches_autograd(shape, cuda_dev):
+    """Data gradient of conv(cat(nearest_up2(a), b)) (Backbone.py:176-178 ...): one stride-1 conv of the output gradient per
+    source with that source's flipped, transposed weight slice (`TrainRunner._dgrad_weight`); the gradient of the upsampled
+    source is the 2x2 sum-pool of its full-resolution slice (what bn_bwd's `pool` gradient sources do).  Against fp64 autograd,
+    through the TMA-fed tensor-core kernel and the CUDA-core validator."""
+    from disconet_b200 import ops
+    from disconet_b200.plan import pack_conv
+    from disconet_b200.train import TrainRunner
+    dev = cuda_dev
+    n, h, w_, c_up, c_skip, cout = shape
+    rng = np.random.default_rng(11)
+    cin = c_up + c_skip
+    wgt = torch.from_numpy((rng.standard_normal((cout, cin, 3, 3)) / np.sqrt(9 * cin)).astype(np.float32))
+    dz = torch.from_numpy(rng.standard_normal((n, cout, h, w_)).astype(np.float32))
+    a = torch.zeros(n, c_up, h // 2, w_ // 2, dtype=torch.float64, requires_grad=True)
+    b = torch.zeros(n, c_skip, h, w_, dtype=torch.float64, requires_grad=True)
+    F.conv2d(torch.cat((F.interpolate(a, scale_factor=2), b), 1), wgt.double(), padding=1).backward(dz.double())
+    dz_act = to_act(dz, P).to(dev)
+    for (c0, cs, want, pool) in ((0, c_up, a.grad, True), (c_up, c_skip, b.grad, False)):
+        wt = TrainRunner._dgrad_weight(wgt.to(dev), c0, cs)
+        plan = pack_conv(wt, torch.zeros(cs, device=dev), src_channels=[cout], stride=1, relu=False, precision=P, keep_ref=True)
+        for reference in (True, False):
+            out = torch.zeros((n, h, w_, cs), device=dev)
+            ops.ConvCall(plan, [dz_act], [0], (out,), n=n, h_in=h, w_in=w_).launch(_stream(dev), reference=reference)
+            torch.cuda.synchronize()
+            got = out.cpu().permute(0, 3, 1, 2).double()
+            if pool:
+                got = F.avg_pool2d(got, 2) * 4
+            e = rel_max(got, want)
+            print("dgrad s1", shape, "upsampled source" if pool else "skip source", "validator" if reference else "tensor-core", f"{e:.2e}")
+            assert e < 1e-4, e
+
+
 # ------------------------------------------------------------------------------------------------------------
 def _disco(case, sd, dev, train=True):
     from disconet_b200 import DiscoNet
