@@ -417,7 +417,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         if (nb < d.c_out) {
 #pragma unroll
                             for (int r = 0; r < 2; ++r) {   // 2 passes x 16 pixels x 2 pieces of 16 B
-                                const int px = r * 16 + (lane >> 1), piece = lane & 1;
+                                // lanes 0-15 read piece 0 of 16 pixels, lanes 16-31 piece 1: every quarter-warp of the LDS.128 reads
+                                // 8 rows at the 80-byte row pitch = 8 distinct 4-bank groups (the (lane >> 1, lane & 1) mapping was a
+                                // 2-way conflict: round-2 source view, 2x the ideal wavefronts on these four loads)
+                                const int px = r * 16 + (lane & 15), piece = lane >> 4;
                                 const int m2 = (warp & 3) * 32 + px;
                                 bool ok;
                                 long long pix2;
@@ -1085,6 +1088,26 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     const bool wide = (d->taps == 1) ? (g->total_pix >= 256) : (w_grid >= 16);
     const int acc_cols = (d->wpack_stacked ? 2 : 1) * d->block_n;   // TMEM columns one accumulator writes
     g->msub = (wide && 4 * acc_cols <= 512) ? 2 : 1;
+    {
+        // Wave quantisation: with few, large items (N >= 128 tiles at 32^2 / 16^2 resolution) the last round of a launch leaves
+        // most SMs idle (e.g. 320 items of two sub-tiles on 148 SMs = 2.16 rounds -> 3).  One sub-tile per item lowers the number of
+        // sub-tile rounds but doubles the weight stream per MAC (42 instead of 21 B/clk per SM for N >= 128: over the L2 cap when
+        // all SMs stream).  Tuning knob DISCO_CONV_MSUB = 1 (force) | 3 (when it saves >= 10 % of the rounds); default: off.
+        static int force = -1;
+        if (force < 0) { const char* e = getenv("DISCO_CONV_MSUB"); force = e ? atoi(e) : 0; }
+        if (g->msub == 2 && d->block_n >= 128) {
+            const long long th = (d->taps == 1) ? 1 : (h_grid + 15) / 16;
+            const long long sub_tiles = (d->taps == 1) ? (g->total_pix + 127) / 128 : (long long)d->n * th * ((w_grid + 7) / 8);
+            const long long items2 = ((d->taps == 1) ? (g->total_pix + 255) / 256 : (long long)d->n * th * ((w_grid + 15) / 16)) * g->n_tiles;
+            const long long items1 = sub_tiles * g->n_tiles;
+            const int sms = g_num_sms > 0 ? g_num_sms : 148;
+            const long long rounds2 = 2 * ((items2 + sms - 1) / sms), rounds1 = (items1 + sms - 1) / sms;
+            if (force == 1 || (force == 3 && rounds1 * 10 <= rounds2 * 9)) g->msub = 1;   // 3: only when >= 10 % fewer sub-tile rounds
+            // default: split only launches that cannot even fill the SMs once (small batches, e.g. one agent per GPU): the
+            // doubled weight stream is harmless when most of the L2 bandwidth is idle, and twice as many SMs get work
+            if (force == 0 && items2 < sms) g->msub = 1;
+        }
+    }
     g->stationary = (g->n_tiles == 1 && g->w_bytes + 3 * g->a_stage_bytes <= budget) ? 1 : 0;
     // Stationary layers: items of one sub-tile with issuers splitting ITEMS (private A rings) -- unless one item
     // needs more channel blocks than a private ring can hold (conv8_1: 3 blocks, 2 slots per ring): then keep
