@@ -1109,6 +1109,13 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
         }
     }
     g->stationary = (g->n_tiles == 1 && g->w_bytes + 3 * g->a_stage_bytes <= budget) ? 1 : 0;
+    {
+        // tuning knob: weight sets larger than DISCO_CONV_NOSTAT_MAXW bytes are streamed even if they would fit (a big resident
+        // set leaves only a shallow A-stage ring: conv8_1 = 110 KB)
+        static long maxw = -1;
+        if (maxw < 0) { const char* e = getenv("DISCO_CONV_NOSTAT_MAXW"); maxw = e ? atol(e) : 0; }
+        if (maxw > 0 && g->w_bytes > maxw && d->chain_c_out == 0) g->stationary = 0;
+    }
     // Stationary layers: items of one sub-tile with issuers splitting ITEMS (private A rings) -- unless one item
     // needs more channel blocks than a private ring can hold (conv8_1: 3 blocks, 2 slots per ring): then keep
     // MSUB = 2 and let the issuers split the SUB-TILES of every item, which pipelines at channel-block granularity.
