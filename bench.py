@@ -58,7 +58,8 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """`nvidia-smi -lms 100` beside the run; `stop(t0, t1)` reports the samples whose timestamps fall inside the timed region."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -73,27 +74,33 @@ class ClockSampler:
         except OSError:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0: float = None, t1: float = None):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        import datetime
         time.sleep(0.15)
         self.p.terminate()
         out, _ = self.p.communicate(timeout=10)
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                ts = None
+            try:
+                rows.append((ts, float(f[1]), float(f[2]), [n for n, v in zip(names, f[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
+        inside = [r for r in rows if t0 is not None and r[0] is not None and t0 - 0.05 <= r[0] <= t1 + 0.05]
+        use = inside or rows[-3:]          # (a very short timed region may fall between two 100 ms samples)
+        sm, mx = [r[1] for r in use], [r[2] for r in use]
+        reasons = sorted({n for r in use for n in r[3]})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(use), "samples_in_timed_region": len(inside), "reasons": reasons}
 
 
 def best_cpu_threads(sd, bev, T, na) -> int:
@@ -458,19 +465,23 @@ def main():
 
     # ---------------- device-resident throughput ("value") ----------------------------------------
     with torch.no_grad():
-        for _ in range(args.warmup):
-            model(bev_d, T_d, na_d, batch_size=B)
+        # the clock sampler (nvidia-smi -lms 100) is started BEFORE the warm-up: its start-up (NVML init over all GPUs) holds driver
+        # locks for tens of ms and, started right at the timed region, intermittently cost the 20-step window ~3 ms per step
         sampler = ClockSampler(local)
-        barrier()
         if rank == 0:
             sampler.start()
+            time.sleep(0.5)
+        for _ in range(args.warmup):
+            model(bev_d, T_d, na_d, batch_size=B)
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        wall0 = time.time()
         e0.record()
         for _ in range(args.steps):
             res, _ = model(bev_d, T_d, na_d, batch_size=B)
         e1.record()
         barrier()
-        clocks = sampler.stop() if rank == 0 else None
+        clocks = sampler.stop(wall0, time.time()) if rank == 0 else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if dist:
         td.all_reduce(ms, op=td.ReduceOp.MAX)

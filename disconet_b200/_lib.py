@@ -172,6 +172,7 @@ EXPORTS = {
     "disco_pwf_train_backward": (C.c_int, [C.POINTER(PwfTrainDesc), C.c_void_p]),
 }
 
+ABI_VERSION = 200    # == disco_version() of the library these ctypes structures describe (csrc/capi.cu)
 _lib = None
 
 
@@ -189,6 +190,10 @@ def load():
         fn = getattr(lib, name)  # AttributeError if an exported symbol is missing
         fn.restype = res
         fn.argtypes = args
+    got = lib.disco_version()
+    if got != ABI_VERSION:
+        raise DiscoError(f"{LIB_PATH} reports ABI version {got}, this package needs {ABI_VERSION}: the library is stale -- rebuild it "
+                         "with `python -m disconet_b200.build --force`")
     _lib = lib
     return lib
 

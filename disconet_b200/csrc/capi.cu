@@ -19,7 +19,9 @@ void disco_set_error(const char* fmt, ...) {
 
 extern "C" {
 
-int disco_version(void) { return 100; }
+// ABI version: bumped whenever a descriptor struct or an entry-point signature changes; disconet_b200/_lib.py refuses to drive a
+// library built from other sources (raw-pointer descriptors read with the wrong layout would corrupt device memory silently).
+int disco_version(void) { return 200; }
 
 int disco_last_error(char* buf, size_t len) {
     if (!buf || len == 0) return DISCO_EINVAL;

@@ -149,6 +149,7 @@ struct alignas(64) ConvGeom {
     CUtensorMap tmap[4];      // [source][part]: TMA views of the conv sources (valid when use_tma)
     int use_tma;              // A operand through the TMA engine (sources that are not zero-stuffed)
     int scratch_warp;         // bytes of low-resolution scratch per producer warp (nearest-upsampled sources), else 0
+    int scr_bufs;             // 2: double-buffered (next box prefetched; 16-channel stages only: a 32-channel box pair would cost 64 KB), else 1
     int scratch_total;
     disco_conv_desc d;
     int ncb, ncb0;            // K stages total / from source 0
@@ -201,7 +202,7 @@ struct __align__(8) SmemCtl {
     uint64_t w2_full;
     uint64_t a2_full[2];
     uint64_t acc2_full[2];
-    uint64_t scr_full[4];     // low-resolution scratch box of producer warp p has landed (TMA complete_tx)
+    uint64_t scr_full[8];     // low-resolution scratch box [producer warp p][buffer 0|1] has landed (TMA complete_tx)
     uint32_t tmem_base;
     uint32_t pad;
 };
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         mbar_init(smem_u32(&ctl->w_full), 1);
         mbar_init(smem_u32(&ctl->w2_full), 1);
-        for (int s = 0; s < 4; ++s) mbar_init(smem_u32(&ctl->scr_full[s]), 1);
+        for (int s = 0; s < 8; ++s) mbar_init(smem_u32(&ctl->scr_full[s]), 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&ctl->a2_full[s]), 4 * 32);
             mbar_init(smem_u32(&ctl->acc2_full[s]), 1);
@@ -511,7 +512,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         // consumer could be a full wrap ahead and pass the parity wait on a stale phase).  Producer warp pw serves
         // ring pw % nmma and, inside it, the stages q with q % nprod == pw / nmma (nprod <= SAr, same argument).
         const int ring = pw % g.nrings, pr = pw / g.nrings;
-        uint32_t scr_phase = 0;
+        // nearest-upsampled sources: the low-resolution box of this warp's NEXT upsampled stage is fetched into the other half of
+        // its scratch while the current one is expanded (and while the warp waits for that stage's ring slot), so the L2 latency
+        // of the box is off the stage's critical path
+        uint32_t scr_par[2] = {0u, 0u};
+        int up_n = 0;          // upsampled stages handled so far (buffer = up_n & 1)
+        bool up_pf = false;    // the box of the stage about to be handled is already in flight
+        const uint32_t scr_half = (g.scr_bufs == 2) ? (uint32_t)g.scratch_warp >> 1 : 0u;
+        auto issue_scratch = [&](int item_x, int s_x, int buf) {     // lane 0 only
+            const Item ix = decode_item<MODE>(g, item_x);
+            const int cb_x = s_x / g.msub, sub_x = s_x - cb_x * g.msub;
+            const int sidx_x = (cb_x < g.ncb0) ? 0 : 1;
+            const int cofs_x = (sidx_x ? cb_x - g.ncb0 : cb_x) * d.c_blk;
+            const int hi_x = ix.h0 - 1, wi_x = ix.w0 + sub_x * 8 - 1;
+            const uint32_t sbar = smem_u32(&ctl->scr_full[pw * 2 + buf]);
+            const uint32_t dst = scr_base + (uint32_t)pw * g.scratch_warp + (uint32_t)buf * scr_half;
+            mbar_arrive_expect_tx(sbar, (uint32_t)(g.nparts * g.chunks) * 960u);
+            for (int part = 0; part < g.nparts; ++part)
+                for (int chunk = 0; chunk < g.chunks; ++chunk)
+                    tma_load_4d(dst + (uint32_t)(part * g.chunks + chunk) * kScrBox, &g.tmap[sidx_x * 2 + part], cofs_x + chunk * 8,
+                                wi_x >> 1, hi_x >> 1, ix.img, sbar);
+        };
         int iacc_p = 0;
         for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++iacc_p) {
             if (pr >= g.nprod) break;
@@ -591,18 +612,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 }
                 if (g.use_tma && upm == 1 && MODE == 0) {
                     // ---- nearest-x2 upsampled source: TMA the 10 x 6 low-resolution box, expand shared -> shared ------
-                    const uint32_t scr = scr_base + (uint32_t)pw * g.scratch_warp;
-                    const uint32_t sbar = smem_u32(&ctl->scr_full[pw]);
+                    const int buf = (g.scr_bufs == 2) ? (up_n & 1) : 0;
+                    const uint32_t scr = scr_base + (uint32_t)pw * g.scratch_warp + (uint32_t)buf * scr_half;
                     const int nbox = g.nparts * g.chunks;
-                    if (lane == 0) {
-                        mbar_arrive_expect_tx(sbar, (uint32_t)nbox * 960u);
-                        for (int part = 0; part < g.nparts; ++part)
-                            for (int chunk = 0; chunk < g.chunks; ++chunk)
-                                tma_load_4d(scr + (uint32_t)(part * g.chunks + chunk) * kScrBox, &g.tmap[sidx * 2 + part],
-                                            cofs + chunk * 8, wi0 >> 1, hi0 >> 1, it.img, sbar);
+                    // this warp's next upsampled stage (same item or a later one of its ring)
+                    int it2 = item, ia2 = iacc_p, s2 = s + g.nprod;
+                    bool found = false;
+                    for (int guard = 0; guard < 32 && !found && g.scr_bufs == 2; ++guard) {
+                        if (s2 >= stages_per_item) {
+                            do { it2 += gridDim.x; ++ia2; } while (it2 < g.items && (ia2 % g.nrings) != ring);
+                            if (it2 >= g.items) break;
+                            const int q02 = (ia2 / g.nrings) * stages_per_item;
+                            s2 = (pr - (q02 % g.nprod) + g.nprod) % g.nprod;
+                            if (s2 >= stages_per_item) continue;
+                        }
+                        const int cb2 = s2 / g.msub;
+                        if (((cb2 < g.ncb0) ? d.src_up[0] : d.src_up[1]) == 1) found = true;
+                        else s2 += g.nprod;
                     }
-                    mbar_wait(sbar, scr_phase);
-                    scr_phase ^= 1u;
+                    if (lane == 0) {
+                        if (!up_pf) issue_scratch(item, s, buf);
+                        if (found) issue_scratch(it2, s2, buf ^ 1);
+                    }
+                    up_pf = found;
+                    mbar_wait(smem_u32(&ctl->scr_full[pw * 2 + buf]), scr_par[buf]);
+                    scr_par[buf] ^= 1u;
+                    ++up_n;
                     // patch pixel (r, c) <- low-res pixel ((r + 1) >> 1, (c + 1) >> 1) of the box (hi0, wi0 are odd)
                     for (int idx = lane; idx < nbox * 180; idx += 32) {
                         const int pc = idx / 180, rem = idx - pc * 180;
@@ -916,6 +951,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         }
                         __syncwarp();
                     } else {
+                    // (Measured in round 2: moving the per-tap weight-stage waits into ONE elected region per channel block, like the
+                    // resident-weight path above, is ~8 % SLOWER on the streamed tensor-bound layers -- conv5_1 0.61 vs 0.56 ms --: the
+                    // elected lane's spin loops run on the divergent path.)
 #pragma unroll
                     for (int tap = 0; tap < TAPS; ++tap) {
                         uint32_t b16;
@@ -1043,7 +1081,7 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     }
     // TMA for the A operand: every source that is not zero-stuffed (src_up == 2 is the transposed-conv trick of the
     // training data gradient and keeps the cp.async gather).  DISCO_CONV_NO_TMA=1 forces the cp.async gather (A/B tests).
-    g->use_tma = 0; g->scratch_warp = 0; g->scratch_total = 0;
+    g->use_tma = 0; g->scratch_warp = 0; g->scratch_total = 0; g->scr_bufs = 1;
     {
         static int no_tma = -1;
         if (no_tma < 0) { const char* e = getenv("DISCO_CONV_NO_TMA"); no_tma = (e && e[0] == '1') ? 1 : 0; }
@@ -1063,7 +1101,13 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
         if (d->taps == 9 && d->stride == 2) { g->parplane = (g->parplane + 127) / 128 * 128; plane = 2 * g->parplane; }
         else plane = (plane + 127) / 128 * 128;
         if (d->taps == 9 && (d->src_up[0] == 1 || (d->src_c[1] && d->src_up[1] == 1))) {
-            g->scratch_warp = g->nparts * g->chunks * kScrBox;
+            // Prefetching the NEXT upsampled stage's box into a second scratch half is implemented (parity-green) but OFF: measured
+            // on conv8_1 it is slower (1.37 vs 1.06 ms) because the extra 16 KB of scratch shrink the A ring from 6 to 4 stages,
+            // which costs more than the hidden L2 latency buys.  DISCO_CONV_SCR_PREFETCH=1 enables it for 16-channel stages.
+            static int pf = -1;
+            if (pf < 0) { const char* e = getenv("DISCO_CONV_SCR_PREFETCH"); pf = (e && e[0] == '1') ? 1 : 0; }
+            g->scr_bufs = (pf && g->chunks <= 2) ? 2 : 1;
+            g->scratch_warp = g->scr_bufs * g->nparts * g->chunks * kScrBox;
             g->scratch_total = kProdWarps * g->scratch_warp;
         }
     } else {

@@ -155,6 +155,9 @@ class _DetBase(nn.Module):
         load()  # raises if libdisco_b200.so is missing
         if self.training and self.precision_name != "bf16x3":
             raise NotImplementedError("training mode runs in the default bf16x3 precision only")
+        if self.training and (self.anchor_num_per_loc, self.category_num, self.box_code_size, self.out_seq_len) != (6, 2, 6, 1):
+            raise NotImplementedError("training mode is built for the default detection head geometry (6 anchors x 2 classes, 6 box codes, "
+                                      "pred_len 1: 12 + 36 head channels); eval mode derives the head widths from the config")
         if self.training and getattr(self, "compress_level", 0) > 4:
             raise NotImplementedError("training mode supports compress_level <= 4 (bottleneck width a multiple of 16)")
         if not bevs.is_cuda:

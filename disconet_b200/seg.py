@@ -60,8 +60,8 @@ class SegDiscoNet(nn.Module):
     def __init__(self, n_channels, n_classes, num_agent, kd_flag=True, compress_level=0, only_v2i=False,
                  precision: Optional[str] = None):
         super().__init__()
-        if compress_level > 0:
-            raise NotImplementedError("disconet_b200.seg implements compress_level == 0")
+        if not 0 <= compress_level <= 9:
+            raise ValueError("compress_level must be in [0, 9] (SegModelBase.py:30-31)")
         self.n_channels, self.n_classes, self.bilinear = n_channels, n_classes, True
         self.num_agent, self.only_v2i, self.kd_flag, self.compress_level = num_agent, only_v2i, kd_flag, compress_level
         # registration order = reference (SegModelBase.__init__, then DiscoNet.__init__)
@@ -75,6 +75,12 @@ class SegDiscoNet(nn.Module):
         self.up3 = UpParams(256, 64)
         self.up4 = UpParams(128, 64)
         self.outc = OutConvParams(64, n_classes)
+        if compress_level > 0:     # communication bottleneck on the shared 512-channel map (SegModelBase.py:29-44, FusionBase.py:31-33)
+            cc = 512 // (2 ** compress_level)
+            self.com_compresser = nn.Conv2d(512, cc, kernel_size=1, stride=1)
+            self.bn_compress = nn.BatchNorm2d(cc)
+            self.com_decompresser = nn.Conv2d(cc, 512, kernel_size=1, stride=1)
+            self.bn_decompress = nn.BatchNorm2d(512)
         self.pixel_weighted_fusion = PixelWeightedFusionParams(512)
         self.neighbor_feat_list = None
         self.tg_agent = None
@@ -152,6 +158,8 @@ class SegDiscoNet(nn.Module):
         from .det import _TrainFn, runner_param_names
         if self.n_channels != 13 or self.n_classes != 8:
             raise NotImplementedError("segmentation training is built for the reference configuration (13 channels, 8 classes)")
+        if self.compress_level > 0:
+            raise NotImplementedError("segmentation training with compress_level > 0 is not built (eval mode is)")
         N, _, H, W = x.shape
         dev = x.device
         kd_keys = list(SEG_KD_KEYS) if self.kd_flag else []
@@ -231,6 +239,23 @@ def build_seg_plans(get, precision: int, n_channels: int, n_classes: int):
     bpad = torch.zeros(nc4, device=wo.device)
     bpad[:n_classes] = bo
     P["outc"] = pack_conv(wpad, bpad, src_channels=[64], relu=False, precision=precision, name="outc.conv")
+    try:
+        get("com_compresser.weight")
+        has_comp = True
+    except KeyError:
+        has_comp = False
+    if has_comp:   # relu(bn(1x1 512 -> cc)), relu(bn(1x1 cc -> 512)); cc padded to the 16-channel lane width
+        w, b = fold_bn(get("com_compresser.weight"), get("com_compresser.bias"), get("bn_compress.weight"), get("bn_compress.bias"),
+                       get("bn_compress.running_mean"), get("bn_compress.running_var"))
+        cc = w.shape[0]
+        cc_pad = (cc + 15) // 16 * 16
+        wp = torch.zeros(cc_pad, 512, 1, 1, device=w.device); wp[:cc] = w
+        bp = torch.zeros(cc_pad, device=w.device); bp[:cc] = b
+        P["compress"] = pack_conv(wp, bp, src_channels=[512], relu=True, precision=precision, name="com_compresser")
+        w, b = fold_bn(get("com_decompresser.weight"), get("com_decompresser.bias"), get("bn_decompress.weight"), get("bn_decompress.bias"),
+                       get("bn_decompress.running_mean"), get("bn_decompress.running_var"))
+        wp = torch.zeros(512, cc_pad, 1, 1, device=w.device); wp[:, :cc] = w
+        P["decompress"] = pack_conv(wp, b, src_channels=[cc_pad], relu=True, precision=precision, name="com_decompresser")
     P["pwf"] = engine.build_pwf_plans(get, precision)
     P["cin_pad"], P["nc4"] = cin_pad, nc4
     return P
@@ -257,6 +282,11 @@ class _SegWorkspace:
             "x8a": A_(1, 128), "x8": A_(1, 64), "u8": A_(0, 64),
             "x9a": A_(0, 64), "x9": A_(0, 64),
         }
+        feat_src = "x4"
+        if "compress" in P:
+            b["x4c"] = A_(3, P["compress"].c_out)
+            b["x4d"] = A_(3, 512)
+            feat_src = "x4d"
         if P["cin_pad"] != 16:
             raise NotImplementedError("segmentation input with more than 16 channels")
         self.x_nhwc = torch.empty((n, h, w, n_channels), dtype=torch.float32, device=device)
@@ -278,7 +308,7 @@ class _SegWorkspace:
         self.na = torch.zeros((batch,), dtype=torch.int32, device=device)
         pwf = P["pwf"]
         f = FusionDesc()
-        f.feat_hi, f.feat_lo_off, f.precision = b["x4"].data_ptr(), ops._lo_off(b["x4"]), precision
+        f.feat_hi, f.feat_lo_off, f.precision = b[feat_src].data_ptr(), ops._lo_off(b[feat_src]), precision
         f.en, f.hid = self.en.data_ptr(), 128
         t = pwf["tail"]
         f.w2, f.b2, f.w3, f.b3, f.w4, f.b4 = (x.data_ptr() for x in t)
@@ -293,7 +323,8 @@ class _SegWorkspace:
             block("down1", ["p1"], "x2a", "x2", 1) + [pool("x2", "p2", 1)] +
             block("down2", ["p2"], "x3a", "x3", 2) + [pool("x3", "p3", 2)] +
             block("down3", ["p3"], "x4a", "x4", 3) +
-            [("conv", ops.ConvCall(pwf["en"], [b["x4"]], [0], (self.en,), n=n, h_in=hf, w_in=wf)), ("fusion",),
+            ([conv(P["compress"], ["x4"], "x4c", 3), conv(P["decompress"], ["x4c"], "x4d", 3)] if "compress" in P else []) +
+            [("conv", ops.ConvCall(pwf["en"], [b[feat_src]], [0], (self.en,), n=n, h_in=hf, w_in=wf)), ("fusion",),
              pool("feat", "p4", 3)] +
             block("down4", ["p4"], "x5a", "x5", 4) + [up("x5", "u5", 4)] +
             block("up1", ["feat", "u5"], "x6a", "x6", 3) + [up("x6", "u6", 3)] +

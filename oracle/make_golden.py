@@ -43,6 +43,7 @@ TRAIN_OUT_KEYS = ("cls", "loc", "x_8", "x_7", "x_6", "x_5", "fused")
 SEG_CASES = {
     "seg_a2_b1": dict(A=2, B=1, num_agent=[2], only_v2i=False, seed=51),
     "seg_a4_b1_absent_v2i": dict(A=4, B=1, num_agent=[3], only_v2i=True, seed=52),
+    "seg_a2_b1_comp2": dict(A=2, B=1, num_agent=[2], only_v2i=False, seed=54, compress_level=2),   # 512 -> 128 -> 512 bottleneck
 }
 SEG_TRAIN_CASE = dict(A=2, B=1, num_agent=[2], only_v2i=False, seed=53)
 SEG_KEYS = ("logits", "x9", "x8", "x7", "x6", "x5", "feat")
@@ -122,11 +123,7 @@ def main(only=None):
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
         print(name, {k: v.shape for k, v in rec.items()})
 
-    if only:
-        with open(kpath, "w") as f:
-            json.dump(keys, f)
-        return
-    for name, case in TRAIN_CASES.items():
+    for name, case in (TRAIN_CASES.items() if not only else ()):
         m = RDisco(cfg, layer=3, kd_flag=1, num_agent=case["A"], compress_level=0, only_v2i=case["only_v2i"]).train()
         keys[name] = [[k, list(v.shape)] for k, v in m.state_dict().items()]
         sd, bev, T, na = golden_case_inputs(case, m.state_dict())
@@ -150,7 +147,9 @@ def main(only=None):
 
     from coperception.models.seg.DiscoNet import DiscoNet as RSeg
     for name, case in SEG_CASES.items():
-        m = RSeg(13, 8, num_agent=case["A"], kd_flag=True, only_v2i=case["only_v2i"]).eval()
+        if only and name not in only:
+            continue
+        m = RSeg(13, 8, num_agent=case["A"], kd_flag=True, only_v2i=case["only_v2i"], compress_level=case.get("compress_level", 0)).eval()
         keys[name] = [[k, list(v.shape)] for k, v in m.state_dict().items()]
         sd, bev, T, na = seg_case_inputs(case, m.state_dict())
         m.load_state_dict(sd)
@@ -163,6 +162,10 @@ def main(only=None):
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
         print(name, {k: v.shape for k, v in rec.items() if k.endswith("_shape")})
 
+    if only:
+        with open(kpath, "w") as f:
+            json.dump(keys, f)
+        return
     # seg DiscoNet in train() mode: outputs + parameter-gradient digest + updated BatchNorm buffers
     name, case = "seg_train_a2_b1", SEG_TRAIN_CASE
     m = RSeg(13, 8, num_agent=case["A"], kd_flag=True, only_v2i=case["only_v2i"]).train()

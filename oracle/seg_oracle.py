@@ -67,6 +67,9 @@ def seg_disconet_forward_graph(sd, x, trans_matrices, num_agent_tensor, agent_nu
     x2 = _down(x1, sd, "down1")
     x3 = _down(x2, sd, "down2")
     x4 = _down(x3, sd, "down3")
+    if "com_compresser.weight" in sd:      # compress_level > 0: 1x1 bottleneck on the shared map (FusionBase.py:31-33)
+        x4 = torch.relu(_bn(F.conv2d(x4, sd["com_compresser.weight"], sd["com_compresser.bias"]), sd, "bn_compress"))
+        x4 = torch.relu(_bn(F.conv2d(x4, sd["com_decompresser.weight"], sd["com_decompresser.bias"]), sd, "bn_decompress"))
     B = x.shape[0] // agent_num
     feat = fuse(sd, x4, trans_matrices, num_agent_tensor, B, agent_num, only_v2i)
     x5 = _down(feat, sd, "down4")

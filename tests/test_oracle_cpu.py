@@ -253,7 +253,7 @@ def test_oracle_training_matches_reference_golden(name):
 
 
 # ---- BEV segmentation DiscoNet (f1 / BASELINE config 5): oracle vs the live-reference golden ----
-@pytest.mark.parametrize("name", ["seg_a2_b1", "seg_a4_b1_absent_v2i"])
+@pytest.mark.parametrize("name", ["seg_a2_b1", "seg_a4_b1_absent_v2i", "seg_a2_b1_comp2"])
 def test_seg_oracle_matches_reference_golden(name):
     from oracle import seg_oracle as S
     from oracle.make_golden import SEG_CASES, SEG_KEYS, SEG_STRIDES, seg_case_inputs

@@ -48,7 +48,7 @@ def test_seg_disconet_matches_oracle_and_golden(name, cuda_dev):
     case = SEG_CASES[name]
     sd, x, T, na = seg_case_inputs(case, _template(name))
     ref = S.seg_disconet_forward(sd, x, T, na, agent_num=case["A"], only_v2i=case["only_v2i"], return_all=True)
-    m = SegDiscoNet(13, 8, num_agent=case["A"], kd_flag=True, only_v2i=case["only_v2i"])
+    m = SegDiscoNet(13, 8, num_agent=case["A"], kd_flag=True, only_v2i=case["only_v2i"], compress_level=case.get("compress_level", 0))
     m.load_state_dict(sd)
     m = m.to(cuda_dev).eval()
     with torch.no_grad():
