@@ -188,6 +188,9 @@ struct alignas(64) ConvGeom {
     int chain_bn;             // its N tile (chain_c_out rounded up to 16)
     int a2_bytes, w2_bytes;   // per-group A2 staging / resident W2 image
     int acc2_col, acc2_stride;// TMEM columns of the chain accumulators (one per epilogue group)
+    int direct;               // epilogue stores straight from registers (no shared-memory staging)
+    int dbg;                  // debug (DISCO_CONV_DBG, MODE 4 timing experiments; results are WRONG when set): 1 no weight copies,
+                              // 2 no A copies, 4 no output stores, 8 no MMAs
     long long* trace;         // debug: per-role clock64 stamps of CTA 0 (DISCO_CONV_TRACE), else null
 };
 
@@ -227,6 +230,7 @@ __device__ __forceinline__ void out_coords(const ConvGeom& g, const Item& it, in
     oh = it.h0 + (m >> 3);
     ow = it.w0 + sub * 8 + (m & 7);
     if (MODE == 3) { oh = 2 * oh + g.d.sub_py; ow = 2 * ow + g.d.sub_px; }
+    if (MODE == 4) { oh = 2 * (it.h0 + (m >> 3)) + (sub >> 1); ow = 2 * (it.w0 + (m & 7)) + (sub & 1); }   // sub = class 2*py + px
 }
 
 template <int MODE>
@@ -253,6 +257,13 @@ __device__ __forceinline__ Item decode_item(const ConvGeom& g, int item) {
 //         tiles of 16 x 8 class pixels (output (2a + py, 2b + px)); source 0 is read at its native half resolution as an
 //         18 x 10 patch with only the 2 x 2 taps the class touches (weights pre-summed on the host), source 1 exactly like a
 //         stride-2 conv whose input origin is shifted by (py, px)
+// MODE 4: ALL FOUR output-parity classes of such a conv in one item ("fused sub-pixel", d.subpix == 2): an item is a 16 x 8 tile of
+//         LOW-RES positions (a, b) = 512 output pixels; the four class accumulators (class 2*py + px -> output (2a + py, 2b + px))
+//         sit side by side in TMEM and share every staged operand: a source-0 stage is the 18 x 10 low-res patch (4 pre-summed
+//         taps per class = 16 MMA pairs instead of 4 tiles x 9 taps = 36), a source-1 stage the two column-parity planes of the
+//         34 x 18 full-resolution window (class (py, px), tap (kh, kw) reads plane (px + kw) & 1 at row py + kh, column
+//         (px + kw) >> 1: 36 pairs, staged once instead of once per class).  Weights are streamed in slots of nine blocks:
+//         source 0 [channel block][low-res tap row ty][class][tx] (+ one pad block), source 1 [channel block][3 x 3 tap].
 template <int MODE, int KSTEPS, int PASSES>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvGeom g) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -270,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int warp = tid >> 5;
     const int lane = tid & 31;
     const disco_conv_desc& d = g.d;
-    constexpr int PW = (MODE == 0 || MODE == 3) ? 10 : (MODE == 1) ? 17 : 128;
+    constexpr int PW = (MODE == 0 || MODE == 3 || MODE == 4) ? 10 : (MODE == 1) ? 17 : 128;
     constexpr int TAPS = (MODE == 2) ? 1 : 9;
     constexpr int STRIDE = (MODE == 1) ? 2 : 1;
     constexpr bool SPLIT = PASSES != 1;     // bf16 hi+lo operands
@@ -282,15 +293,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (tid == 0) {
         for (int s = 0; s < g.SA; ++s) {
             mbar_init(smem_u32(&ctl->a_full[s]), 1);   // one arrival per stage: the TMA issuer's expect_tx, or lane 0 of a cp.async warp
-            mbar_init(smem_u32(&ctl->a_empty[s]), 1);
+            mbar_init(smem_u32(&ctl->a_empty[s]), MODE == 4 ? 2 : 1);      // MODE 4: both issuers read every stage
         }
         for (int s = 0; s < g.SB; ++s) {
             mbar_init(smem_u32(&ctl->b_full[s]), 1);
-            mbar_init(smem_u32(&ctl->b_empty[s]), g.by_sub ? 2 : 1);
+            mbar_init(smem_u32(&ctl->b_empty[s]), (g.by_sub || MODE == 4) ? 2 : 1);
         }
         for (int s = 0; s < kMaxAcc; ++s) {
-            mbar_init(smem_u32(&ctl->acc_full[s]), g.by_sub ? 2 : 1);
-            mbar_init(smem_u32(&ctl->acc_empty[s]), 4 * 32);   // one epilogue group (4 warps) drains a buffer
+            mbar_init(smem_u32(&ctl->acc_full[s]), (g.by_sub || MODE == 4) ? 2 : 1);
+            mbar_init(smem_u32(&ctl->acc_empty[s]), (MODE == 4 ? 8 : 4) * 32);   // one epilogue group (4 warps) drains a buffer (MODE 4: both groups, two classes each)
         }
         mbar_init(smem_u32(&ctl->w_full), 1);
         mbar_init(smem_u32(&ctl->w2_full), 1);
@@ -328,14 +339,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         uint32_t acc_par = 0;
         const int egrp = warp >> 2;   // the epilogue of one item is latency-bound (~3000 cycles); two groups overlap two items
         for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++iacc, buf = (buf + 1 == g.nacc) ? 0 : buf + 1, acc_par ^= (buf == 0)) {
-            if ((iacc & 1) != egrp) continue;
+            if (MODE != 4 && (iacc & 1) != egrp) continue;
             const Item it = decode_item<MODE>(g, item);
             if (warp == 0) TRACE(0, iacc, 0);
             mbar_wait(smem_u32(&ctl->acc_full[buf]), acc_par);
             tc_fence_after();
             if (warp == 0) TRACE(0, iacc, 1);
             const int m = (warp & 3) * 32 + lane;   // TMEM lane == pixel row of the tile; warp w may touch lanes 32*(w%4)..+31
-            for (int sub = 0; sub < g.msub; ++sub) {
+            const int nsub = (MODE == 4) ? 4 : g.msub;                   // accumulators per buffer
+            const int sub_b = (MODE == 4) ? 2 * egrp : 0, sub_e = (MODE == 4) ? 2 * egrp + 2 : g.msub;
+            for (int sub = sub_b; sub < sub_e; ++sub) {
                 bool valid;
                 long long pixel;
                 if (MODE != 2) {
@@ -348,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     valid = pixel < g.total_pix;
                 }
                 const uint32_t t_lane = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) +
-                                        (uint32_t)((buf * g.msub + sub) * g.acc_stride);
+                                        (uint32_t)((buf * nsub + sub) * g.acc_stride);
                 const int nchunks = d.block_n / 16;
                 uint32_t nxt[16], nxt2[16];
                 tmem_ld16(t_lane, nxt);
@@ -390,6 +403,50 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         uint4* dstl = reinterpret_cast<uint4*>(a2 + part_b + (2 * j) * 2048 + m * 16);
                         dstl[0] = pack_bf16x8(lo);
                         dstl[128] = pack_bf16x8(lo + 8);
+                    } else if (g.direct && d.out_mode == DISCO_OUT_ACT && SPLIT) {
+                        // Register-direct stores (no shared-memory staging): a lane holds one pixel's 16 channels = one 32-byte
+                        // sector per plane.  Lane pairs swap halves (one shuffle per plane) so that every store instruction writes
+                        // BOTH halves of a sector -- a lane storing its own two halves in two instructions writes half sectors
+                        // (measured: slower than staging).
+                        const bool odd = lane & 1;
+                        bool val_e, val_o;
+                        long long pix_e, pix_o;
+                        {
+                            const int me = m & ~1, mo = m | 1;
+                            if (MODE != 2) {
+                                int oh, ow;
+                                out_coords<MODE>(g, it, sub, me, oh, ow);
+                                val_e = (oh < d.h_out) && (ow < d.w_out);
+                                pix_e = ((long long)it.img * d.h_out + oh) * d.w_out + ow;
+                                out_coords<MODE>(g, it, sub, mo, oh, ow);
+                                val_o = (oh < d.h_out) && (ow < d.w_out);
+                                pix_o = ((long long)it.img * d.h_out + oh) * d.w_out + ow;
+                            } else {
+                                pix_e = it.p0 + sub * 128 + me; val_e = pix_e < g.total_pix;
+                                pix_o = it.p0 + sub * 128 + mo; val_o = pix_o < g.total_pix;
+                            }
+                        }
+                        float lo[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) lo[i] = v[i] - bf16_bits_to_f32(f32_to_bf16_bits(v[i]));
+                        const uint4 h0 = pack_bf16x8(v), h1 = pack_bf16x8(v + 8), l0 = pack_bf16x8(lo), l1 = pack_bf16x8(lo + 8);
+                        uint4 sh = odd ? h0 : h1, sl = odd ? l0 : l1;       // even lanes give away their upper half, odd lanes their lower half
+                        sh.x = __shfl_xor_sync(0xffffffffu, sh.x, 1); sh.y = __shfl_xor_sync(0xffffffffu, sh.y, 1);
+                        sh.z = __shfl_xor_sync(0xffffffffu, sh.z, 1); sh.w = __shfl_xor_sync(0xffffffffu, sh.w, 1);
+                        sl.x = __shfl_xor_sync(0xffffffffu, sl.x, 1); sl.y = __shfl_xor_sync(0xffffffffu, sl.y, 1);
+                        sl.z = __shfl_xor_sync(0xffffffffu, sl.z, 1); sl.w = __shfl_xor_sync(0xffffffffu, sl.w, 1);
+                        if (nb < d.c_out && !(g.dbg & 4)) {
+                            uint16_t* oe = reinterpret_cast<uint16_t*>(d.out[0]) + pix_e * d.c_out + nb + (odd ? 8 : 0);
+                            uint16_t* oo = reinterpret_cast<uint16_t*>(d.out[0]) + pix_o * d.c_out + nb + (odd ? 8 : 0);
+                            if (val_e) {      // the even lane's pixel: own lower half | partner's copy of its upper half
+                                *reinterpret_cast<uint4*>(oe) = odd ? sh : h0;
+                                *reinterpret_cast<uint4*>(oe + d.out_lo_off) = odd ? sl : l0;
+                            }
+                            if (val_o) {      // the odd lane's pixel
+                                *reinterpret_cast<uint4*>(oo) = odd ? h1 : sh;
+                                *reinterpret_cast<uint4*>(oo + d.out_lo_off) = odd ? l1 : sl;
+                            }
+                        }
                     } else if (d.out_mode == DISCO_OUT_ACT) {
                         // Stage the warp's 32 pixels x 16 channels in shared memory, then store row-wise: each
                         // store instruction writes 8 neighbouring pixels x 32 B (full sectors; one contiguous 512 B
@@ -585,6 +642,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     __syncwarp();
                     continue;
                 }
+                if (MODE == 4) {
+                    // ---- fused sub-pixel item: source 0 = 18 x 10 low-res patch, source 1 = column-parity planes (34 rows x 9) of the
+                    //      34 x 18 full-resolution window whose origin is (2*a0 - 1, 2*b0 - 1) ----
+                    if (lane == 0) {
+                        const uint32_t bar = smem_u32(&ctl->a_full[sa]);
+                        const int a0 = it.h0, b0 = it.w0;
+                        if (g.dbg & 2) {
+                            mbar_arrive(bar);
+                        } else if (sidx == 0) {
+                            mbar_arrive_expect_tx(bar, (uint32_t)(g.nparts * g.chunks) * 2880u);
+                            for (int part = 0; part < g.nparts; ++part)
+                                for (int chunk = 0; chunk < g.chunks; ++chunk)
+                                    tma_load_4d(stage + (uint32_t)part * g.a_part0 + (uint32_t)chunk * g.plane0, &g.tmap[part],
+                                                cofs + chunk * 8, b0 - 1, a0 - 1, it.img, bar);
+                        } else {
+                            mbar_arrive_expect_tx(bar, (uint32_t)(g.nparts * g.chunks) * (2u * 34u * 9u * 16u));
+                            const int hs = 2 * a0 - 1, wsx = 2 * b0 - 1;
+                            for (int part = 0; part < g.nparts; ++part)
+                                for (int chunk = 0; chunk < g.chunks; ++chunk) {
+                                    const uint32_t dst = stage + (uint32_t)part * g.a_part_bytes + (uint32_t)chunk * g.plane;
+                                    tma_load_4d(dst, &g.tmap[2 + part], cofs + chunk * 8, wsx, hs, it.img, bar);
+                                    tma_load_4d(dst + g.parplane, &g.tmap[2 + part], cofs + chunk * 8, wsx + 1, hs, it.img, bar);
+                                }
+                        }
+                    }
+                    __syncwarp();
+                    continue;
+                }
                 if (g.use_tma && upm == 0) {
                     // ---- TMA: one box per (chunk, part); out-of-image pixels arrive as zeros (= the conv padding) ----
                     if (lane == 0) {
@@ -651,7 +736,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     if (lane == 0) mbar_arrive(smem_u32(&ctl->a_full[sa]));
                     continue;
                 }
-                if (MODE != 2 && MODE != 3) {
+                if (MODE != 2 && MODE != 3 && MODE != 4) {
                     // Row-wise gather: the (column, chunk) a lane handles is the same for every patch row, so
                     // its shared/global offsets are computed once per stage and each row only adds its base.
                     constexpr int PH = (MODE == 0) ? 18 : 33;
@@ -731,18 +816,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     bulk_g2s(b_base + off, wp + off, (uint32_t)n, bar);
                 }
             } else {
-                int ib = 0;
+                int sb = 0;              // ring slot and wrap parity by counters (no divisions per slot)
+                uint32_t sb_par = 0;
                 for (int item = blockIdx.x; item < g.items; item += gridDim.x) {
-                    const int n_tile = item / g.m_tiles;
+                    const int n_tile = fast_div(item, g.fd_m_tiles);
                     const uint8_t* wp = reinterpret_cast<const uint8_t*>(d.wpack) +
                                         (size_t)n_tile * iters_per_tile * g.b_stage_bytes;
-                    for (int t = 0; t < iters_per_tile; ++t, ++ib) {
-                        const int sb = ib % g.SB;
-                        mbar_wait(smem_u32(&ctl->b_empty[sb]), ((uint32_t)(ib / g.SB) & 1u) ^ 1u);
+                    for (int t = 0; t < iters_per_tile; ++t) {
+                        mbar_wait(smem_u32(&ctl->b_empty[sb]), sb_par ^ 1u);
                         const uint32_t bar = smem_u32(&ctl->b_full[sb]);
-                        mbar_arrive_expect_tx(bar, (uint32_t)g.b_stage_bytes);
-                        bulk_g2s(b_base + sb * g.b_stage_bytes, wp + (size_t)t * g.b_stage_bytes,
-                                 (uint32_t)g.b_stage_bytes, bar);
+                        if (MODE == 4 && (g.dbg & 1)) {
+                            mbar_arrive(bar);
+                        } else {
+                            mbar_arrive_expect_tx(bar, (uint32_t)g.b_stage_bytes);
+                            bulk_g2s(b_base + sb * g.b_stage_bytes, wp + (size_t)t * g.b_stage_bytes,
+                                     (uint32_t)g.b_stage_bytes, bar);
+                        }
+                        if (++sb == g.SB) { sb = 0; sb_par ^= 1u; }
                     }
                 }
             }
@@ -833,14 +923,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const int sub_lo = g.by_sub ? mw : 0, sub_hi = g.by_sub ? mw + 1 : g.msub;
             for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++iacc, buf = (buf + 1 == g.nacc) ? 0 : buf + 1,
                      acc_par ^= (buf == 0), turn = (turn + 1 == g.nmma) ? 0 : turn + 1) {
-                if (mw >= g.nmma || (!g.by_sub && turn != mw)) continue;
+                if (mw >= g.nmma || (MODE != 4 && !g.by_sub && turn != mw)) continue;
                 if (mw == 0) TRACE(2, iacc, 0);
                 uint32_t wblk = 0;   // sub-pixel mode, resident weights: running weight-block index inside the N tile
                 (void)wblk;
                 mbar_wait(smem_u32(&ctl->acc_empty[buf]), acc_par ^ 1u);
                 tc_fence_after();
                 if (mw == 0) TRACE(2, iacc, 1);
-                const uint32_t td0 = tmem_d + (uint32_t)(buf * g.msub * g.acc_stride);
+                const uint32_t td0 = tmem_d + (uint32_t)(buf * ((MODE == 4) ? 4 : g.msub) * g.acc_stride);
                 const uint32_t td1 = td0 + (uint32_t)g.acc_stride;
                 for (int cb = 0; cb < g.ncb; ++cb) {
                     // wait for the MSUB patches of this channel block
@@ -860,7 +950,73 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     tc_fence_after();
                     if (cb == 0 && mw == 0) TRACE(2, iacc, 2);
                     const uint32_t first = (cb > 0) ? 1u : 0u;   // accumulate flag of the first MMA of the item
-                    if (MODE == 3) {
+                    if (MODE == 4) {
+                        // ---- fused sub-pixel item: four class accumulators (td0 + cls * acc_stride) share this stage.  TWO issuers:
+                        //      issuer `mw` owns the classes of output-row parity py = mw.  (tools/mma_rate4.cu: a satisfied mbarrier
+                        //      wait costs the issuing thread ~200 cycles and tcgen05.mma issue is serial in the thread, ~45 cycles
+                        //      each, so one issuer loses every wait; two issuers hide each other's waits until the shared-memory
+                        //      operand port, 44 cycles per MMA of this mix, is the limit.)  Weight slots hold nine blocks of
+                        //      64 * block_n bytes and are read by both issuers. ----
+                        const bool s1 = cb >= g.ncb0;
+                        const uint32_t blk16 = 4u * (uint32_t)d.block_n;
+                        const uint32_t accs = (uint32_t)g.acc_stride;
+                        const uint32_t py = (uint32_t)mw;
+                        const uint32_t tdp = td0 + 2u * py * accs;
+                        if (!s1) {
+                            const uint32_t ahi = (160u >> 4) | (1u << 14);
+                            const uint32_t part16 = (uint32_t)g.a_part0 >> 4;
+                            const uint32_t sa0 = (a_base >> 4) + (uint32_t)slot0 * a_stage16 + (((uint32_t)g.plane0 >> 4) << 16) + py * 10u;
+#pragma unroll
+                            for (int ty = 0; ty < 2; ++ty) {      // slot = low-res tap row ty of the four classes: [class][tx] (+ pad block)
+                                mbar_wait(bar_b_full + 8u * sb_slot, sb_phase);
+                                tc_fence_after();
+                                const uint32_t b16 = b_base16 + (uint32_t)sb_slot * b_stage16 + 4u * py * blk16;
+                                if (elect_one()) {
+                                    if (!(g.dbg & 8))
+#pragma unroll
+                                    for (int px = 0; px < 2; ++px) {
+                                        const uint32_t td = tdp + (uint32_t)px * accs;
+#pragma unroll
+                                        for (int tx = 0; tx < 2; ++tx) {
+                                            const uint32_t a16 = sa0 + (uint32_t)(ty * 10 + px + tx);
+                                            const uint32_t blo = b16 + (uint32_t)(px * 2 + tx) * blk16;
+                                            umma_f16_parts(td, a16, ahi, blo, b_hi, idesc2, (ty == 0 && tx == 0) ? first : 1u);
+                                            umma_f16_parts(td, a16 + part16, ahi, blo, b_hi, idesc, 1u);
+                                        }
+                                    }
+                                    umma_commit(bar_b_empty + 8u * sb_slot);
+                                }
+                                __syncwarp();
+                                if (++sb_slot == g.SB) { sb_slot = 0; sb_phase ^= 1u; }
+                            }
+                        } else {
+                            mbar_wait(bar_b_full + 8u * sb_slot, sb_phase);      // slot = the nine taps of this channel block
+                            tc_fence_after();
+                            const uint32_t b16 = b_base16 + (uint32_t)sb_slot * b_stage16;
+                            const uint32_t a0p = a0_16 + py * 9u;
+                            if (elect_one()) {
+                                if (!(g.dbg & 8))
+#pragma unroll
+                                for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                                    for (int kw = 0; kw < 3; ++kw) {
+                                        const uint32_t blo = b16 + (uint32_t)(kh * 3 + kw) * blk16;
+#pragma unroll
+                                        for (int px = 0; px < 2; ++px) {
+                                            const int c = px + kw;
+                                            const uint32_t a16 = a0p + (uint32_t)(c & 1) * par16 + (uint32_t)(kh * 9 + (c >> 1));
+                                            const uint32_t td = tdp + (uint32_t)px * accs;
+                                            umma_f16_parts(td, a16, a_hi, blo, b_hi, idesc2, 1u);   // source-0 stages come first: accumulate
+                                            umma_f16_parts(td, a16 + a_part16, a_hi, blo, b_hi, idesc, 1u);
+                                        }
+                                    }
+                                }
+                                umma_commit(bar_b_empty + 8u * sb_slot);
+                            }
+                            __syncwarp();
+                            if (++sb_slot == g.SB) { sb_slot = 0; sb_phase ^= 1u; }
+                        }
+                    } else if (MODE == 3) {
                         // ---- sub-pixel class: 4 pre-summed taps on a source-0 stage (18 x 10 low-res patch), all 9 taps on a
                         //      source-1 stage (stride-2 parity planes); weight blocks are consumed in packed order ----
                         const bool s1 = cb >= g.ncb0;
@@ -1034,6 +1190,10 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
                           d->precision == DISCO_PREC_BF16X3 && d->chain_c_out == 0 && (d->sub_py | d->sub_px) >= 0 && d->sub_py <= 1 &&
                           d->sub_px <= 1 && d->h_in % 2 == 0 && d->w_in % 2 == 0 && get_encode_tiled() != nullptr,
                       "conv: sub-pixel class needs a 3x3 stride-1 conv over (upsampled, plain) sources, c_blk 16, bf16x3 and TMA");
+    const bool fused = d->subpix == 2;   // all four classes per item (MODE 4)
+    if (fused)
+        DISCO_REQUIRE(d->wpack_stacked && d->block_n <= 64 && d->c_out <= d->block_n && d->out_mode == DISCO_OUT_ACT,
+                      "conv: the fused sub-pixel form needs one stacked N tile (c_out <= 64) and an activation output");
     DISCO_REQUIRE(((d->c_out + d->block_n - 1) / d->block_n) * d->block_n * 4 <= kBiasBytes, "conv: c_out %d too large", d->c_out);
     if (d->taps == 9) {
         DISCO_REQUIRE(d->h_out == (d->h_in - 1) / d->stride + 1 && d->w_out == (d->w_in - 1) / d->stride + 1,
@@ -1062,6 +1222,10 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     {
         const char* tr = getenv("DISCO_CONV_TRACE");
         g->trace = tr ? (long long*)strtoull(tr, nullptr, 0) : nullptr;
+        const char* dbg = getenv("DISCO_CONV_DBG");
+        g->dbg = dbg ? atoi(dbg) : 0;
+        const char* ds = getenv("DISCO_CONV_DIRECT_STORE");
+        g->direct = (ds && ds[0] == '1') ? 1 : 0;
     }
     g->ncb0 = d->src_c[0] / d->c_blk;
     g->ncb = g->ncb0 + d->src_c[1] / d->c_blk;
@@ -1072,6 +1236,8 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     g->plane0 = 0; g->a_part0 = 0;
     if (d->taps == 1) {
         g->PIX = 128; g->parplane = 0; g->sbo_a = 128;
+    } else if (fused) {
+        g->PIX = 34 * 18; g->parplane = 34 * 9 * 16; g->sbo_a = 2 * 9 * 16;   // 34 x 18 window as two column-parity planes
     } else if (d->subpix) {
         g->PIX = 33 * 17; g->parplane = 33 * 9 * 16; g->sbo_a = 2 * 9 * 16;   // source-1 stages: stride-2 geometry
     } else if (d->stride == 1) {
@@ -1119,19 +1285,20 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     g->a_part_bytes = g->chunks * plane;
     g->a_stage_bytes = ((g->nparts * g->a_part_bytes + 127) / 128) * 128;
     g->b_part_bytes = d->c_blk * d->block_n * 2;
-    g->b_stage_bytes = g->nparts * g->b_part_bytes;
+    g->b_stage_bytes = fused ? 9 * 64 * d->block_n : g->nparts * g->b_part_bytes;   // fused: slots of nine weight blocks
     g->n_tiles = (d->c_out + d->block_n - 1) / d->block_n;
 
     const int stage_region = d->chain_c_out > 0 ? 0 : kStageBytes;
     const int budget = 224 * 1024 - kCtlBytes - kBiasBytes - stage_region - g->scratch_total;
-    g->w_iters = d->subpix ? g->ncb0 * 4 + (g->ncb - g->ncb0) * 9 : g->ncb * d->taps;
+    g->w_iters = fused ? g->ncb0 * 2 + (g->ncb - g->ncb0)
+                       : d->subpix ? g->ncb0 * 4 + (g->ncb - g->ncb0) * 9 : g->ncb * d->taps;
     g->w_bytes = g->w_iters * g->b_stage_bytes;
     // MSUB = 2 (256-pixel items) when the N tile leaves room for double-buffered accumulators and the
     // image is wide enough; it halves the weight stream per MAC.
     const int h_grid = d->subpix ? d->h_out / 2 : d->h_out, w_grid = d->subpix ? d->w_out / 2 : d->w_out;   // tiled pixel grid
     const bool wide = (d->taps == 1) ? (g->total_pix >= 256) : (w_grid >= 16);
     const int acc_cols = (d->wpack_stacked ? 2 : 1) * d->block_n;   // TMEM columns one accumulator writes
-    g->msub = (wide && 4 * acc_cols <= 512) ? 2 : 1;
+    g->msub = (wide && 4 * acc_cols <= 512 && !fused) ? 2 : 1;
     {
         // Wave quantisation: with few, large items (N >= 128 tiles at 32^2 / 16^2 resolution) the last round of a launch leaves
         // most SMs idle (e.g. 320 items of two sub-tiles on 148 SMs = 2.16 rounds -> 3).  One sub-tile per item lowers the number of
@@ -1152,7 +1319,7 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
             if (force == 0 && items2 < sms) g->msub = 1;
         }
     }
-    g->stationary = (g->n_tiles == 1 && g->w_bytes + 3 * g->a_stage_bytes <= budget) ? 1 : 0;
+    g->stationary = (g->n_tiles == 1 && g->w_bytes + 3 * g->a_stage_bytes <= budget && !fused) ? 1 : 0;
     {
         // tuning knob: weight sets larger than DISCO_CONV_NOSTAT_MAXW bytes are streamed even if they would fit (a big resident
         // set leaves only a shallow A-stage ring: conv8_1 = 110 KB)
@@ -1171,16 +1338,17 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
         stationary_by_sub = (d->chain_c_out == 0 && g->msub == 2 && acc_cols <= 128 && sa_fit >= 4 && sa_fit / 2 < g->ncb);
         if (!stationary_by_sub) g->msub = 1;
     }
-    g->nacc = (2 * g->msub * acc_cols <= 512) ? 2 : 1;
+    const int nsub = fused ? 4 : g->msub;   // accumulators per TMEM buffer
+    g->nacc = (2 * nsub * acc_cols <= 512) ? 2 : 1;
     g->nmma = 1;
     if (g->stationary && g->nacc == 2) {
         g->nmma = kMmaWarps;
         if (kMaxAcc * g->msub * ((acc_cols + 31) / 32 * 32) <= 512) g->nacc = kMaxAcc;   // two buffers per issuer
     }
     g->acc_stride = (acc_cols + 31) / 32 * 32;
-    if (g->nacc * g->msub * g->acc_stride > 512) g->acc_stride = acc_cols;
+    if (g->nacc * nsub * g->acc_stride > 512) g->acc_stride = acc_cols;
     int cols = 32;
-    while (cols < g->nacc * g->msub * g->acc_stride) cols *= 2;
+    while (cols < g->nacc * nsub * g->acc_stride) cols *= 2;
     g->tmem_cols = cols;
     int ctas_per_sm = 1;
     g->chain = d->chain_c_out > 0 ? 1 : 0;
@@ -1218,6 +1386,13 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
     } else {
         int sa = 2 * g->msub;  // current + next channel block
         if (sa < 4 && 4 * g->a_stage_bytes <= budget / 3) sa = 4;
+        if (fused) {
+            // 39 KB stages carrying 16 (source 0) / 36 (source 1) MMA pairs each: three slots = two stages of lookahead; the rest
+            // of shared memory is the weight ring (8 / 16 KB slots).  Tuning knob: DISCO_CONV_FUSED_SA.
+            static int fsa = -1;
+            if (fsa < 0) { const char* e = getenv("DISCO_CONV_FUSED_SA"); fsa = e ? atoi(e) : 0; }
+            sa = (fsa >= 2 && fsa <= kMaxStages) ? fsa : 3;
+        }
         int sb = (budget - sa * g->a_stage_bytes) / g->b_stage_bytes;
         while (sb < 2 && sa > g->msub) {
             --sa;
@@ -1241,6 +1416,7 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
         g->nmma = 2;
         g->SA &= ~1;   // even ring: slot parity == sub-tile, i.e. one consumer per slot
     }
+    if (fused) { g->nmma = 2; g->nrings = 1; g->by_sub = 0; }   // two issuers, one per output-row parity, sharing every stage
     g->SAr = g->SA / g->nrings;
     g->nprod = kProdWarps / g->nrings;
     if (g->nprod > g->SAr) g->nprod = g->SAr;
@@ -1263,7 +1439,7 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
             const uint16_t* b1 = reinterpret_cast<const uint16_t*>(d->src[1]) + (part ? d->src_lo_off[1] : 0);
             DISCO_REQUIRE(((reinterpret_cast<uintptr_t>(b0) | reinterpret_cast<uintptr_t>(b1)) & 15) == 0, "conv: sources not 16-byte aligned");
             const bool ok = make_tmap4(&g->tmap[part], b0, d->src_c[0], d->w_in / 2, d->h_in / 2, d->n, 10, 18, 1) &&
-                            make_tmap4(&g->tmap[2 + part], b1, d->src_c[1], d->w_in, d->h_in, d->n, 18, 33, 2);
+                            make_tmap4(&g->tmap[2 + part], b1, d->src_c[1], d->w_in, d->h_in, d->n, 18, fused ? 34 : 33, 2);
             DISCO_REQUIRE(ok, "conv: cuTensorMapEncodeTiled failed (sub-pixel class)");
         }
     } else if (g->use_tma) {
@@ -1329,6 +1505,7 @@ int disco_conv_tc_launch(const disco_conv_desc* d, void* stream) {
     if (rc < 0) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     if (d->taps == 1) return launch_mode<2>(g, s);
+    if (d->subpix == 2) return launch_inst<4, 1, 2>(g, s);
     if (d->subpix) return g.d.wpack_stacked ? launch_inst<3, 1, 2>(g, s) : launch_inst<3, 1, 3>(g, s);
     return d->stride == 1 ? launch_mode<0>(g, s) : launch_mode<1>(g, s);
 }

@@ -15,7 +15,7 @@ import torch
 
 from . import ops
 from ._lib import PREC_BF16X3, PREC_FP16, FusionDesc
-from .plan import ConvPlan, fold_bn, pack_chain, pack_conv, pack_conv_subpix
+from .plan import ConvPlan, fold_bn, pack_chain, pack_conv, pack_conv_subpix, pack_conv_subpix_fused
 
 # Output-parity ("sub-pixel") decomposition of the four upsample-concat convs (conv5_1 .. conv8_1): 4 launches, one per parity
 # class, with 4 instead of 9 taps on the upsampled channels (-37 % MMAs on those layers).  Parity-green (tests/test_conv_gpu.py)
@@ -25,6 +25,13 @@ from .plan import ConvPlan, fold_bn, pack_chain, pack_conv, pack_conv_subpix
 # per-class grids quantise badly over 148 SMs.  The profitable form keeps the four class accumulators of one tile in TMEM and
 # shares one staged window.  DISCO_B200_SUBPIX=1 enables it.
 USE_SUBPIX = os.environ.get("DISCO_B200_SUBPIX", "0") == "1"
+
+# Fused form (conv.h subpix == 2, conv_tc.cu MODE 4): ONE launch whose work items keep the four class accumulators of a low-res tile
+# in TMEM and share every staged operand -- for the C_out <= 64 layers (conv7_1, conv8_1), where TMEM holds four stacked
+# accumulators.  ON by default (measured round 2, B = 16: conv8_1 1.13 -> 0.69 ms, conv7_1 0.71 -> 0.53 ms);
+# DISCO_B200_FUSED_SUBPIX=0 disables it, a comma list selects layers.
+_fused_env = os.environ.get("DISCO_B200_FUSED_SUBPIX", "c7_1,c8_1")
+FUSED_SUBPIX_LAYERS = set() if _fused_env in ("0", "none", "") else set(x for x in _fused_env.split(",") if x)
 
 PRECISIONS = {"bf16x3": PREC_BF16X3, "fp16": PREC_FP16}
 
@@ -93,7 +100,9 @@ def build_decoder_plans(get: Getter, p: str, precision: int) -> Dict[str, ConvPl
         c_blk = int(os.environ.get("DISCO_CBLK_" + name.upper(), "0")) or c_blk     # tuning hook (K-stage width of one layer)
         w, b = _conv_bn(get, p + conv, p + bn)
         P[name] = pack_conv(w, b, src_channels=srcs, relu=True, precision=precision, name=p + conv, c_blk=c_blk)
-        if USE_SUBPIX and len(srcs) == 2 and precision == PREC_BF16X3 and name in subpix:
+        if name in FUSED_SUBPIX_LAYERS and len(srcs) == 2 and precision == PREC_BF16X3 and w.shape[0] <= 64:
+            P[name + "/fused"] = pack_conv_subpix_fused(w, b, src_channels=srcs, relu=True, precision=precision, name=p + conv)
+        elif USE_SUBPIX and len(srcs) == 2 and precision == PREC_BF16X3 and name in subpix:
             P[name + "/sub"] = [pack_conv_subpix(w, b, src_channels=srcs, py=py, px=px, relu=True, precision=precision, name=p + conv)
                                 for py in (0, 1) for px in (0, 1)]
 
@@ -245,6 +254,8 @@ class Workspace:
                 x2_dec = b["x2f"]
         def up(name, srcs, out, hh, ww):
             """conv(cat(nearest_up2(srcs[0]), srcs[1])): one launch, or one per output-parity class (engine.USE_SUBPIX)."""
+            if name + "/fused" in dec and hh % 2 == 0 and ww % 2 == 0:
+                return [mk(dec[name + "/fused"], srcs, [1, 0], out, hh, ww)]
             if name + "/sub" in dec and hh % 2 == 0 and ww % 2 == 0:
                 return [mk(pl, srcs, [1, 0], out, hh, ww) for pl in dec[name + "/sub"]]
             return [mk(dec[name], srcs, [1, 0], out, hh, ww)]

@@ -108,6 +108,10 @@ class ConvCall:
             if list(ups) != [1, 0] or len(srcs) != 2:
                 raise ValueError(f"conv[{plan.name}]: a sub-pixel class plan needs (upsampled, plain) sources")
             d.subpix, d.sub_py, d.sub_px = 1, int(plan.subpix[0]), int(plan.subpix[1])
+        if plan.fused_subpix:             # the four classes of every low-res tile in one work item
+            if list(ups) != [1, 0] or len(srcs) != 2:
+                raise ValueError(f"conv[{plan.name}]: a fused sub-pixel plan needs (upsampled, plain) sources")
+            d.subpix = 2
         self.desc = d
         self.flops = fpp * n * d.h_out * d.w_out // (4 if plan.subpix is not None else 1)
         self.set_output(out, out_split)

@@ -68,6 +68,7 @@ class ConvPlan:
     name: str = ""
     flops_per_pixel: int = field(default=0)
     subpix: Optional[tuple] = None   # (py, px): this plan computes ONE output-parity class of an upsample-concat conv (conv.h subpix)
+    fused_subpix: bool = False       # all four classes per work item (conv.h subpix == 2, pack_conv_subpix_fused)
 
 
 def pack_conv(wf: torch.Tensor, bf: torch.Tensor, *, src_channels, stride: int = 1, relu: bool = True,
@@ -184,3 +185,48 @@ def pack_conv_subpix(wf: torch.Tensor, bf: torch.Tensor, *, src_channels, py: in
     return ConvPlan(taps=9, stride=1, c_in=c_in_real, c_out=c_out, c_blk=c_blk, block_n=block_n, relu=relu, precision=precision,
                     wpack=wpack.reshape(-1), bias=bias, wref=None, name=name + f"[py{py}px{px}]", stacked=stacked,
                     flops_per_pixel=2 * 9 * c_in_real * c_out, subpix=(py, px))
+
+
+def pack_conv_subpix_fused(wf: torch.Tensor, bf: torch.Tensor, *, src_channels, relu: bool = True,
+                           precision: int = PREC_BF16X3, name: str = "") -> ConvPlan:
+    """Weights of the FUSED sub-pixel form (conv.h subpix == 2; C_out <= 64): one work item computes the four output-parity
+    classes of a 16 x 8 low-res tile.  The image is a stream of slots of nine blocks (block = [chunk 2][hi rows | lo rows][8 ch],
+    64 * block_n bytes), in the order the MMA issuers consume them:
+      source-0 channel block:  two slots, one per low-res tap row ty: [class 2*py + px][tx] pre-summed taps + one zero block
+                               (class (py, px), tap (ty, tx) multiplies the low-res pixel at window row py + ty, column px + tx)
+      source-1 channel block:  one slot = the nine 3 x 3 taps (shared by the four classes)"""
+    assert precision == PREC_BF16X3 and wf.shape[2:] == (3, 3) and len(src_channels) == 2
+    c_out, c_in_real = wf.shape[0], wf.shape[1]
+    c0, c1 = int(src_channels[0]), int(src_channels[1])
+    assert c0 + c1 == c_in_real and c0 % 16 == 0 and c1 % 16 == 0 and c0 > 0 and c1 > 0
+    block_n = (c_out + 15) // 16 * 16
+    assert block_n <= 64, "fused sub-pixel form: C_out <= 64 (four stacked class accumulators must fit TMEM)"
+    dev = wf.device
+    w = torch.zeros(block_n, c_in_real, 3, 3, dtype=torch.float32, device=dev)
+    w[:c_out] = wf.detach().float()
+    bias = torch.zeros(block_n, dtype=torch.float32, device=dev)
+    bias[:c_out] = bf
+
+    def blocks_of(wt):   # [block_n, C, taps...] -> stacked bf16 blocks [C/16, taps..., chunk, part, n, 8]
+        C = wt.shape[1]
+        t = wt.reshape(block_n, C // 16, 2, 8, -1).permute(1, 4, 2, 0, 3).contiguous()    # [cb, tap, chunk, n, 8]
+        hi, lo = split_bf16(t)
+        return torch.stack((hi, lo), dim=3).contiguous()                                   # [cb, tap, chunk, part, n, 8]
+
+    cls_w = []
+    for py in (0, 1):
+        for px in (0, 1):
+            w0 = torch.zeros(block_n, c0, 3, 3, dtype=torch.float32, device=dev)
+            for kh in range(3):
+                for kw in range(3):
+                    w0[:, :, _SUBPIX_MAP[py][kh], _SUBPIX_MAP[px][kw]] += w[:, :c0, kh, kw]
+            cls_w.append(blocks_of(w0[:, :, py:py + 2, px:px + 2].contiguous()))            # [cb, 4, ...]
+    s0 = torch.stack(cls_w, dim=1)                                                          # [cb0, class, 4 taps (ty, tx), chunk, part, n, 8]
+    s0 = s0.view(s0.shape[0], 4, 2, 2, *s0.shape[3:]).permute(0, 2, 1, 3, 4, 5, 6, 7).contiguous()   # [cb0, ty, class, tx, ...]
+    s0 = s0.view(s0.shape[0], 2, 8, *s0.shape[4:])
+    s0 = torch.cat((s0, torch.zeros_like(s0[:, :, :1])), dim=2)                             # [cb0, ty, 8 blocks + pad, ...]
+    s1 = blocks_of(w[:, c0:].contiguous())                                                  # [cb1, 9 taps, ...]
+    wpack = torch.cat((s0.reshape(-1), s1.reshape(-1))).view(torch.int16)
+    return ConvPlan(taps=9, stride=1, c_in=c_in_real, c_out=c_out, c_blk=16, block_n=block_n, relu=relu, precision=precision,
+                    wpack=wpack.reshape(-1), bias=bias, wref=None, name=name + "[subpix x4]", stacked=True,
+                    flops_per_pixel=2 * 9 * c_in_real * c_out, fused_subpix=True)
