@@ -55,7 +55,11 @@ struct disco_conv_desc {
      * (2a + sub_py, 2b + sub_px); wpack then holds, per 16-channel block, the 4 pre-summed taps of that class for source 0
      * (ascending tap index inside the 3x3 window: rows sub_py..sub_py+1, columns sub_px..sub_px+1) and all 9 taps for source 1
      * (see disconet_b200/plan.py::pack_conv_subpix).  Needs taps 9, stride 1, src_up = {1, 0}, c_blk 16, bf16x3.  Four launches
-     * (one per class) replace one launch with src_up[0] = 1 and execute 4/9 of its source-0 MMAs. */
+     * (one per class) replace one launch with src_up[0] = 1 and execute 4/9 of its source-0 MMAs.
+     * subpix = 2 is the FUSED form (C_out <= 64, one stacked N tile, activation output): one launch whose work items are 16 x 8
+     * tiles of LOW-RES positions and keep the four class accumulators side by side in TMEM, so every staged operand (the low-res
+     * patch of source 0, the 34 x 18 window of source 1) is shared by the four classes; wpack is then the slot stream of
+     * disconet_b200/plan.py::pack_conv_subpix_fused and sub_py / sub_px are ignored. */
     int subpix, sub_py, sub_px;
 };
 

@@ -211,12 +211,21 @@ struct __align__(8) SmemCtl {
 };
 static_assert(sizeof(SmemCtl) <= kCtlBytes, "control block");
 
-__device__ __forceinline__ uint4 pack_bf16x8(const float* v) {
-    uint32_t w[4];
+// 16 fp32 values -> bf16 hi (two uint4) and bf16 lo = bf16(v - hi) (two uint4) with the packed two-at-a-time converter: 6
+// instructions per value pair instead of ~10 (round-2 trace: the bias/ReLU/split arithmetic of one 16-channel chunk took ~830
+// cycles of an epilogue warp, the longest leg of the C_out <= 64 layers' epilogue).  Same round-to-nearest-even results.
+__device__ __forceinline__ void split_pack16(const float* v, uint4& h0, uint4& h1, uint4& l0, uint4& l1) {
+    uint32_t hw[8], lw[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-        w[i] = (uint32_t)f32_to_bf16_bits(v[2 * i]) | ((uint32_t)f32_to_bf16_bits(v[2 * i + 1]) << 16);
-    return make_uint4(w[0], w[1], w[2], w[3]);
+    for (int i = 0; i < 8; ++i) {
+        uint32_t p, q;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(v[2 * i + 1]), "f"(v[2 * i]));   // upper half <- first source
+        const float le = v[2 * i] - __uint_as_float(p << 16), lo_ = v[2 * i + 1] - __uint_as_float(p & 0xffff0000u);
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q) : "f"(lo_), "f"(le));
+        hw[i] = p; lw[i] = q;
+    }
+    h0 = make_uint4(hw[0], hw[1], hw[2], hw[3]); h1 = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+    l0 = make_uint4(lw[0], lw[1], lw[2], lw[3]); l1 = make_uint4(lw[4], lw[5], lw[6], lw[7]);
 }
 
 struct Item {
@@ -363,6 +372,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 const uint32_t t_lane = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) +
                                         (uint32_t)((buf * nsub + sub) * g.acc_stride);
                 const int nchunks = d.block_n / 16;
+                // staged stores: pass r writes pixel r*16 + (lane & 15), 16-byte piece lane >> 4 -- element offsets / validity per pass
+                // depend on the item only, not on the channel chunk
+                long long st_off[2];
+                bool st_ok[2];
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const int m2 = (warp & 3) * 32 + r * 16 + (lane & 15);
+                    long long pix2;
+                    if (MODE != 2) {
+                        int oh, ow;
+                        out_coords<MODE>(g, it, sub, m2, oh, ow);
+                        st_ok[r] = (oh < d.h_out) && (ow < d.w_out);
+                        pix2 = ((long long)it.img * d.h_out + oh) * d.w_out + ow;
+                    } else {
+                        pix2 = it.p0 + sub * 128 + m2;
+                        st_ok[r] = pix2 < g.total_pix;
+                    }
+                    st_off[r] = pix2 * d.c_out + (lane >> 4) * 8;
+                }
                 uint32_t nxt[16], nxt2[16];
                 tmem_ld16(t_lane, nxt);
                 if (STACKED) tmem_ld16(t_lane + (uint32_t)d.block_n, nxt2);
@@ -370,6 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     uint32_t raw[16];
                     tmem_ld_wait();
                     if (warp == 0 && sub == 0 && j == 0) TRACE(0, iacc, 3);
+                    if (warp == 0 && sub == 0 && j == 1) TRACE(3, iacc, 3);
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
                         raw[i] = STACKED ? __float_as_uint(__uint_as_float(nxt[i]) + __uint_as_float(nxt2[i])) : nxt[i];
@@ -392,17 +421,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     if (g.chain) {
                         // chained 1x1: the ReLU'd tile becomes the A operand of a second MMA -- write bf16 hi/lo
                         // straight into the UMMA K-major layout [part][channel/8][pixel][8 ch] of this group's A2 buffer
-                        float lo[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) lo[i] = v[i] - bf16_bits_to_f32(f32_to_bf16_bits(v[i]));
+                        uint4 ph0, ph1, pl0, pl1;
+                        split_pack16(v, ph0, ph1, pl0, pl1);
                         uint8_t* a2 = smem_raw + (a2_base - smem_base) + egrp * g.a2_bytes;
                         const int part_b = (d.block_n / 8) * 2048;
                         uint4* dsth = reinterpret_cast<uint4*>(a2 + (2 * j) * 2048 + m * 16);
-                        dsth[0] = pack_bf16x8(v);
-                        dsth[128] = pack_bf16x8(v + 8);              // next channel chunk: +2048 B
+                        dsth[0] = ph0;
+                        dsth[128] = ph1;              // next channel chunk: +2048 B
                         uint4* dstl = reinterpret_cast<uint4*>(a2 + part_b + (2 * j) * 2048 + m * 16);
-                        dstl[0] = pack_bf16x8(lo);
-                        dstl[128] = pack_bf16x8(lo + 8);
+                        dstl[0] = pl0;
+                        dstl[128] = pl1;
                     } else if (g.direct && d.out_mode == DISCO_OUT_ACT && SPLIT) {
                         // Register-direct stores (no shared-memory staging): a lane holds one pixel's 16 channels = one 32-byte
                         // sector per plane.  Lane pairs swap halves (one shuffle per plane) so that every store instruction writes
@@ -426,10 +454,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                                 pix_o = it.p0 + sub * 128 + mo; val_o = pix_o < g.total_pix;
                             }
                         }
-                        float lo[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) lo[i] = v[i] - bf16_bits_to_f32(f32_to_bf16_bits(v[i]));
-                        const uint4 h0 = pack_bf16x8(v), h1 = pack_bf16x8(v + 8), l0 = pack_bf16x8(lo), l1 = pack_bf16x8(lo + 8);
+                        uint4 h0, h1, l0, l1;
+                        split_pack16(v, h0, h1, l0, l1);
                         uint4 sh = odd ? h0 : h1, sl = odd ? l0 : l1;       // even lanes give away their upper half, odd lanes their lower half
                         sh.x = __shfl_xor_sync(0xffffffffu, sh.x, 1); sh.y = __shfl_xor_sync(0xffffffffu, sh.y, 1);
                         sh.z = __shfl_xor_sync(0xffffffffu, sh.z, 1); sh.w = __shfl_xor_sync(0xffffffffu, sh.w, 1);
@@ -454,11 +480,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         uint8_t* st = smem_raw + kCtlBytes + kBiasBytes + warp * kStagePerWarp;
                         uint4 h0v, h1v, l0v, l1v;
                         if (SPLIT) {
-                            float lo[16];
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) lo[i] = v[i] - bf16_bits_to_f32(f32_to_bf16_bits(v[i]));
-                            h0v = pack_bf16x8(v); h1v = pack_bf16x8(v + 8);
-                            l0v = pack_bf16x8(lo); l1v = pack_bf16x8(lo + 8);
+                            split_pack16(v, h0v, h1v, l0v, l1v);
                         } else {
                             uint32_t w[8];
 #pragma unroll
@@ -467,11 +489,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                             h0v = make_uint4(w[0], w[1], w[2], w[3]); h1v = make_uint4(w[4], w[5], w[6], w[7]);
                             l0v = h0v; l1v = h1v;
                         }
+                        if (warp == 0 && sub == 0 && j == 0) TRACE(3, iacc, 0);
                         __syncwarp();   // previous chunk's read-back is done
                         uint4* row = reinterpret_cast<uint4*>(st + lane * kStageRow);
                         row[0] = h0v; row[1] = h1v;
                         if (SPLIT) { row[2] = l0v; row[3] = l1v; }
                         __syncwarp();
+                        if (warp == 0 && sub == 0 && j == 0) TRACE(3, iacc, 1);
                         if (nb < d.c_out) {
 #pragma unroll
                             for (int r = 0; r < 2; ++r) {   // 2 passes x 16 pixels x 2 pieces of 16 B
@@ -479,26 +503,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                                 // 8 rows at the 80-byte row pitch = 8 distinct 4-bank groups (the (lane >> 1, lane & 1) mapping was a
                                 // 2-way conflict: round-2 source view, 2x the ideal wavefronts on these four loads)
                                 const int px = r * 16 + (lane & 15), piece = lane >> 4;
-                                const int m2 = (warp & 3) * 32 + px;
-                                bool ok;
-                                long long pix2;
-                                if (MODE != 2) {
-                                    int oh, ow;
-                                    out_coords<MODE>(g, it, sub, m2, oh, ow);
-                                    ok = (oh < d.h_out) && (ow < d.w_out);
-                                    pix2 = ((long long)it.img * d.h_out + oh) * d.w_out + ow;
-                                } else {
-                                    pix2 = it.p0 + sub * 128 + m2;
-                                    ok = pix2 < g.total_pix;
-                                }
-                                if (ok) {
+                                if (st_ok[r]) {
                                     const uint4* srow = reinterpret_cast<const uint4*>(st + px * kStageRow);
-                                    uint16_t* o = reinterpret_cast<uint16_t*>(d.out[0]) + pix2 * d.c_out + nb + piece * 8;
+                                    uint16_t* o = reinterpret_cast<uint16_t*>(d.out[0]) + st_off[r] + nb;
                                     *reinterpret_cast<uint4*>(o) = srow[piece];
                                     if (SPLIT) *reinterpret_cast<uint4*>(o + d.out_lo_off) = srow[2 + piece];
                                 }
                             }
                         }
+                        if (warp == 0 && sub == 0 && j == 0) TRACE(3, iacc, 2);
                     } else if (valid) {
                         const int c1 = d.c_out - d.out_split;
 #pragma unroll
@@ -531,21 +544,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 const uint32_t t2 = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) +
                                     (uint32_t)(g.acc2_col + egrp * g.acc2_stride);
                 const int c1 = d.chain_c_out - d.out_split;
-                for (int j = 0; j < g.chain_bn / 16; ++j) {
-                    uint32_t r0[16], r1[16];
-                    tmem_ld16(t2 + (uint32_t)(j * 16), r0);
-                    tmem_ld16(t2 + (uint32_t)(g.chain_bn + j * 16), r1);   // stacked: columns [N2, 2*N2) = A2_hi * W2_lo
+                const int nch2 = g.chain_bn / 16;
+                uint32_t n0[16], n1[16];
+                tmem_ld16(t2, n0);
+                tmem_ld16(t2 + (uint32_t)g.chain_bn, n1);                  // stacked: columns [N2, 2*N2) = A2_hi * W2_lo
+                for (int j = 0; j < nch2; ++j) {
+                    float r0[16];
                     tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) r0[i] = __uint_as_float(n0[i]) + __uint_as_float(n1[i]);
+                    if (j + 1 < nch2) {      // next chunk's TMEM reads overlap this chunk's bias add and stores
+                        tmem_ld16(t2 + (uint32_t)((j + 1) * 16), n0);
+                        tmem_ld16(t2 + (uint32_t)(g.chain_bn + (j + 1) * 16), n1);
+                    }
                     if (ok) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const int c = j * 16 + 4 * q;
                             if (c >= d.chain_c_out) continue;
                             const float4 b4 = *reinterpret_cast<const float4*>(s_bias + kBias2Off + c);
-                            float o4[4] = {__uint_as_float(r0[4 * q]) + __uint_as_float(r1[4 * q]) + b4.x,
-                                           __uint_as_float(r0[4 * q + 1]) + __uint_as_float(r1[4 * q + 1]) + b4.y,
-                                           __uint_as_float(r0[4 * q + 2]) + __uint_as_float(r1[4 * q + 2]) + b4.z,
-                                           __uint_as_float(r0[4 * q + 3]) + __uint_as_float(r1[4 * q + 3]) + b4.w};
+                            float o4[4] = {r0[4 * q] + b4.x, r0[4 * q + 1] + b4.y, r0[4 * q + 2] + b4.z, r0[4 * q + 3] + b4.w};
                             if (d.chain_relu) {
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) o4[i] = fmaxf(o4[i], 0.f);

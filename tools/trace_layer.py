@@ -26,4 +26,4 @@ for name in sys.argv[1:]:
     print("item | epi: wait_start got_acc done first_ld_done | mma: wait_accempty got start_issue committed | prod0(stage): wait_empty got issued landed")
     for i in range(12):
         f = lambda r: " ".join(f"{(x - t0) if x > 0 else -1:7d}" for x in t[r, i].tolist())
-        print(f"{i:3d} | {f(0)} | {f(2)} | {f(1)}")
+        print(f"{i:3d} | {f(0)} | {f(2)} | {f(1)}" + (f" | epi detail (chunk 0 math done, staged, stored; chunk 1 ready): {f(3)}" if (t[3, i] > 0).any() else ""))
