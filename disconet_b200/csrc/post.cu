@@ -47,11 +47,7 @@ __device__ __forceinline__ double poly_area_signed(const double* x, const double
 // local memory and the kernel moved 2.5 GB through L2 per 80 agents (round-2 ncu capture).
 constexpr int kClipStride = 64;
 struct ClipScratch {
-    double* base;   // &scratch[threadIdx.x]; arrays sx, sy, ox, oy of 8 doubles each at stride kClipStride
-    __device__ __forceinline__ double& sx(int i) const { return base[(i) * kClipStride]; }
-    __device__ __forceinline__ double& sy(int i) const { return base[(8 + i) * kClipStride]; }
-    __device__ __forceinline__ double& ox(int i) const { return base[(16 + i) * kClipStride]; }
-    __device__ __forceinline__ double& oy(int i) const { return base[(24 + i) * kClipStride]; }
+    double* base;   // &scratch[threadIdx.x]; two vertex lists (x[8], y[8] each) at stride kClipStride
 };
 
 __device__ double quad_intersection_area(const double* P, const double* Q, const ClipScratch& w) {
@@ -67,35 +63,44 @@ __device__ double quad_intersection_area(const double* P, const double* Q, const
         t = qx[1]; qx[1] = qx[3]; qx[3] = t; t = qy[1]; qy[1] = qy[3]; qy[3] = t;
     }
     int n = 4;
+    // two vertex lists in the thread's shared-memory scratch, used alternately as source and destination of a clip pass
+    double* cur = w.base;                          // x at [i], y at [8 + i] (stride kClipStride)
+    double* nxt = w.base + 16 * kClipStride;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { w.sx(i) = px[i]; w.sy(i) = py[i]; }
+    for (int i = 0; i < 4; ++i) { cur[i * kClipStride] = px[i]; cur[(8 + i) * kClipStride] = py[i]; }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         if (n <= 0) break;
         const double ax = qx[e], ay = qy[e], bx = qx[(e + 1) & 3], by = qy[(e + 1) & 3];
+        double sjx_c = 0.0, sjy_c = 0.0, de_c = 0.0;
         int m = 0;
-        for (int i = 0; i < n; ++i) {
-            const int j = (i + 1 == n) ? 0 : i + 1;
-            const double six = w.sx(i), siy = w.sy(i), sjx = w.sx(j), sjy = w.sy(j);
-            const double ds = cross3(ax, ay, bx, by, six, siy);
-            const double de = cross3(ax, ay, bx, by, sjx, sjy);
+        // (the end vertex of step i is the start vertex of step i + 1: its coordinates and its cross product are carried over
+        //  instead of being re-read and re-evaluated -- same expressions on the same inputs, so the same bits)
+        double six = cur[0], siy = cur[8 * kClipStride];
+        double ds = cross3(ax, ay, bx, by, six, siy);
+        const double s0x = six, s0y = siy, d0 = ds;
+        for (int i = 0; i < n; ++i, six = sjx_c, siy = sjy_c, ds = de_c) {
+            const bool last = i + 1 == n;
+            const double sjx = last ? s0x : cur[(i + 1) * kClipStride], sjy = last ? s0y : cur[(8 + i + 1) * kClipStride];
+            const double de = last ? d0 : cross3(ax, ay, bx, by, sjx, sjy);
+            sjx_c = sjx; sjy_c = sjy; de_c = de;
             const bool in_s = ds >= 0.0, in_e = de >= 0.0;
-            if (in_s && m < 8) { w.ox(m) = six; w.oy(m) = siy; ++m; }
+            if (in_s && m < 8) { nxt[m * kClipStride] = six; nxt[(8 + m) * kClipStride] = siy; ++m; }
             if (in_s != in_e && m < 8) {
                 const double t = ds / dsub(ds, de);
-                w.ox(m) = dadd(six, dmul(t, dsub(sjx, six)));
-                w.oy(m) = dadd(siy, dmul(t, dsub(sjy, siy)));
+                nxt[m * kClipStride] = dadd(six, dmul(t, dsub(sjx, six)));
+                nxt[(8 + m) * kClipStride] = dadd(siy, dmul(t, dsub(sjy, siy)));
                 ++m;
             }
         }
         n = m;
-        for (int i = 0; i < n; ++i) { w.sx(i) = w.ox(i); w.sy(i) = w.oy(i); }
+        double* tmp = cur; cur = nxt; nxt = tmp;
     }
     if (n < 3) return 0.0;
     double s = 0.0;   // shoelace in index order (poly_area_signed)
     for (int i = 0; i < n; ++i) {
         const int j = (i + 1 == n) ? 0 : i + 1;
-        s = dadd(s, dsub(dmul(w.sx(i), w.sy(j)), dmul(w.sx(j), w.sy(i))));
+        s = dadd(s, dsub(dmul(cur[i * kClipStride], cur[(8 + j) * kClipStride]), dmul(cur[j * kClipStride], cur[(8 + i) * kClipStride])));
     }
     return fabs(dmul(0.5, s));
 }
@@ -186,6 +191,9 @@ __global__ void __launch_bounds__(1024) nms_sort_kernel(const CT* __restrict__ c
 //    it: round 2's first version launched 32 x 32 x n mostly-empty CTAs and spent 0.8 ms per 80 agents on their launch slots).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kMaskBlocks = 96;   // >= the 91 block pairs of ~800 candidates: one pair per CTA in the common case
+// (Measured and rejected in round 2: dealing the (agent, block pair) items of ALL agents round-robin over one 1184-CTA grid -- K varies
+//  between agents, mean ~700, largest 2048 -- 317 -> 346 us; a separating-axis pre-check before the clip -- the candidates that
+//  pass the bounds test are the six anchors of neighbouring cells and nearly all truly intersect -- 346 -> 375 us.)
 
 __global__ void __launch_bounds__(64) nms_mask_kernel(const double* __restrict__ s_corners, const int* __restrict__ s_count,
                                                       int kmax, int words, double thr,
@@ -249,55 +257,85 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const double* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// 3. greedy scan (postprocess.py:97-112), one warp per agent, 64 candidates at a time: the 64 x 64 diagonal block decides which
-//    of them survive (serial over bits, all in registers / shared memory), then the rows of the survivors are OR-ed into the
-//    removed set in parallel -- two dependent global-memory rounds per 64 candidates instead of one per kept box.
+// 3. greedy scan (postprocess.py:97-112), one CTA per agent, 64 candidates (one chunk) at a time.  The sequential part must never
+//    wait on global memory: warps 1-7 copy the 64 rows of chunk c + 1 into the other half of a shared-memory double buffer while
+//    warp 0 resolves chunk c -- the 64 x 64 diagonal block decides which of its boxes survive (a register chain of test + OR whose
+//    shared-memory loads do not depend on the chain, so they pipeline), then the survivors' rows are OR-ed into the removed set,
+//    lane = word.  The kept list is written afterwards by all threads from the per-chunk survivor masks.
+//    (Round 2, first version: one warp, rows read from global memory with one dependent ~600-cycle load per kept box: 180 us per
+//    80 agents of ~700 candidates, the largest agent -- 2048 candidates -- setting the time.)
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ s_count,
-                                                      const int* __restrict__ s_slot, int kmax, int words, int* __restrict__ keep,
-                                                      int* __restrict__ n_keep) {
-    extern __shared__ unsigned long long removed[];     // [words] removed set, then [64] diagonal rows
-    unsigned long long* diag = removed + words;
-    const int a = blockIdx.x, lane = threadIdx.x;
+constexpr int kScanThreads = 256;
+
+__global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ s_count,
+                                                                const int* __restrict__ s_slot, int kmax, int words,
+                                                                int* __restrict__ keep, int* __restrict__ n_keep) {
+    extern __shared__ unsigned long long scan_smem[];    // [2][64][words] row buffers, [words] survivor masks, [words + 1] prefix counts
+    unsigned long long* kept_s = scan_smem + 2 * 64 * words;
+    int* prefix = reinterpret_cast<int*>(kept_s + words);
+    const int a = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int K = s_count[a];
     if (K > kmax) K = kmax;
-    const int kw = (K + 63) / 64;
-    for (int w = lane; w < kw; w += 32) removed[w] = 0ull;
-    __syncwarp();
+    const int kw = (K + 63) / 64;                        // <= 128 (kmax <= 8192)
+    const unsigned long long* grow = mask + (long long)a * kmax * words;
+    // rows of chunk c, words c .. kw-1 (the words left of the diagonal are never written by nms_mask_kernel, nor read here)
+    auto load_chunk = [&](int c, int t0, int nt) {
+        unsigned long long* buf = scan_smem + (c & 1) * 64 * words;
+        const int i0 = c * 64, cn = min(64, K - i0), nw = kw - c;
+        for (int idx = t0; idx < cn * nw; idx += nt) {
+            const int r = idx / nw, w = c + idx - r * nw;
+            buf[r * words + w] = grow[(long long)(i0 + r) * words + w];
+        }
+    };
+    if (kw > 0) load_chunk(0, tid, kScanThreads);
+    __syncthreads();
+    unsigned long long rem[4] = {0ull, 0ull, 0ull, 0ull};   // warp 0, lane l: removed bits of words l, l + 32, l + 64, l + 96
     int nk = 0;
     for (int c = 0; c < kw; ++c) {
-        const int i0 = c * 64, cn = min(64, K - i0);
-        // diagonal block: row i0 + r, word c (bits j > i inside the chunk)
-        for (int r = lane; r < 64; r += 32) diag[r] = (r < cn) ? mask[((long long)a * kmax + i0 + r) * words + c] : 0ull;
-        __syncwarp();
-        unsigned long long rem = removed[c], kept = 0ull;
-        for (int r = 0; r < cn; ++r) {             // warp-uniform serial pass over the chunk
-            if (!((rem >> r) & 1ull)) { kept |= 1ull << r; rem |= diag[r]; }
-        }
-        // record the survivors in pick order ...
-        {
-            const int nsurv = __popcll(kept);
-            for (int q = lane; q < nsurv; q += 32) {       // lane q takes the q-th set bit of `kept`
-                unsigned long long m = kept;
-                for (int z = 0; z < q; ++z) m &= m - 1;
-                const int r = __ffsll((long long)m) - 1;
-                keep[(long long)a * kmax + nk + q] = s_slot[(long long)a * kmax + i0 + r];
+        if (warp > 0) {
+            if (c + 1 < kw) load_chunk(c + 1, tid - 32, kScanThreads - 32);
+        } else {
+            const unsigned long long* buf = scan_smem + (c & 1) * 64 * words;
+            const int cn = min(64, K - c * 64);
+            unsigned long long mine = rem[0];
+#pragma unroll
+            for (int k = 1; k < 4; ++k) mine = ((c >> 5) == k) ? rem[k] : mine;
+            unsigned long long remc = __shfl_sync(0xffffffffu, mine, c & 31), kept = 0ull;
+            const unsigned long long* dr = buf + c;      // diagonal word of row r: dr[r * words]
+#pragma unroll 8
+            for (int r = 0; r < cn; ++r) {               // every lane runs the same chain (no shuffles inside)
+                const unsigned long long d = dr[r * words];
+                const bool alive = !((remc >> r) & 1ull);
+                kept |= alive ? (1ull << r) : 0ull;
+                remc |= alive ? d : 0ull;
             }
-            nk += nsurv;
-        }
-        // ... and fold their rows into the removed set of the later chunks: lane = word, independent loads over the survivors
-        for (int w = c + 1 + lane; w < kw; w += 32) {
-            unsigned long long acc = removed[w], m = kept;
-            while (m) {
-                const int r = __ffsll((long long)m) - 1;
-                m &= m - 1;
-                acc |= __ldg(mask + ((long long)a * kmax + i0 + r) * words + w);
+            if (lane == 0) { kept_s[c] = kept; prefix[c] = nk; }
+            nk += __popcll(kept);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {                // fold the survivors' rows into the later words (lane + 32 k = word)
+                const int w = lane + 32 * k;
+                if (w > c && w < kw) {
+                    unsigned long long m = kept, acc = 0ull;
+                    while (m) {
+                        const int r = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        acc |= buf[r * words + w];
+                    }
+                    rem[k] |= acc;
+                }
             }
-            removed[w] = acc;
         }
-        __syncwarp();
+        __syncthreads();
     }
-    if (lane == 0) n_keep[a] = nk;
+    if (tid == 0) n_keep[a] = nk;
+    // kept list in pick order: candidate i is the (prefix[chunk] + rank inside the chunk)-th survivor
+    for (int i = tid; i < K; i += kScanThreads) {
+        const unsigned long long kc = kept_s[i >> 6];
+        if ((kc >> (i & 63)) & 1ull) {
+            const int pos = prefix[i >> 6] + __popcll(kc & ((1ull << (i & 63)) - 1ull));
+            keep[(long long)a * kmax + pos] = s_slot[(long long)a * kmax + i];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -419,7 +457,15 @@ int disco_nms_rotated_launch(const void* corners, int corners_f64, const float* 
     dim3 grid(kMaskBlocks, n);
     nms_mask_kernel<<<grid, 64, 0, s>>>(s_corners, s_count, kmax, words, iou_thresh, mask);
     DISCO_CHECK_CUDA(cudaGetLastError());
-    nms_scan_kernel<<<n, 32, (size_t)(words + 64) * 8, s>>>(mask, s_count, s_slot, kmax, words, keep, n_keep);
+    {
+        static bool scan_attr[64] = {false};
+        if (dev < 64 && !scan_attr[dev]) {
+            DISCO_CHECK_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            scan_attr[dev] = true;
+        }
+        const size_t scan_smem_bytes = (size_t)(2 * 64 + 1) * words * 8 + (size_t)(words + 1) * 4;   // <= 133 KB at kmax = 8192
+        nms_scan_kernel<<<n, kScanThreads, scan_smem_bytes, s>>>(mask, s_count, s_slot, kmax, words, keep, n_keep);
+    }
     DISCO_CHECK_CUDA(cudaGetLastError());
     if (n_valid) DISCO_CHECK_CUDA(cudaMemcpyAsync(n_valid, s_count, sizeof(int) * n, cudaMemcpyDeviceToDevice, s));
     return DISCO_OK;
