@@ -114,6 +114,11 @@ class ConvCall:
             d.subpix = 2
         self.desc = d
         self.flops = fpp * n * d.h_out * d.w_out // (4 if plan.subpix is not None else 1)
+        # multiply-accumulates the tensor cores execute per split pass (sub-pixel forms run 4 instead of 9 taps on the upsampled source)
+        self.mma_flops = self.flops
+        if plan.fused_subpix or plan.subpix is not None:
+            c0, c1 = srcs[0].shape[-1], srcs[1].shape[-1]
+            self.mma_flops = int(self.flops * (4.0 / 9.0 * c0 + c1) / (c0 + c1))
         self.set_output(out, out_split)
         self._fn = load().disco_conv_forward
         self._ref = load().disco_conv_reference
