@@ -271,8 +271,10 @@ __device__ __forceinline__ Item decode_item(const ConvGeom& g, int item) {
 //         sit side by side in TMEM and share every staged operand: a source-0 stage is the 18 x 10 low-res patch (4 pre-summed
 //         taps per class = 16 MMA pairs instead of 4 tiles x 9 taps = 36), a source-1 stage the two column-parity planes of the
 //         34 x 18 full-resolution window (class (py, px), tap (kh, kw) reads plane (px + kw) & 1 at row py + kh, column
-//         (px + kw) >> 1: 36 pairs, staged once instead of once per class).  Weights are streamed in slots of nine blocks:
-//         source 0 [channel block][low-res tap row ty][class][tx] (+ one pad block), source 1 [channel block][3 x 3 tap].
+//         (px + kw) >> 1: 36 pairs, staged once instead of once per class).  Weights are streamed in slots of nine units
+//         (unit = [W_hi | W_lo] rows of one tap): source 0 [channel block][low-res tap row ty][py][chunk][(px, tx)] (+ one pad
+//         unit), source 1 [channel block][kh][chunk][kw = 2, 1, 0] -- chunk-major inside a group, so two neighbouring units form
+//         ONE B operand of twice the rows (the px-merged MMAs of the issuer).
 template <int MODE, int KSTEPS, int PASSES>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvGeom g) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -901,6 +903,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         {
             const uint32_t idesc = umma_idesc_f16(d.precision == DISCO_PREC_BF16X3, 128, d.block_n);
             const uint32_t idesc2 = umma_idesc_f16(1, 128, 2 * d.block_n);   // STACKED: [W_hi; W_lo]
+            const uint32_t idesc4 = (MODE == 4) ? umma_idesc_f16(1, 128, 4 * d.block_n) : 0u;   // two classes' stacked units
+            const uint32_t idesc3 = (MODE == 4) ? umma_idesc_f16(1, 128, 3 * d.block_n) : 0u;   // their lo pass: [W_hi; W_lo; W_hi]
+            (void)idesc4; (void)idesc3;
             // descriptor halves (see umma_desc_kmajor_noswizzle): lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version
             const uint32_t lbo_b16 = (uint32_t)d.block_n * (STACKED ? 2u : 1u);   // rows per chunk * 16 B, >> 4
             const uint32_t a_hi = ((uint32_t)g.sbo_a >> 4) | (1u << 14);
@@ -975,32 +980,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         //      each, so one issuer loses every wait; two issuers hide each other's waits until the shared-memory
                         //      operand port, 44 cycles per MMA of this mix, is the limit.)  Weight slots hold nine blocks of
                         //      64 * block_n bytes and are read by both issuers. ----
+                        //      px-merged MMAs: the classes (py, 0) and (py, 1) read the SAME A window for neighbouring taps (class px = 0 with
+                        //      tap column t + 1 and class px = 1 with tap column t), and their accumulators are adjacent in TMEM, so
+                        //      one N = 4 * block_n instruction with the two classes' weight units stacked -- the units of a group are
+                        //      laid out so that the pair is contiguous -- replaces two N = 2 * block_n ones (lo pass: N = 3 * block_n,
+                        //      whose middle block adds the exact A_lo * W_lo term to one class).  Operand-port bytes per item -19 %.
                         const bool s1 = cb >= g.ncb0;
-                        const uint32_t blk16 = 4u * (uint32_t)d.block_n;
-                        const uint32_t accs = (uint32_t)g.acc_stride;
+                        const uint32_t n2 = 2u * (uint32_t)d.block_n;            // rows of one weight unit [W_hi | W_lo] = its size in 16-byte units
+                        const uint32_t accs = (uint32_t)g.acc_stride;            // == n2 (checked on the host): class accumulators are contiguous
                         const uint32_t py = (uint32_t)mw;
                         const uint32_t tdp = td0 + 2u * py * accs;
+                        const uint32_t bs = (b_base >> 4) + (uint32_t)sb_slot * b_stage16;
                         if (!s1) {
                             const uint32_t ahi = (160u >> 4) | (1u << 14);
                             const uint32_t part16 = (uint32_t)g.a_part0 >> 4;
                             const uint32_t sa0 = (a_base >> 4) + (uint32_t)slot0 * a_stage16 + (((uint32_t)g.plane0 >> 4) << 16) + py * 10u;
 #pragma unroll
-                            for (int ty = 0; ty < 2; ++ty) {      // slot = low-res tap row ty of the four classes: [class][tx] (+ pad block)
+                            for (int ty = 0; ty < 2; ++ty) {      // slot = low-res tap row ty: [py][chunk][(px0,tx0) (px0,tx1) (px1,tx0) (px1,tx1)] (+ pad)
                                 mbar_wait(bar_b_full + 8u * sb_slot, sb_phase);
                                 tc_fence_after();
-                                const uint32_t b16 = b_base16 + (uint32_t)sb_slot * b_stage16 + 4u * py * blk16;
+                                const uint32_t bg = (b_base >> 4) + (uint32_t)sb_slot * b_stage16 + py * 8u * n2 + ((4u * n2) << 16);
                                 if (elect_one()) {
-                                    if (!(g.dbg & 8))
-#pragma unroll
-                                    for (int px = 0; px < 2; ++px) {
-                                        const uint32_t td = tdp + (uint32_t)px * accs;
-#pragma unroll
-                                        for (int tx = 0; tx < 2; ++tx) {
-                                            const uint32_t a16 = sa0 + (uint32_t)(ty * 10 + px + tx);
-                                            const uint32_t blo = b16 + (uint32_t)(px * 2 + tx) * blk16;
-                                            umma_f16_parts(td, a16, ahi, blo, b_hi, idesc2, (ty == 0 && tx == 0) ? first : 1u);
-                                            umma_f16_parts(td, a16 + part16, ahi, blo, b_hi, idesc, 1u);
-                                        }
+                                    if (!(g.dbg & 8)) {
+                                        const uint32_t a16 = sa0 + (uint32_t)(ty * 10);
+                                        const uint32_t f = (ty == 0) ? first : 1u;
+                                        umma_f16_parts(tdp, a16, ahi, bg, b_hi, idesc2, f);                         // column 0: class px = 0
+                                        umma_f16_parts(tdp, a16 + part16, ahi, bg, b_hi, idesc, 1u);
+                                        umma_f16_parts(tdp + accs, a16 + 2u, ahi, bg + 3u * n2, b_hi, idesc2, f);   // column 2: class px = 1
+                                        umma_f16_parts(tdp + accs, a16 + 2u + part16, ahi, bg + 3u * n2, b_hi, idesc, 1u);
+                                        umma_f16_parts(tdp, a16 + 1u, ahi, bg + n2, b_hi, idesc4, 1u);              // column 1: both classes
+                                        umma_f16_parts(tdp, a16 + 1u + part16, ahi, bg + n2, b_hi, idesc3, 1u);
                                     }
                                     umma_commit(bar_b_empty + 8u * sb_slot);
                                 }
@@ -1008,26 +1017,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                                 if (++sb_slot == g.SB) { sb_slot = 0; sb_phase ^= 1u; }
                             }
                         } else {
-                            mbar_wait(bar_b_full + 8u * sb_slot, sb_phase);      // slot = the nine taps of this channel block
+                            mbar_wait(bar_b_full + 8u * sb_slot, sb_phase);      // slot = [kh][chunk][kw = 2, 1, 0] of this channel block
                             tc_fence_after();
-                            const uint32_t b16 = b_base16 + (uint32_t)sb_slot * b_stage16;
                             const uint32_t a0p = a0_16 + py * 9u;
                             if (elect_one()) {
                                 if (!(g.dbg & 8))
 #pragma unroll
                                 for (int kh = 0; kh < 3; ++kh) {
-#pragma unroll
-                                    for (int kw = 0; kw < 3; ++kw) {
-                                        const uint32_t blo = b16 + (uint32_t)(kh * 3 + kw) * blk16;
-#pragma unroll
-                                        for (int px = 0; px < 2; ++px) {
-                                            const int c = px + kw;
-                                            const uint32_t a16 = a0p + (uint32_t)(c & 1) * par16 + (uint32_t)(kh * 9 + (c >> 1));
-                                            const uint32_t td = tdp + (uint32_t)px * accs;
-                                            umma_f16_parts(td, a16, a_hi, blo, b_hi, idesc2, 1u);   // source-0 stages come first: accumulate
-                                            umma_f16_parts(td, a16 + a_part16, a_hi, blo, b_hi, idesc, 1u);
-                                        }
-                                    }
+                                    const uint32_t bg = bs + (uint32_t)kh * 6u * n2 + ((3u * n2) << 16);
+                                    const uint32_t ar = a0p + (uint32_t)(kh * 9);
+                                    // window column c = px + kw: plane c & 1, column index c >> 1
+                                    umma_f16_parts(tdp, ar, a_hi, bg + 2u * n2, b_hi, idesc2, 1u);                              // c = 0: px 0, kw 0
+                                    umma_f16_parts(tdp, ar + a_part16, a_hi, bg + 2u * n2, b_hi, idesc, 1u);
+                                    umma_f16_parts(tdp + accs, ar + par16 + 1u, a_hi, bg, b_hi, idesc2, 1u);                    // c = 3: px 1, kw 2
+                                    umma_f16_parts(tdp + accs, ar + par16 + 1u + a_part16, a_hi, bg, b_hi, idesc, 1u);
+                                    umma_f16_parts(tdp, ar + par16, a_hi, bg + n2, b_hi, idesc4, 1u);                           // c = 1: [W(kh,1); W(kh,0)]
+                                    umma_f16_parts(tdp, ar + par16 + a_part16, a_hi, bg + n2, b_hi, idesc3, 1u);
+                                    umma_f16_parts(tdp, ar + 1u, a_hi, bg, b_hi, idesc4, 1u);                                   // c = 2: [W(kh,2); W(kh,1)]
+                                    umma_f16_parts(tdp, ar + 1u + a_part16, a_hi, bg, b_hi, idesc3, 1u);
                                 }
                                 umma_commit(bar_b_empty + 8u * sb_slot);
                             }
@@ -1434,7 +1441,10 @@ int build_geom(const disco_conv_desc* d, ConvGeom* g) {
         g->nmma = 2;
         g->SA &= ~1;   // even ring: slot parity == sub-tile, i.e. one consumer per slot
     }
-    if (fused) { g->nmma = 2; g->nrings = 1; g->by_sub = 0; }   // two issuers, one per output-row parity, sharing every stage
+    if (fused) {
+        g->nmma = 2; g->nrings = 1; g->by_sub = 0;
+        DISCO_REQUIRE(g->acc_stride == 2 * d->block_n, "conv: fused sub-pixel accumulators must be contiguous (stride %d, block_n %d)", g->acc_stride, d->block_n);
+    }   // two issuers, one per output-row parity, sharing every stage
     g->SAr = g->SA / g->nrings;
     g->nprod = kProdWarps / g->nrings;
     if (g->nprod > g->SAr) g->nprod = g->SAr;

@@ -192,9 +192,11 @@ def pack_conv_subpix_fused(wf: torch.Tensor, bf: torch.Tensor, *, src_channels, 
     """Weights of the FUSED sub-pixel form (conv.h subpix == 2; C_out <= 64): one work item computes the four output-parity
     classes of a 16 x 8 low-res tile.  The image is a stream of slots of nine blocks (block = [chunk 2][hi rows | lo rows][8 ch],
     64 * block_n bytes), in the order the MMA issuers consume them:
-      source-0 channel block:  two slots, one per low-res tap row ty: [class 2*py + px][tx] pre-summed taps + one zero block
+      source-0 channel block:  two slots, one per low-res tap row ty: [py][chunk][(px, tx) = (0,0) (0,1) (1,0) (1,1)] + one zero unit
                                (class (py, px), tap (ty, tx) multiplies the low-res pixel at window row py + ty, column px + tx)
-      source-1 channel block:  one slot = the nine 3 x 3 taps (shared by the four classes)"""
+      source-1 channel block:  one slot [kh][chunk][kw = 2, 1, 0] (shared by the four classes)
+    A unit is the [W_hi | W_lo] rows (2 * block_n x 8 channels) of one tap; inside a group the units are chunk-major, so two
+    neighbouring units are ONE UMMA B operand of 4 * block_n rows: the kernel's px-merged MMAs (conv_tc.cu MODE 4)."""
     assert precision == PREC_BF16X3 and wf.shape[2:] == (3, 3) and len(src_channels) == 2
     c_out, c_in_real = wf.shape[0], wf.shape[1]
     c0, c1 = int(src_channels[0]), int(src_channels[1])
@@ -222,10 +224,14 @@ def pack_conv_subpix_fused(wf: torch.Tensor, bf: torch.Tensor, *, src_channels, 
                     w0[:, :, _SUBPIX_MAP[py][kh], _SUBPIX_MAP[px][kw]] += w[:, :c0, kh, kw]
             cls_w.append(blocks_of(w0[:, :, py:py + 2, px:px + 2].contiguous()))            # [cb, 4, ...]
     s0 = torch.stack(cls_w, dim=1)                                                          # [cb0, class, 4 taps (ty, tx), chunk, part, n, 8]
-    s0 = s0.view(s0.shape[0], 4, 2, 2, *s0.shape[3:]).permute(0, 2, 1, 3, 4, 5, 6, 7).contiguous()   # [cb0, ty, class, tx, ...]
-    s0 = s0.view(s0.shape[0], 2, 8, *s0.shape[4:])
-    s0 = torch.cat((s0, torch.zeros_like(s0[:, :, :1])), dim=2)                             # [cb0, ty, 8 blocks + pad, ...]
-    s1 = blocks_of(w[:, c0:].contiguous())                                                  # [cb1, 9 taps, ...]
+    cb0 = s0.shape[0]
+    s0 = s0.view(cb0, 2, 2, 2, 2, 2, 2, block_n, 8)                                         # [cb0, py, px, ty, tx, chunk, part, n, 8]
+    s0 = s0.permute(0, 3, 1, 5, 2, 4, 6, 7, 8).contiguous()                                 # [cb0, ty, py, chunk, px, tx, part, n, 8]
+    s0 = s0.view(cb0, 2, -1)
+    s0 = torch.cat((s0, torch.zeros(cb0, 2, 2 * 2 * block_n * 8, dtype=s0.dtype, device=dev)), dim=2)   # + one pad unit per slot
+    s1 = blocks_of(w[:, c0:].contiguous())                                                  # [cb1, 9 taps, chunk, part, n, 8]
+    cb1 = s1.shape[0]
+    s1 = s1.view(cb1, 3, 3, 2, 2, block_n, 8).flip(2).permute(0, 1, 3, 2, 4, 5, 6).contiguous()   # [cb1, kh, chunk, kw = 2,1,0, part, n, 8]
     wpack = torch.cat((s0.reshape(-1), s1.reshape(-1))).view(torch.int16)
     return ConvPlan(taps=9, stride=1, c_in=c_in_real, c_out=c_out, c_blk=16, block_n=block_n, relu=relu, precision=precision,
                     wpack=wpack.reshape(-1), bias=bias, wref=None, name=name + "[subpix x4]", stacked=True,
