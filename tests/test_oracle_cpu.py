@@ -390,3 +390,67 @@ def test_seg_oracle_training_matches_reference_golden():
     assert cos >= 0.999, cos
     bsub, _ = grad_digest({k: v.float() for k, v in bufs.items()}, stride=7)
     assert np.abs(bsub - rec["buf_sub"]).max() <= 5e-4 * np.abs(rec["buf_sub"]).max()
+
+
+def test_fused_subpix_weight_stream_reproduces_the_conv():
+    """plan.pack_conv_subpix_fused: walk the packed slot stream exactly the way conv_tc.cu MODE 4 addresses it (two issuers py, the
+    px-merged B operands of 4 * block_n rows, unit order inside the chunk-major groups) and check that the four class accumulators
+    add up to conv(cat(nearest_up2(a), b)) (Backbone.py:214-216,233-235)."""
+    import torch.nn.functional as F
+    from disconet_b200.plan import pack_conv_subpix_fused
+    g = torch.Generator().manual_seed(11)
+    c0, c1, c_out, H, W = 32, 16, 24, 8, 12                # c_out padded to block_n = 32
+    bf = lambda t: t.to(torch.bfloat16).float()            # activations exact in bf16: the A_lo pass contributes nothing
+    a = bf(torch.randn(1, c0, H // 2, W // 2, generator=g))
+    b = bf(torch.randn(1, c1, H, W, generator=g))
+    w = torch.randn(c_out, c0 + c1, 3, 3, generator=g) / 10
+    bias = torch.randn(c_out, generator=g)
+    plan = pack_conv_subpix_fused(w, bias, src_channels=[c0, c1])
+    n = plan.block_n
+    assert n == 32 and plan.stacked and plan.fused_subpix and plan.c_blk == 16
+    unit = 2 * 2 * n * 8                                   # elements of one unit [chunk 2][part 2][n][8]
+    stream = plan.wpack.view(torch.bfloat16).float().view(-1, 9 * unit)          # slots of nine units
+    ncb0, ncb1 = c0 // 16, c1 // 16
+    assert stream.shape[0] == 2 * ncb0 + ncb1
+
+    def operand(group, units_in_group, u0, rows):
+        """B operand that starts at unit u0 of a chunk-major group and spans `rows` 8-channel rows -> [rows, 16 channels]."""
+        gr = group.view(2, units_in_group * 2 * n, 8)      # [chunk][(unit, part, n) rows][8 ch]
+        return torch.cat((gr[0, u0 * 2 * n: u0 * 2 * n + rows], gr[1, u0 * 2 * n: u0 * 2 * n + rows]), dim=1)
+
+    ap = F.pad(a, (1, 1, 1, 1))                            # low-res window origin (a0 - 1, b0 - 1)
+    bp = F.pad(b, (1, 2, 1, 2))                            # full-res window origin (2 a0 - 1, 2 b0 - 1), 34 x 18 per tile
+    hl, wl = H // 2, W // 2
+    acc = torch.zeros(2, 2, hl, wl, 2 * n)                 # [py][px][a][b][hh | hl columns]
+    slot = 0
+    for cb in range(ncb0):
+        A = ap[0, cb * 16:(cb + 1) * 16]                   # [16, hl + 2, wl + 2]
+        for ty in range(2):
+            s = stream[slot]; slot += 1
+            assert s[8 * unit:].abs().max() == 0           # pad unit
+            for py in range(2):
+                grp = s[py * 4 * unit:(py + 1) * 4 * unit]
+                win = lambda c: A[:, py + ty: py + ty + hl, c: c + wl].permute(1, 2, 0)      # A rows of window column c
+                acc[py, 0] += win(0) @ operand(grp, 4, 0, 2 * n).T                            # class px = 0, tx = 0
+                acc[py, 1] += win(2) @ operand(grp, 4, 3, 2 * n).T                            # class px = 1, tx = 1
+                both = win(1) @ operand(grp, 4, 1, 4 * n).T                                   # px-merged: (px 0, tx 1) | (px 1, tx 0)
+                acc[py, 0] += both[..., :2 * n]; acc[py, 1] += both[..., 2 * n:]
+    for cb in range(ncb1):
+        Bw = bp[0, cb * 16:(cb + 1) * 16]
+        s = stream[slot]; slot += 1
+        for py in range(2):
+            for kh in range(3):
+                grp = s[kh * 3 * unit:(kh + 1) * 3 * unit]
+                win = lambda c: Bw[:, py + kh: py + kh + 2 * hl: 2, c: c + 2 * wl: 2].permute(1, 2, 0)   # window column c = px + kw
+                acc[py, 0] += win(0) @ operand(grp, 3, 2, 2 * n).T                            # px 0, kw 0
+                acc[py, 1] += win(3) @ operand(grp, 3, 0, 2 * n).T                            # px 1, kw 2
+                m1 = win(1) @ operand(grp, 3, 1, 4 * n).T                                     # [W(kh,1); W(kh,0)]
+                m2 = win(2) @ operand(grp, 3, 0, 4 * n).T                                     # [W(kh,2); W(kh,1)]
+                acc[py, 0] += m1[..., :2 * n] + m2[..., :2 * n]; acc[py, 1] += m1[..., 2 * n:] + m2[..., 2 * n:]
+    out = torch.zeros(H, W, n)
+    for py in range(2):
+        for px in range(2):
+            out[py::2, px::2] = acc[py, px][..., :n] + acc[py, px][..., n:] + plan.bias       # epilogue: hh + hl columns + bias
+    ref = F.conv2d(torch.cat((F.interpolate(a, scale_factor=2), b), 1), w, bias, padding=1)[0].permute(1, 2, 0)
+    assert (out[..., :c_out] - ref).abs().max() < 2e-4 * ref.abs().max()
+    assert out[..., c_out:].abs().max() == 0
