@@ -269,9 +269,10 @@ __device__ __forceinline__ Item decode_item(const ConvGeom& g, int item) {
 // MODE 4: ALL FOUR output-parity classes of such a conv in one item ("fused sub-pixel", d.subpix == 2): an item is a 16 x 8 tile of
 //         LOW-RES positions (a, b) = 512 output pixels; the four class accumulators (class 2*py + px -> output (2a + py, 2b + px))
 //         sit side by side in TMEM and share every staged operand: a source-0 stage is the 18 x 10 low-res patch (4 pre-summed
-//         taps per class = 16 MMA pairs instead of 4 tiles x 9 taps = 36), a source-1 stage the two column-parity planes of the
-//         34 x 18 full-resolution window (class (py, px), tap (kh, kw) reads plane (px + kw) & 1 at row py + kh, column
-//         (px + kw) >> 1: 36 pairs, staged once instead of once per class).  Weights are streamed in slots of nine units
+//         taps per class = 16 class-taps, issued as 12 MMA pairs, instead of 4 tiles x 9 taps = 36), a source-1 stage the two
+//         column-parity planes of the 34 x 18 full-resolution window (class (py, px), tap (kh, kw) reads plane (px + kw) & 1 at
+//         row py + kh, column (px + kw) >> 1: 36 class-taps issued as 24 pairs, the window staged once instead of once per
+//         class).  Weights are streamed in slots of nine units
 //         (unit = [W_hi | W_lo] rows of one tap): source 0 [channel block][low-res tap row ty][py][chunk][(px, tx)] (+ one pad
 //         unit), source 1 [channel block][kh][chunk][kw = 2, 1, 0] -- chunk-major inside a group, so two neighbouring units form
 //         ONE B operand of twice the rows (the px-merged MMAs of the issuer).
