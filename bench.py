@@ -103,20 +103,43 @@ class ClockSampler:
                 "samples": len(use), "samples_in_timed_region": len(inside), "reasons": reasons}
 
 
-def best_cpu_threads(sd, bev, T, na) -> int:
+def cpu_reference_runner(sd):
+    """The reference's CPU implementation of the path as a callable (bev, T, na, batch) -> outputs, and what it is:
+    kind "reference" = the reference's OWN `coperception.models.det.DiscoNet` class, unmodified, from the staged copy under
+    oracle/_ref (git-ignored, travels to the GPU box; oracle/stage_ref.py); kind "port" = the oracle restatement of it
+    (oracle/disconet_oracle.py, pinned to the reference by tests/golden) when no staged copy is present."""
+    from oracle import ref_import
+    if ref_import.available():
+        try:
+            RDisco, _, _, Config = ref_import.reference_classes()
+            ref = RDisco(Config("train", binary=True, only_det=True), layer=3, kd_flag=0, num_agent=AGENTS)
+            ref.load_state_dict(sd)
+            ref = ref.eval()
+
+            def run_ref(bev, T, na, b):
+                with torch.no_grad():
+                    return ref(bev, T, na, batch_size=b)
+            return run_ref, "reference", "coperception.models.det.DiscoNet (unmodified reference class, staged copy), torch CPU"
+        except Exception as e:      # an import problem of the staged tree must not cost the baseline
+            print(f"[bench] staged reference unusable ({type(e).__name__}: {e}); using the oracle port", file=sys.stderr)
+    from oracle import disconet_oracle as O
+    return (lambda bev, T, na, b: O.disconet_forward(sd, bev, T, na, b, agent_num=AGENTS)), "port", \
+        "oracle port of the reference PyTorch CPU path"
+
+
+def best_cpu_threads(run, bev, T, na) -> int:
     """torch's CPU convs scale badly past a few dozen threads on these small per-agent problems (128
     threads measured 20x slower than 16 on the B200 host), so the baseline uses the thread count that
     maximises throughput: a fair "all the threads it can use" figure.  ~1 scene per candidate."""
-    from oracle import disconet_oracle as O
     ncpu = os.cpu_count() or 1
     cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
     best, best_t = cands[0], float("inf")
     torch.set_num_threads(cands[0])
-    O.disconet_forward(sd, bev, T, na, 1, agent_num=AGENTS)   # warm-up
+    run(bev, T, na, 1)   # warm-up
     for c in cands:
         torch.set_num_threads(c)
         t0 = time.perf_counter()
-        O.disconet_forward(sd, bev, T, na, 1, agent_num=AGENTS)
+        run(bev, T, na, 1)
         dt = time.perf_counter() - t0
         if dt < best_t:
             best, best_t = c, dt
@@ -126,22 +149,24 @@ def best_cpu_threads(sd, bev, T, na) -> int:
 
 
 def cpu_oracle_rate(seconds_budget: float, threads: int, scenes_per_call: int = 1):
-    """Oracle port (reference's torch CPU ops) on the host cores: scenes/s over a bounded sample."""
+    """The reference's CPU path (its own class from the staged copy, else the oracle port) on the host cores: scenes/s over a
+    bounded sample.  Returns (scenes/s, scenes, seconds, threads, kind, impl description)."""
     from oracle import disconet_oracle as O
     from disconet_b200 import DiscoNet
     sd = O.synth_state_dict(DiscoNet(Cfg(), kd_flag=0, num_agent=AGENTS).state_dict(), seed=0)
+    run, kind, impl = cpu_reference_runner(sd)
     bev, T, na = synth_inputs(scenes_per_call, seed=100)
-    threads = best_cpu_threads(sd, bev, T, na)
+    threads = best_cpu_threads(run, bev, T, na)
     torch.set_num_threads(threads)
-    O.disconet_forward(sd, bev, T, na, scenes_per_call, agent_num=AGENTS)   # warm-up
+    run(bev, T, na, scenes_per_call)   # warm-up
     n, t0 = 0, time.perf_counter()
     while True:
-        O.disconet_forward(sd, bev, T, na, scenes_per_call, agent_num=AGENTS)
+        run(bev, T, na, scenes_per_call)
         n += scenes_per_call
         dt = time.perf_counter() - t0
         if dt >= seconds_budget or n >= 64:
             break
-    return n / dt, n, dt, threads
+    return n / dt, n, dt, threads, kind, impl
 
 
 def cpu_oracle_train_ms(threads: int):
@@ -383,23 +408,24 @@ def torch_gpu_baseline(dev, model, B):
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port; the Python
-    reference cannot travel to the GPU box), all host threads, one scene per step."""
+    """--impl reference: the reference's own CPU implementation of the path -- its unmodified model class from the staged
+    copy under oracle/_ref (which travels to the GPU box), else the oracle port -- all host threads, one scene per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import disconet_oracle as O
     from disconet_b200 import DiscoNet
     sd = O.synth_state_dict(DiscoNet(Cfg(), kd_flag=0, num_agent=AGENTS).state_dict(), seed=0)
+    run, kind, impl = cpu_reference_runner(sd)
     bev, T, na = synth_inputs(1, seed=100)
-    threads = best_cpu_threads(sd, bev, T, na)
+    threads = best_cpu_threads(run, bev, T, na)
     torch.set_num_threads(threads)
     for _ in range(max(1, min(args.warmup, 2))):
-        O.disconet_forward(sd, bev, T, na, 1, agent_num=AGENTS)
+        run(bev, T, na, 1)
     steps = args.steps
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.disconet_forward(sd, bev, T, na, 1, agent_num=AGENTS)
+        run(bev, T, na, 1)
     dt = time.perf_counter() - t0
     v = steps / dt
     line = {
@@ -407,8 +433,8 @@ def run_reference(args):
         "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "5-agent DiscoNet detection, 256x256x13 BEV (BASELINE configs[1])", "agents": AGENTS,
-                   "scenes_per_step": 1, "impl": "oracle port of the reference PyTorch CPU path (fp32, eval)"},
-        "cpu_baseline": {"value": v, "unit": "scenes/s", "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
+                   "scenes_per_step": 1, "impl": impl + " (fp32, eval)"},
+        "cpu_baseline": {"value": v, "unit": "scenes/s", "cores": threads, "kind": kind, "host_cpus": os.cpu_count(),
                          "sample": f"{steps} steps x 1 scene (A=5, 256x256x13), torch {torch.__version__} CPU"},
         "e2e": {"value": v, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -662,9 +688,9 @@ def main():
                 traffic = traffic * B
     cpu = None
     if not args.no_cpu_baseline:
-        v, n, dt, threads = cpu_oracle_rate(12.0, 0)
-        cpu = {"value": v, "unit": "scenes/s", "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
-               "sample": f"{n} scenes in {dt:.1f}s (A=5, 256x256x13, fp32 eval, oracle port of the reference torch CPU path)"}
+        v, n, dt, threads, kind, impl = cpu_oracle_rate(12.0, 0)
+        cpu = {"value": v, "unit": "scenes/s", "cores": threads, "kind": kind, "host_cpus": os.cpu_count(),
+               "sample": f"{n} scenes in {dt:.1f}s (A=5, 256x256x13, fp32 eval, {impl})"}
         if train is not None and "error" not in train:
             train["cpu_port_ms_per_scene"] = cpu_oracle_train_ms(threads)
     line = {
